@@ -1,0 +1,116 @@
+/* wrenc_b200.h — C ABI of the B200-native all-intra RD search (+ slice_data coder) for hjmkt/wrenc.
+ *
+ * Drop-in boundary.  The reference has no plugin/FFI interface; the narrowest seam is the raster CTU loop of
+ * SliceEncoder::encode (reference src/slice_encoder.rs:352-414), which for every CTU calls CtuEncoder::encode
+ * (src/ctu_encoder.rs:33-202) = BlockSplitter::split_ct (src/block_splitter.rs:782-1154, the RD search) followed by the
+ * syntax/CABAC writer (src/ctu_encoder.rs:227-2269).  A picture's slice_data() depends only on (Y,Cb,Cr, W, H, QP,
+ * max_split_depth, tuning constants), so this library replaces that loop picture by picture:
+ *
+ *   wrenc_b200_create   <->  BlockSplitter::new + Quantizer::new  (src/block_splitter.rs:20-62, src/quantizer.rs:15-26),
+ *                            Args --qp/--max-split-depth/--extra-params (src/main.rs:85-115,193-216)
+ *   wrenc_b200_submit   <->  Picture::new + plane read + init_ctus (src/main.rs:318-361, src/picture.rs:170-195)
+ *   wrenc_b200_receive  <->  SliceEncoder::encode's CTU loop result (src/slice_encoder.rs:352-419) and
+ *                            Picture::get_reconst_pixels (src/picture.rs:248, --reconst dump src/main.rs:391-401)
+ *   wrenc_b200_decisions<->  the decided CodingTree / TransformUnit.quantized_transformed_coeffs of every CTU
+ *                            (src/ctu.rs:324-367,1190-1330,1794-1960) in flat form — the phase-1 / parity view
+ *
+ * Rules: plain pointers and sizes only; every function returns 0 on success or a negative error code (message via
+ * wrenc_b200_last_error); nothing throws across the boundary; a handle is not thread-safe; output pointers are owned by the
+ * handle and stay valid until the next receive/flush/destroy on that handle; inputs are copied before submit returns.
+ * There is NO CPU fallback: create fails with WRENC_B200_ENODEV when no CUDA device is usable.
+ */
+#ifndef WRENC_B200_H
+#define WRENC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wrenc_b200 wrenc_b200;
+
+enum {
+    WRENC_B200_OK = 0,
+    WRENC_B200_EINVAL = -1,  /* bad argument / malformed extra_params (reference: main.rs:206-214 prints and exits) */
+    WRENC_B200_ENODEV = -2,  /* no CUDA device / not sm_100 capable */
+    WRENC_B200_ECUDA = -3,   /* CUDA runtime error */
+    WRENC_B200_EAGAIN = -4,  /* receive with nothing submitted */
+    WRENC_B200_EFULL = -5    /* submit while pictures_in_flight pictures are pending (call receive first) */
+};
+
+typedef struct {
+    int32_t width, height;        /* luma size; multiples of 32 (reference README.md:40) */
+    int32_t qp;                   /* slice QP == --qp (reference default 26 when absent) */
+    int32_t max_split_depth;      /* 0..3, --max-split-depth (default 3: CUs 32,16,8,4) */
+    int32_t device;               /* CUDA device ordinal (one handle per GPU; shard picture ranges across handles) */
+    int32_t pictures_in_flight;   /* pictures searched by one kernel launch (CTU wavefronts of all of them interleave) */
+    int32_t want_recon;           /* copy reconstructed planes back (--reconst) */
+    int32_t want_decisions;       /* copy per-CTU records + quantised levels back (parity / phase-1 consumers) */
+    const char *extra_params;     /* "k=v,k=v" or NULL: keys of reference --extra-params */
+} wrenc_b200_config;
+
+/* One record per CTU, raster order (88 bytes, little endian). */
+typedef struct {
+    uint32_t split_mask;     /* bit0: 32x32 split; bits1..4: 16x16 #i split (z-order); bits5..20: 8x8 #(4i+j) split */
+    uint8_t luma_mode[64];   /* intra luma mode of the CU covering each 4x4 block (8x8 raster grid) */
+    uint8_t chroma_mode[16]; /* chroma prediction mode used (luma-derived value or 81=LT_CCLM,82=L_CCLM,83=T_CCLM) per 8x8 */
+    float cost;              /* RD cost split_ct returned for the CTU root */
+} wrenc_b200_ctu_record;
+
+int wrenc_b200_create(const wrenc_b200_config *cfg, wrenc_b200 **out);
+void wrenc_b200_destroy(wrenc_b200 *h);
+const char *wrenc_b200_last_error(const wrenc_b200 *h); /* h may be NULL: error of the last failed create */
+
+/* Host planes, tightly packed I420 as main.rs:320-349 reads them. */
+int wrenc_b200_submit(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
+/* Strictly in submit order.  Launches the pending batch if it has not run yet, then blocks until the picture is ready.
+ * slice_data/len: CABAC-coded slice_data() bytes of the picture (byte aligned, ends with rbsp stop bit + alignment zeros).
+ * rec_*: reconstructed planes (NULL unless want_recon). Any out pointer may be NULL. */
+int wrenc_b200_receive(wrenc_b200 *h, uint64_t *pic_idx, const uint8_t **slice_data, size_t *len, const uint8_t **rec_y,
+                       const uint8_t **rec_cb, const uint8_t **rec_cr);
+/* Decisions of the picture returned by the LAST receive (want_decisions must be set): records[(H/32)*(W/32)], and the
+ * final quantised levels as int16 planes (luma W*H, chroma W/2*H/2), each TB stored at its own position. */
+int wrenc_b200_decisions(wrenc_b200 *h, const wrenc_b200_ctu_record **records, const int16_t **lev_y, const int16_t **lev_cb,
+                         const int16_t **lev_cr);
+/* Launch whatever is pending without waiting (receive does this implicitly). */
+int wrenc_b200_flush(wrenc_b200 *h);
+/* Number of pictures submitted and not yet received. */
+int wrenc_b200_pending(const wrenc_b200 *h);
+
+/* Device-resident entry (throughput path / bench "value"): n_pictures I420 pictures already in HBM, contiguous, each
+ * width*height*3/2 bytes; outputs written to device buffers of the same geometry (rec: u8, levels: i16 per sample),
+ * records: n_pictures*(H/32)*(W/32).  All pointers are DEVICE pointers on cfg.device; rec/levels/records may be NULL
+ * only if the handle was created for it... they are required.  Runs on `stream` (a cudaStream_t, or NULL for the
+ * handle's own stream) and does not synchronise.  Returns the number of search-kernel launches enqueued (>=1) or <0. */
+int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t *d_yuv, uint8_t *d_rec, int16_t *d_levels,
+                               wrenc_b200_ctu_record *d_records, void *stream);
+/* Workspace the resident entry needs for n_pictures (bytes of device memory it will allocate once and keep). */
+size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n_pictures);
+
+/* Constants the search derives on the host with libm (known-answer checks). */
+typedef struct {
+    int64_t lambda_q;
+    float lambda_rd, lambda_rd_chroma;
+    int32_t ls;
+    int64_t lv[8], dq[8];
+} wrenc_b200_consts;
+int wrenc_b200_get_consts(const wrenc_b200 *h, wrenc_b200_consts *out);
+
+/* Per-block entry points (host pointers): the block operations of the search, exposed for bit-exactness tests against
+ * IntraPredictor::predict (src/intra_predictor.rs:56-144), Transformer::transform / inverse_transform
+ * (src/transformer.rs:2040,2380), Quantizer::quantize / dequantize (src/quantizer.rs:519,761) and the rate walk of
+ * get_intra_pred_cost (src/block_splitter.rs:415-460).  Blocks are n x n int16, row-major, `count` of them back to back.
+ * predict: rec_i420 is a full width x height I420 reconstruction; (x,y,w) the luma TU; tree 0/1/2 = SINGLE/DUAL_LUMA/
+ * DUAL_CHROMA; ar/bl the tree-position availability flags (src/ctu.rs:2083-2188); c the component; mode 0..66 or 81..83. */
+int wrenc_b200_block_predict(wrenc_b200 *h, const uint8_t *rec_i420, int x, int y, int w, int tree, int ar, int bl, int c, int mode, uint8_t *pred);
+int wrenc_b200_block_fwd_dct(wrenc_b200 *h, const int16_t *res, int log2n, int count, int16_t *coef);
+int wrenc_b200_block_inv_dct(wrenc_b200 *h, const int16_t *deq, int log2n, int count, int16_t *out);
+int wrenc_b200_block_quantize(wrenc_b200 *h, const int16_t *coef, int log2n, int count, int16_t *levels, int32_t *rates);
+int wrenc_b200_block_dequantize(wrenc_b200 *h, const int16_t *levels, int log2n, int count, int16_t *out);
+
+const char *wrenc_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

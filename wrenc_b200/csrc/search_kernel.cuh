@@ -1,0 +1,888 @@
+// search_kernel.cuh — the all-intra RD search of one CTU per CTA, hand-written for sm_100a.
+//
+// What it computes (reference file:line, all under /root/reference/src):
+//   split_ct quad-tree RD decision 32->16->8->4 (+ local dual-tree chroma CT)      block_splitter.rs:782-1154
+//   leaf evaluation: 15 coarse modes, SAD step search, 3 RD evals, chroma DM vs CCLM  block_splitter.rs:886-1078, 794-885
+//   full evaluation (predict, fwd DCT, dep-quant trellis, dequant, inv DCT, recon, SSD, rate)  block_splitter.rs:110-474,524-780
+//   intra prediction incl. reference substitution/filter, PDPC, CCLM                intra_predictor.rs:56-2055
+//   DCT-II 4..32 by matrix multiply                                                 transformer.rs:2040-2378,2380-2737
+//   dependent quantisation (memoised DFS == Viterbi with first-visit flags, H2/H3)  quantizer.rs:338-759, dequantize 761-1079
+//   MPM derivation for the mode-bit estimate (H1: in-CTU neighbours see the root CU) ctu.rs:1498-1635
+//
+// Execution model: a persistent grid; each CTA (8 warps) pulls CTUs from a work list sorted in wavefront order
+// (key = x + 2y + stagger*picture), waits on the left and above-right CTU's done flags, stages the CTU's source and the
+// neighbouring reconstruction in shared memory, and runs the whole tree search there.  Inside a CTU the candidates of one
+// decision phase are independent tasks, one warp each; the decision itself is recomputed redundantly by every thread from
+// the task results in shared memory (uniform control flow, no broadcast needed).  All arithmetic is exact integer except the
+// RD cost, which is IEEE f32 with explicit _rn intrinsics (no FMA contraction) in the reference's operation order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "search_kernel_api.h"
+
+namespace wb {
+
+constexpr int NW = 8;        // warps per CTA
+constexpr int NTHREADS = NW * 32;
+constexpr int NBIG = 3;      // warps with scratch large enough for a 32x32 luma pipeline
+
+enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
+enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// constant tables
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ int8_t c_angle[67] = {0,   0,   32,  29,  26,  23,  20,  18,  16,  14,  12,  10,  8,   6,   4,   3,   2,
+                                   1,   0,   -1,  -2,  -3,  -4,  -6,  -8,  -10, -12, -14, -16, -18, -20, -23, -26, -29,
+                                   -32, -29, -26, -23, -20, -18, -16, -14, -12, -10, -8,  -6,  -4,  -3,  -2,  -1,  0,
+                                   1,   2,   3,   4,   6,   8,   10,  12,  14,  16,  18,  20,  23,  26,  29,  32};
+// VVC Table 25, fC (common.rs:153-186); fG is the closed form {16-(p>>1), 32-(p>>1), 16+(p>>1), p>>1}
+__constant__ int8_t c_fC[32][4] = {
+    {0, 64, 0, 0},    {-1, 63, 2, 0},   {-2, 62, 4, 0},   {-2, 60, 7, -1},  {-2, 58, 10, -2}, {-3, 57, 12, -2},
+    {-4, 56, 14, -2}, {-4, 55, 15, -2}, {-4, 54, 16, -2}, {-5, 53, 18, -2}, {-6, 52, 20, -2}, {-6, 49, 24, -3},
+    {-6, 46, 28, -4}, {-5, 44, 29, -4}, {-4, 42, 30, -4}, {-4, 39, 33, -4}, {-4, 36, 36, -4}, {-4, 33, 39, -4},
+    {-4, 30, 42, -4}, {-4, 29, 44, -5}, {-4, 28, 46, -6}, {-3, 24, 49, -6}, {-2, 20, 52, -6}, {-2, 18, 53, -5},
+    {-2, 16, 54, -4}, {-2, 15, 55, -4}, {-2, 14, 56, -4}, {-2, 12, 57, -3}, {-2, 10, 58, -2}, {-1, 7, 60, -2},
+    {0, 4, 62, -2},   {0, 2, 63, -1}};
+// DCT-II magnitudes c[j] = 32-point basis value at angle j*pi/64 (even rows of the 64-point VVC matrix, transformer.rs:934-1234)
+__constant__ int8_t c_cos32[33] = {91, 90, 90, 90, 89, 88, 87, 85, 83, 82, 80, 78, 75, 73, 70, 67, 64,
+                                   61, 57, 54, 50, 46, 43, 38, 36, 31, 25, 22, 18, 13, 9,  4,  0};
+__constant__ uint8_t c_divsig[16] = {0, 7, 6, 5, 5, 4, 4, 3, 3, 2, 2, 1, 1, 1, 1, 0};
+__constant__ uint8_t c_cand15[15] = {0, 1, 2, 7, 13, 18, 23, 29, 34, 39, 45, 50, 55, 60, 66};
+
+__host__ __device__ constexpr int tab_off(int l2) { return l2 == 2 ? 0 : (l2 == 3 ? 16 : (l2 == 4 ? 80 : 336)); }
+constexpr int TAB_TOTAL = 16 + 64 + 256 + 1024;
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared memory layout
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int RY_STRIDE = 68, RY_X0 = 4, RY_Y0 = 2, RY_ROWS = 34;  // luma window: rows -2..31, cols -4..63
+constexpr int RC_STRIDE = 36, RC_X0 = 4, RC_Y0 = 1, RC_ROWS = 17;  // chroma window: rows -1..15, cols -4..31
+
+struct Tables {
+    int8_t T[TAB_TOTAL];       // DCT matrix per size, row-major  T[i*n + x]
+    int8_t Tt[TAB_TOTAL];      // transposed                      Tt[x*n + i]
+    uint16_t scan[TAB_TOTAL];  // forward scan index k (sub-block diagonal, then 4x4 diagonal; ctu.rs:14-81) -> raster offset
+    int32_t ldq[64];
+    int32_t lv[64];
+    int32_t fc[32];            // fC taps packed as 4 x int8
+};
+
+struct WarpScratch {  // pointers into the scratch pool
+    int16_t *A, *B;
+    uint16_t *Wd;
+    uint8_t *pred;
+    int16_t *refx;  // 3n+3 entries, index n+idx for idx in [-n, 2n+2]
+};
+
+constexpr int MAXTASK = 48;
+
+struct Shared {
+    Tables tb;
+    // CTU state
+    uint8_t orgY[1024];
+    uint8_t orgC[2][256];
+    uint8_t recY[RY_ROWS * RY_STRIDE];
+    uint8_t recC[2][RC_ROWS * RC_STRIDE];
+    int16_t lvY[1024];
+    int16_t lvC[2][256];
+    uint8_t lm[64], cm[16];
+    // no-split state saved per depth (0: 32x32, 1: 16x16, 2: 8x8)
+    uint8_t svRecY[1024 + 256 + 64];
+    uint8_t svRecC[2][256 + 64 + 16];
+    int16_t svLvY[1024 + 256 + 64];
+    int16_t svLvC[2][256 + 64 + 16];
+    uint8_t svLm[3][64], svCm[3][16];
+    // reference samples of the current node: [comp][raw|filtered]
+    int16_t seq[3][132];
+    int16_t refL[3][2][68];
+    int16_t refA[3][2][64];
+    uint8_t pds[256];         // CCLM down-sampled luma of the current node
+    uint8_t leftModes[8];     // final luma modes of the left CTU's right-most 4x4 column
+    // task results
+    uint32_t r_ssd[MAXTASK];
+    int32_t r_rate[MAXTASK];
+    uint32_t r_sad[MAXTASK];
+    int item;
+    // per-warp scratch
+    int16_t bigA[NBIG][1024], bigB[NBIG][1024];
+    uint16_t bigW[NBIG][1024];
+    uint8_t bigP[NBIG][1024];
+    int16_t smA[NW - NBIG][256], smB[NW - NBIG][256];
+    uint16_t smW[NW - NBIG][256];
+    uint8_t smP[NW - NBIG][256];
+    int16_t refx[NW][100];
+};
+
+struct Node {
+    int x, y, w;  // CTU-relative luma position / size
+    int tree;
+    bool ar, bl;
+};
+
+struct CtuGeom {
+    int cx, cy;  // absolute luma position of the CTU
+    int W, H;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ilog2i(int v) { return 31 - __clz(v); }
+__device__ __forceinline__ int clip8(int v) { return min(255, max(0, v)); }
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ unsigned warp_sumu(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint8_t &RY(Shared &S, int x, int y) { return S.recY[(y + RY_Y0) * RY_STRIDE + x + RY_X0]; }
+__device__ __forceinline__ uint8_t &RC(Shared &S, int c, int x, int y) { return S.recC[c - 1][(y + RC_Y0) * RC_STRIDE + x + RC_X0]; }
+__device__ __forceinline__ int rec_at(Shared &S, int c, int x, int y) { return c == 0 ? RY(S, x, y) : RC(S, c, x, y); }
+__device__ __forceinline__ int org_at(Shared &S, int c, int x, int y) { return c == 0 ? S.orgY[y * 32 + x] : S.orgC[c - 1][y * 16 + x]; }
+
+// encoder_context.rs:918-956 derive_neighbouring_block_availability, CTU-relative luma coordinates (H9)
+__device__ __forceinline__ bool nb_avail(const CtuGeom &g, const Node &nd, int xn, int yn, bool ar, bool bl) {
+    int ax = g.cx + xn, ay = g.cy + yn;
+    return ax >= 0 && ay >= 0 && ax < g.W && ay < g.H && (((xn >> 5) <= 0) || ((yn >> 5) < 0)) && ((yn >> 5) < 1) &&
+           (xn < nd.x + nd.w || ar) && (yn < nd.y + nd.w || bl);
+}
+
+__device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float lambda) {
+    // block_splitter.rs:472-473 / 779: ssd as f32 + lambda * (level as f32 / 16384.0)
+    return __fadd_rn(__uint2float_rn(ssd), __fmul_rn(lambda, __fdiv_rn(__ll2float_rn(level), 16384.0f)));
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reference samples (intra_predictor.rs:146-353), one warp per component
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void build_refs(Shared &S, const CtuGeom &g, const Node &nd, int c, int lane) {
+    const int cs = c != 0;
+    const int n = nd.w >> cs, xt = nd.x >> cs, yt = nd.y >> cs;
+    const int nl = 2 * n + 1, na = 2 * n, tot = nl + na;
+    int16_t *seq = S.seq[c];
+    unsigned masks[5];
+    const int rounds = (tot + 31) >> 5;
+    // sequence order: left[nl-1] ... left[0], above[0] ... above[na-1]
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        masks[r] = 0;
+        if (r < rounds) {
+            int j = r * 32 + lane;
+            int v = -1;
+            if (j < tot) {
+                if (j < nl) {
+                    int y = (nl - 1 - j) - 1;
+                    int yr = (y == -1) ? -1 : (y & ~3);
+                    if (nb_avail(g, nd, (xt - 1) << cs, (yt + yr) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt - 1, yt + y);
+                } else {
+                    int x = j - nl;
+                    int xr = x & ~3;
+                    if (nb_avail(g, nd, (xt + xr) << cs, (yt - 1) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt + x, yt - 1);
+                }
+                seq[j] = (int16_t)v;
+            }
+            masks[r] = __ballot_sync(0xffffffffu, v >= 0);
+        }
+    }
+    __syncwarp();
+    int first = -1;
+#pragma unroll
+    for (int r = 4; r >= 0; r--)
+        if (r < rounds && masks[r]) first = r * 32 + __ffs(masks[r]) - 1;
+    int16_t *L = S.refL[c][0], *A = S.refA[c][0];
+    int vals[5];
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        vals[r] = 128;
+        if (r < rounds) {
+            int j = r * 32 + lane;
+            if (j < tot && first >= 0) {
+                unsigned mm = masks[r] & (0xffffffffu >> (31 - lane));
+                int src = -1;
+                if (mm) src = r * 32 + 31 - __clz(mm);
+                else {
+#pragma unroll
+                    for (int q = 4; q >= 0; q--)
+                        if (q < r && src < 0 && masks[q]) src = q * 32 + 31 - __clz(masks[q]);
+                    if (src < 0) src = first;
+                }
+                vals[r] = seq[src];
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        if (r < rounds) {
+            int j = r * 32 + lane;
+            if (j < tot) {
+                if (j < nl) L[nl - 1 - j] = (int16_t)vals[r];
+                else A[j - nl] = (int16_t)vals[r];
+            }
+        }
+    }
+    __syncwarp();
+    if (c == 0 && n >= 8) {  // [1 2 1] filtered copy, used by modes 0,2,34,66 (intra_predictor.rs:304-352)
+        int16_t *LF = S.refL[0][1], *AF = S.refA[0][1];
+        for (int i = lane; i < nl; i += 32) {
+            int v;
+            if (i == 0) v = (L[1] + 2 * L[0] + A[0] + 2) >> 2;
+            else if (i == nl - 1) v = L[i];
+            else v = (L[i + 1] + 2 * L[i] + L[i - 1] + 2) >> 2;
+            LF[i] = (int16_t)v;
+        }
+        for (int i = lane; i < na; i += 32) {
+            int v;
+            if (i == 0) v = (L[0] + 2 * A[0] + A[1] + 2) >> 2;
+            else if (i == na - 1) v = A[i];
+            else v = (A[i - 1] + 2 * A[i] + A[i + 1] + 2) >> 2;
+            AF[i] = (int16_t)v;
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// prediction (per-sample evaluation after a per-task setup)
+// ---------------------------------------------------------------------------------------------------------------
+struct PredCtx {
+    int kind;  // 0 planar, 1 dc, 2 angular, 3 cclm
+    int mode, c, n, l2;
+    const int16_t *lf;  // left incl. corner at [0]
+    const int16_t *ab;  // above
+    int dc;
+    int ang, inv_angle, vertical, use_fg, nscale, pdpc;
+    const int16_t *rx;  // refx + n
+    int a, k, b;        // cclm
+    bool cclm128;
+};
+
+__device__ __forceinline__ int pdpc_w(int ns, int i) {
+    int s = (2 * i) >> ns;
+    return s > 5 ? 0 : (32 >> s);
+}
+
+// CCLM luma accessor with the replication rules of intra_predictor.rs:1775-1818 (only the reachable cases)
+__device__ __forceinline__ int cclm_py(Shared &S, int bx, int by, bool avail_l, int y, int x) {
+    if (x < 0 && !avail_l) x = 0;
+    return RY(S, bx + x, by + y);
+}
+__device__ __forceinline__ int cclm_ds6(Shared &S, int bx, int by, bool avail_l, int sy, int sx) {
+    return (cclm_py(S, bx, by, avail_l, sy, sx - 1) + cclm_py(S, bx, by, avail_l, sy + 1, sx - 1) + 2 * cclm_py(S, bx, by, avail_l, sy, sx) +
+            2 * cclm_py(S, bx, by, avail_l, sy + 1, sx) + cclm_py(S, bx, by, avail_l, sy, sx + 1) + cclm_py(S, bx, by, avail_l, sy + 1, sx + 1) + 4) >> 3;
+}
+
+// down-sampled luma of the node (intra_predictor.rs:1854-1868), one warp
+__device__ void cclm_downsample(Shared &S, const CtuGeom &g, const Node &nd, int lane) {
+    Node tmp = nd;
+    bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
+    int tw = nd.w >> 1;
+    for (int i = lane; i < tw * tw; i += 32) {
+        int y = i / tw, x = i - y * tw;
+        S.pds[i] = (uint8_t)cclm_ds6(S, nd.x, nd.y, avail_l, 2 * y, 2 * x);
+    }
+}
+
+// derive (a,k,b) for one CCLM mode / component (intra_predictor.rs:1604-2031); uniform across the warp
+__device__ void cclm_params(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, PredCtx &pc) {
+    const int tw = nd.w >> 1, th = tw, tx = nd.x >> 1, ty = nd.y >> 1;
+    bool avail_l = nb_avail(g, nd, nd.x - 1, nd.y, false, false);
+    bool avail_t = nb_avail(g, nd, nd.x, nd.y - 1, false, false);
+    int num_tr = 0, num_bl = 0;
+    if (mode == MODE_T_CCLM) {
+        for (int x = tw; x < 2 * tw; x++) {
+            if (!nb_avail(g, nd, nd.x + x * 2, nd.y - 1, nd.ar, nd.bl)) break;
+            num_tr++;
+        }
+    }
+    if (mode == MODE_L_CCLM) {
+        for (int y = th; y < 2 * th; y++) {
+            if (!nb_avail(g, nd, nd.x - 1, nd.y + y * 2, nd.ar, nd.bl)) break;
+            num_bl++;
+        }
+    }
+    int num_t, num_l;
+    if (mode == MODE_LT_CCLM) {
+        num_t = avail_t ? tw : 0;
+        num_l = avail_l ? th : 0;
+    } else {
+        num_t = (avail_t && mode == MODE_T_CCLM) ? tw + min(num_tr, th) : 0;
+        num_l = (avail_l && mode == MODE_L_CCLM) ? th + min(num_bl, tw) : 0;
+    }
+    pc.cclm128 = (num_l == 0 && num_t == 0);
+    pc.a = 0; pc.k = 0; pc.b = 128;
+    if (pc.cclm128) return;
+    const bool ctu_boundary = nd.y == 0;  // (tu.y & 31) == 0
+    const int is4 = !(avail_t && avail_l && mode == MODE_LT_CCLM);
+    int cnt_t = 0, cnt_l = 0;
+    int start_t = num_t >> (2 + is4), step_t = max(1, num_t >> (1 + is4));
+    int start_l = num_l >> (2 + is4), step_l = max(1, num_l >> (1 + is4));
+    if (avail_t && (mode == MODE_LT_CCLM || mode == MODE_T_CCLM)) cnt_t = min((1 + is4) << 1, num_t);
+    if (avail_l && (mode == MODE_LT_CCLM || mode == MODE_L_CCLM)) cnt_l = min((1 + is4) << 1, num_l);
+    int sy[4] = {0, 0, 0, 0}, sc[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        if (i < cnt_t) {
+            int p = start_t + i * step_t;
+            sc[i] = RC(S, c, tx + p, ty - 1);
+            int sx = 2 * p;
+            if (!ctu_boundary)
+                sy[i] = (cclm_py(S, nd.x, nd.y, avail_l, -1, sx - 1) + cclm_py(S, nd.x, nd.y, avail_l, -2, sx - 1) +
+                         2 * cclm_py(S, nd.x, nd.y, avail_l, -1, sx) + 2 * cclm_py(S, nd.x, nd.y, avail_l, -2, sx) +
+                         cclm_py(S, nd.x, nd.y, avail_l, -1, sx + 1) + cclm_py(S, nd.x, nd.y, avail_l, -2, sx + 1) + 4) >> 3;
+            else
+                sy[i] = (cclm_py(S, nd.x, nd.y, avail_l, -1, sx - 1) + 2 * cclm_py(S, nd.x, nd.y, avail_l, -1, sx) +
+                         cclm_py(S, nd.x, nd.y, avail_l, -1, sx + 1) + 2) >> 2;
+        } else if (i < cnt_t + cnt_l) {
+            int p = start_l + (i - cnt_t) * step_l;
+            sc[i] = RC(S, c, tx - 1, ty + p);
+            sy[i] = cclm_ds6(S, nd.x, nd.y, avail_l, 2 * p, -2);
+        }
+    }
+    int mn0 = 0, mn1 = 2, mx0 = 1, mx1 = 3, t;
+    if (sy[mn0] > sy[mn1]) { t = mn0; mn0 = mn1; mn1 = t; }
+    if (sy[mx0] > sy[mx1]) { t = mx0; mx0 = mx1; mx1 = t; }
+    if (sy[mn0] > sy[mx1]) { t = mn0; mn0 = mx0; mx0 = t; t = mn1; mn1 = mx1; mx1 = t; }
+    if (sy[mn1] > sy[mx0]) { t = mn1; mn1 = mx0; mx0 = t; }
+    int max_y = (sy[mx0] + sy[mx1] + 1) >> 1, max_c = (sc[mx0] + sc[mx1] + 1) >> 1;
+    int min_y = (sy[mn0] + sy[mn1] + 1) >> 1, min_c = (sc[mn0] + sc[mn1] + 1) >> 1;
+    int diff = max_y - min_y;
+    if (diff != 0) {
+        int diff_c = max_c - min_c;
+        int x = ilog2i(diff);
+        int norm = ((diff << 4) >> x) & 15;
+        x += norm != 0;
+        int adc = abs(diff_c);
+        int y = adc > 0 ? ilog2i(adc) + 1 : 0;
+        int a = diff_c == 0 ? 0 : (diff_c * (c_divsig[norm] | 8) + (1 << (y - 1))) >> y;
+        int k;
+        if (3 + x - y < 1) {
+            k = 1;
+            a = a < 0 ? -15 : (a > 0 ? 15 : 0);
+        } else {
+            k = 3 + x - y;
+        }
+        pc.a = a;
+        pc.k = k;
+        pc.b = min_c - ((a * min_y) >> k);
+    } else {
+        pc.a = 0;
+        pc.k = 0;
+        pc.b = min_c;
+    }
+}
+
+// per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
+__device__ void pred_setup(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+    const int cs = c != 0;
+    const int n = nd.w >> cs;
+    pc.mode = mode; pc.c = c; pc.n = n; pc.l2 = ilog2i(n);
+    pc.pdpc = 0; pc.nscale = 0; pc.dc = 0; pc.ang = 0; pc.inv_angle = 0; pc.vertical = 0; pc.use_fg = 0; pc.rx = refx + n;
+    pc.a = pc.k = pc.b = 0; pc.cclm128 = false;
+    if (mode > 66) {
+        pc.kind = 3;
+        pc.lf = pc.ab = nullptr;
+        cclm_params(S, g, nd, c, mode, pc);
+        return;
+    }
+    const int filt = (c == 0 && n >= 8 && (mode == 0 || mode == 2 || mode == 34 || mode == 66)) ? 1 : 0;
+    pc.lf = S.refL[c][filt];
+    pc.ab = S.refA[c][filt];
+    if (mode == MODE_PLANAR) {
+        pc.kind = 0; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
+        return;
+    }
+    if (mode == MODE_DC) {
+        pc.kind = 1; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
+        int s = 0;
+        for (int i = lane; i < n; i += 32) s += pc.ab[i] + pc.lf[1 + i];
+        s = warp_sum(s) + n;
+        pc.dc = (s >> (pc.l2 + 1)) & 255;
+        return;
+    }
+    pc.kind = 2;
+    const int ang = c_angle[mode];
+    pc.ang = ang;
+    pc.inv_angle = ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0);
+    pc.vertical = mode >= 34;
+    if (mode == 2 || mode == 34 || mode == 66) pc.use_fg = 0;
+    else {
+        int md = min(abs(mode - 50), abs(mode - 18));
+        int thr = pc.l2 == 2 ? 24 : (pc.l2 == 3 ? 14 : (pc.l2 == 4 ? 2 : 0));
+        pc.use_fg = md > thr;
+    }
+    if (mode <= 18 || mode >= 50) {
+        pc.pdpc = 1;
+        if (mode == 18 || mode == 50) pc.nscale = (2 * pc.l2 - 2) >> 2;
+        else pc.nscale = min(pc.l2 - ilog2i(3 * pc.inv_angle - 2) + 8, 2);
+        if (pc.nscale < 0) pc.pdpc = 0;
+    }
+    // projection array r[idx], idx in [-n, 2n+2]  (intra_predictor.rs:1398-1414 / 1480-1495)
+    int16_t *r = refx + n;
+    const int lo = ang < 0 ? -n : 0, hi = ang < 0 ? n + 1 : 2 * n + 2;
+    for (int idx = lo + lane; idx <= hi; idx += 32) {
+        int v;
+        if (pc.vertical) {
+            if (idx < 0) v = pc.lf[min((idx * pc.inv_angle + 256) >> 9, n)];
+            else if (idx == 0) v = pc.lf[0];
+            else v = pc.ab[min(idx - 1, 2 * n - 1)];
+        } else {
+            if (idx < 0) {
+                int t = min((idx * pc.inv_angle + 256) >> 9, n);
+                v = t == 0 ? pc.lf[0] : pc.ab[t - 1];
+            } else v = pc.lf[min(idx, 2 * n)];
+        }
+        r[idx] = (int16_t)v;
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ int pred_sample(Shared &S, const PredCtx &pc, int x, int y) {
+    const int n = pc.n;
+    int p;
+    if (pc.kind == 3) {
+        if (pc.cclm128) return 128;
+        return clip8(((S.pds[y * n + x] * pc.a) >> pc.k) + pc.b);
+    }
+    const int16_t *lrs = pc.lf + 1, *ars = pc.ab;
+    if (pc.kind == 0) {
+        int pv = (n - 1 - y) * ars[x] + (y + 1) * lrs[n];
+        int ph = (n - 1 - x) * lrs[y] + (x + 1) * ars[n];
+        p = ((pv + ph + n) >> (pc.l2 + 1)) & 255;
+    } else if (pc.kind == 1) {
+        p = pc.dc;
+    } else {
+        int t = pc.vertical ? y : x, u = pc.vertical ? x : y;
+        int prod = (t + 1) * pc.ang;
+        int iidx = prod >> 5, ifact = prod & 31;
+        const int16_t *r = pc.rx + u + iidx;
+        if (pc.c == 0) {
+            int f0, f1, f2, f3;
+            if (pc.use_fg) {
+                int h = ifact >> 1;
+                f0 = 16 - h; f1 = 32 - h; f2 = 16 + h; f3 = h;
+            } else {
+                int pk = S.tb.fc[ifact];
+                f0 = (int8_t)(pk & 255); f1 = (int8_t)((pk >> 8) & 255); f2 = (int8_t)((pk >> 16) & 255); f3 = (int8_t)((pk >> 24) & 255);
+            }
+            int s = f0 * r[0] + f1 * r[1] + f2 * r[2] + f3 * r[3];
+            p = clip8((s + 32) >> 6);
+        } else if (ifact != 0) {
+            p = (((32 - ifact) * r[1] + ifact * r[2] + 16) >> 5) & 255;
+        } else {
+            p = r[1] & 255;
+        }
+    }
+    if (pc.pdpc) {
+        int refl = 0, reft = 0, wl = 0, wt = 0;
+        const int mode = pc.mode, ns = pc.nscale;
+        if (mode < 2) {
+            refl = lrs[y]; reft = ars[x]; wl = pdpc_w(ns, x); wt = pdpc_w(ns, y);
+        } else if (mode == 18 || mode == 50) {
+            int corner = pc.lf[0];
+            refl = lrs[y] - corner + p; reft = ars[x] - corner + p;
+            if (mode == 50) wl = pdpc_w(ns, x); else wt = pdpc_w(ns, y);
+        } else if (mode < 18) {
+            if (y < (3 << ns)) reft = ars[x + (((y + 1) * pc.inv_angle + 256) >> 9)];
+            wt = pdpc_w(ns, y);
+        } else {
+            if (x < (3 << ns)) refl = lrs[y + (((x + 1) * pc.inv_angle + 256) >> 9)];
+            wl = pdpc_w(ns, x);
+        }
+        int v = (int16_t)(refl * wl + reft * wt + (64 - wt - wl) * p + 32);
+        p = clip8(v >> 6);
+    }
+    return p;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// transforms (transformer.rs:2040-2378 forward, 2380-2737 inverse), one warp per TB, direct matrix multiply
+// ---------------------------------------------------------------------------------------------------------------
+// out[y][i] = (sum_x T[i][x] * in[y][x] + rnd) >> sh              (rows; lanes over i, Tt makes the T read conflict-free)
+__device__ __forceinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+    const int nn = n * n;
+    for (int o = lane; o < nn; o += 32) {
+        int y = o >> l2, i = o & (n - 1);
+        const int16_t *row = in + y * n;
+        int s = 0;
+#pragma unroll 4
+        for (int x = 0; x < n; x++) s += (int)Tt[x * n + i] * (int)row[x];
+        s = (s + rnd) >> sh;
+        if (clamp16) s = min(32767, max(-32768, s));
+        out[o] = (int16_t)s;
+    }
+}
+// out[i][x] = (sum_y T[i][y] * in[y][x] + rnd) >> sh              (columns; lanes over x)
+__device__ __forceinline__ void mm_cols(const int8_t *T, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+    const int nn = n * n;
+    for (int o = lane; o < nn; o += 32) {
+        int i = o >> l2, x = o & (n - 1);
+        const int8_t *trow = T + i * n;
+        int s = 0;
+#pragma unroll 4
+        for (int y = 0; y < n; y++) s += (int)trow[y] * (int)in[y * n + x];
+        s = (s + rnd) >> sh;
+        if (clamp16) s = min(32767, max(-32768, s));
+        out[o] = (int16_t)s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// dependent quantisation (quantizer.rs:338-517 search_dq + 686-721 walk) and the rate walk (block_splitter.rs:415-460)
+// ---------------------------------------------------------------------------------------------------------------
+#define WB_LDQ(i) ((i) < 64 ? S.tb.ldq[(i)] : __ldg(&tab->ldq[min((i), 1023)]))
+#define WB_LV(i) ((i) < 64 ? S.tb.lv[(i)] : __ldg(&tab->lv[min((i), 1023)]))
+
+__device__ __forceinline__ unsigned map_compose(unsigned a, unsigned b) {  // apply a first, then b (4 x 2-bit next-state maps)
+    unsigned r = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) r |= ((b >> (2 * ((a >> (2 * s)) & 3))) & 3) << (2 * s);
+    return r;
+}
+
+// coef (raster, n x n) -> lev (raster).  Returns rate (sum of lv[] per block_splitter.rs:415-460) and whether any level != 0.
+__device__ void trellis(Shared &S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
+                        int &rate_out, bool &any_out) {
+    const int n = 1 << l2, nn = n * n, sh = l2 + 4, off = 1 << (sh - 1);
+    const int ls = tab->ls;
+    const uint16_t *scan = S.tb.scan + tab_off(l2);
+    const int ldq1 = S.tb.ldq[1];
+    // ---- pre-pass: x = S / ls per position; k* = highest scan position whose state-0 lower candidate is non-zero (H2)
+    int kstar = -1;
+    bool anytc = false;
+    for (int k = lane; k < nn; k += 32) {
+        int tc = coef[scan[k]];
+        unsigned x = 0, nz = tc != 0;
+        if (nz) {
+            unsigned s = tc > 0 ? ((unsigned)tc << sh) - (unsigned)off : ((unsigned)(-tc) << sh) + (unsigned)off;
+            x = min(s / (unsigned)ls, 2047u);
+            anytc = true;
+            if (x >= 2) kstar = k;
+        }
+        Wd[k] = (uint16_t)(x | (nz << 11));
+    }
+    kstar = warp_max(kstar);
+    anytc = __any_sync(0xffffffffu, anytc);
+    __syncwarp();
+    if (!anytc) {  // every candidate level is 0 and every position is a trailing zero: levels 0, rate 0
+        for (int k = lane; k < nn; k += 32) lev[k] = 0;
+        rate_out = 0;
+        any_out = false;
+        __syncwarp();
+        return;
+    }
+    // ---- backward DP from DC upwards; costs are int32 relative values compared by wrapped difference (exact: the true
+    //      differences between state costs stay far below 2^31)
+    const int INF = 1 << 29;
+    int C0, C1, C2, C3;
+    {   // DC leaf (quantizer.rs:367-409), computed uniformly
+        int tc = coef[0];
+        unsigned x = Wd[0] & 2047u;
+        int Cs[4];
+        unsigned dec = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            const bool itz = (s == 0) && (kstar < 0);
+            int cost;
+            if (tc == 0) {
+                cost = itz ? 0 : ldq1;
+                if (itz) cost -= ldq1;
+            } else {
+                const int delta = s > 1;
+                int a0 = (int)(x >> 1);
+                int q0 = (int)(int16_t)(2 * a0 - delta);
+                if (tc < 0) q0 = -q0;
+                int d0 = abs(tc - ((q0 * ls + off) >> sh));
+                int bits0 = (a0 != 0 || !itz) ? a0 + 1 : 0;
+                int cost0 = 128 * d0 + WB_LDQ(bits0);
+                int a1 = a0 + 1;
+                int q1 = 2 * a1 - delta;
+                if (tc < 0) q1 = -q1;
+                int d1 = abs(tc - ((q1 * ls + off) >> sh));
+                int cost1 = 128 * d1 + WB_LDQ(a1 + 1);
+                if (cost0 <= cost1) {
+                    cost = cost0;
+                    if (itz && a0 == 0) cost -= ldq1;
+                } else {
+                    cost = cost1;
+                    dec |= 1u << s;
+                }
+            }
+            Cs[s] = cost;
+        }
+        C0 = Cs[0]; C1 = Cs[1]; C2 = Cs[2]; C3 = Cs[3];
+        if (lane == 0) Wd[0] = (uint16_t)(Wd[0] | (dec << 12));
+    }
+    for (int base = 0; base < nn; base += 32) {
+        const int k = base + lane;
+        int L00 = 0, L10 = INF, L01 = 0, L11 = INF, L0s0 = 0;
+        unsigned pk = 0;
+        if (k < nn) {
+            unsigned w = Wd[k];
+            unsigned x = w & 2047u;
+            const bool flagged = k > kstar;
+            if (w & 2048u) {
+                int tc = coef[scan[k]];
+                // delta = 0
+                int a0 = (int)(x >> 1);
+                int q0 = 2 * a0;  // a0 > 0 ? 2*a0 - 0 : 0
+                int q1 = 2 * a0 + 2;
+                if (tc < 0) { q0 = -q0; q1 = -q1; }
+                int d0 = abs(tc - ((q0 * ls + off) >> sh));
+                int d1 = abs(tc - ((q1 * ls + off) >> sh));
+                L00 = 128 * d0 + WB_LDQ(a0 + 1);
+                L10 = 128 * d1 + WB_LDQ(a0 + 2);
+                L0s0 = (flagged && a0 == 0) ? 128 * d0 : L00;
+                pk = a0 & 1;
+                // delta = 1
+                a0 = (int)((x + 1) >> 1);
+                q0 = a0 > 0 ? 2 * a0 - 1 : 0;
+                q1 = 2 * a0 + 1;
+                if (tc < 0) { q0 = -q0; q1 = -q1; }
+                d0 = abs(tc - ((q0 * ls + off) >> sh));
+                d1 = abs(tc - ((q1 * ls + off) >> sh));
+                L01 = 128 * d0 + WB_LDQ(a0 + 1);
+                L11 = 128 * d1 + WB_LDQ(a0 + 2);
+                pk |= (a0 & 1) << 1;
+            } else {
+                L00 = L01 = ldq1;
+                L0s0 = flagged ? 0 : ldq1;
+            }
+            if (flagged && (k & 15) == 0) pk |= 4;
+        }
+        unsigned mydec = 0;
+        const int cnt = min(32, nn - base);
+        for (int j = (base == 0 ? 1 : 0); j < cnt; j++) {
+            const int l0s0 = __shfl_sync(0xffffffffu, L0s0, j);
+            const int l00 = __shfl_sync(0xffffffffu, L00, j);
+            const int l10 = __shfl_sync(0xffffffffu, L10, j);
+            const int l01 = __shfl_sync(0xffffffffu, L01, j);
+            const int l11 = __shfl_sync(0xffffffffu, L11, j);
+            const unsigned p = __shfl_sync(0xffffffffu, pk, j);
+            // states 0,1 move to {0,2}; states 2,3 move to {1,3}   (q_state_trans_table, encoder_context.rs:339)
+            int X = (p & 1) ? C2 : C0, Y = (p & 1) ? C0 : C2;
+            int c0 = l0s0 + X, c1 = l10 + Y;
+            bool d_0 = (c1 - c0) < 0;
+            int n0 = d_0 ? c1 : c0;
+            if ((p & 4) && !d_0) n0 -= ldq1;
+            c0 = l00 + Y; c1 = l10 + X;
+            bool d_1 = (c1 - c0) < 0;
+            int n1 = d_1 ? c1 : c0;
+            X = (p & 2) ? C3 : C1; Y = (p & 2) ? C1 : C3;
+            c0 = l01 + X; c1 = l11 + Y;
+            bool d_2 = (c1 - c0) < 0;
+            int n2 = d_2 ? c1 : c0;
+            c0 = l01 + Y; c1 = l11 + X;
+            bool d_3 = (c1 - c0) < 0;
+            int n3 = d_3 ? c1 : c0;
+            C0 = n0; C1 = n1; C2 = n2; C3 = n3;
+            if (lane == j) mydec = (unsigned)d_0 | ((unsigned)d_1 << 1) | ((unsigned)d_2 << 2) | ((unsigned)d_3 << 3);
+        }
+        if (k < nn && k > 0) Wd[k] = (uint16_t)(Wd[k] | (mydec << 12));
+    }
+    __syncwarp();
+    // ---- walk from the last scan position with state 0 (quantizer.rs:686-721): parallel prefix over next-state maps
+    unsigned state = 0;
+    bool seen_nz = false;
+    int rate = 0;
+    for (int top = nn - 1; top >= 0; top -= 32) {
+        const int k = top - lane;
+        unsigned m = 0xE4u;  // identity
+        unsigned w = 0, x = 0, dec = 0;
+        bool nz = false;
+        if (k >= 0) {
+            w = Wd[k];
+            x = w & 2047u;
+            nz = (w & 2048u) != 0;
+            dec = w >> 12;
+            m = 0;
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                unsigned a = nz ? (((k == 0) ? (x >> 1) : ((x + (s > 1)) >> 1)) + ((dec >> s) & 1u)) : 0u;
+                unsigned nx = 2u * ((a & 1u) ^ (s & 1u)) + (s >> 1);
+                m |= nx << (2 * s);
+            }
+        }
+        unsigned inc = m;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc = map_compose(t, inc);
+        }
+        unsigned exc = __shfl_up_sync(0xffffffffu, inc, 1);
+        const unsigned s_in = (lane == 0) ? state : ((exc >> (2 * state)) & 3u);
+        const unsigned last = __shfl_sync(0xffffffffu, inc, 31);
+        state = (last >> (2 * state)) & 3u;
+        int q = 0;
+        const int delta = s_in > 1;
+        if (k >= 0 && nz) {
+            int a = (int)(((k == 0) ? (x >> 1) : ((x + delta) >> 1)) + ((dec >> s_in) & 1u));
+            if (k == 0) q = (int)(int16_t)(2 * a - delta);  // H3: a == 0, delta == 1 gives -1
+            else q = a > 0 ? 2 * a - delta : 0;
+            if (coef[scan[k]] < 0) q = -q;
+        }
+        if (k >= 0) lev[scan[k]] = (int16_t)q;
+        const bool isnz = q != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, isnz);
+        if (k >= 0) {
+            if (isnz) {
+                int ar = (abs(q) + delta) >> 1;
+                rate += WB_LV(ar);
+            } else if (seen_nz || (bal & ((1u << lane) - 1u))) {
+                rate += S.tb.lv[0];
+            }
+        }
+        seen_nz = seen_nz || bal != 0;
+    }
+    rate_out = warp_sum(rate);
+    any_out = seen_nz;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tasks
+// ---------------------------------------------------------------------------------------------------------------
+__device__ WarpScratch warp_scratch(Shared &S, int warp) {
+    WarpScratch ws;
+    if (warp < NBIG) {
+        ws.A = S.bigA[warp]; ws.B = S.bigB[warp]; ws.Wd = S.bigW[warp]; ws.pred = S.bigP[warp];
+    } else {
+        ws.A = S.smA[warp - NBIG]; ws.B = S.smB[warp - NBIG]; ws.Wd = S.smW[warp - NBIG]; ws.pred = S.smP[warp - NBIG];
+    }
+    ws.refx = S.refx[warp];
+    return ws;
+}
+
+// SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
+__device__ unsigned sad_task(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, const WarpScratch &ws, int lane) {
+    PredCtx pc;
+    pred_setup(S, g, nd, c, mode, ws.refx, lane, pc);
+    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
+    unsigned sad = 0;
+    for (int i = lane; i < n * n; i += 32) {
+        int y = i >> l2, x = i & (n - 1);
+        int p = pred_sample(S, pc, x, y);
+        sad += abs(p - org_at(S, c, bx + x, by + y));
+    }
+    return warp_sumu(sad);
+}
+
+// full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
+// commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
+__device__ void full_task(Shared &S, const DevTables *__restrict__ tab, const CtuGeom &g, const Node &nd, int c, int mode, bool commit,
+                          const WarpScratch &ws, int lane, unsigned &ssd_out, int &rate_out) {
+    PredCtx pc;
+    pred_setup(S, g, nd, c, mode, ws.refx, lane, pc);
+    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2, nn = n * n;
+    int16_t *A = ws.A, *B = ws.B;
+    bool anyres = false;
+    for (int i = lane; i < nn; i += 32) {
+        int y = i >> l2, x = i & (n - 1);
+        int p = pred_sample(S, pc, x, y);
+        ws.pred[i] = (uint8_t)p;
+        int r = org_at(S, c, bx + x, by + y) - p;
+        A[i] = (int16_t)r;
+        anyres |= r != 0;
+    }
+    anyres = __any_sync(0xffffffffu, anyres);
+    __syncwarp();
+    const int to = tab_off(l2);
+    bool anylev = false;
+    int rate = 0;
+    if (anyres) {
+        mm_rows(S.tb.Tt + to, A, B, n, l2, 1 << (l2 - 2), l2 - 1, false, lane);
+        __syncwarp();
+        mm_cols(S.tb.T + to, B, A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
+        __syncwarp();
+        trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
+    } else {
+        for (int i = lane; i < nn; i += 32) B[i] = 0;
+        __syncwarp();
+    }
+    if (commit) {
+        int16_t *dst = c == 0 ? S.lvY : S.lvC[c - 1];
+        const int stride = c == 0 ? 32 : 16;
+        for (int i = lane; i < nn; i += 32) {
+            int y = i >> l2, x = i & (n - 1);
+            dst[(by + y) * stride + bx + x] = B[i];
+        }
+    }
+    if (anylev) {
+        const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
+        for (int i = lane; i < nn; i += 32) A[i] = (int16_t)min(32767, max(-32768, ((int)B[i] * ls + off) >> sh));  // quantizer.rs:1074-1075
+        __syncwarp();
+        // vertical: V[y][x] = clamp16((sum_i T[i][y] * D[i][x] + 64) >> 7)   (Tt's rows are T's columns)
+        mm_cols(S.tb.Tt + to, A, B, n, l2, 64, 7, true, lane);
+        __syncwarp();
+        // horizontal: R[y][x] = (sum_i T[i][x] * V[y][i] + 2048) >> 12
+        mm_rows(S.tb.T + to, B, A, n, l2, 2048, 12, false, lane);
+        __syncwarp();
+    }
+    unsigned ssd = 0;
+    for (int i = lane; i < nn; i += 32) {
+        int y = i >> l2, x = i & (n - 1);
+        int res = anylev ? (int)A[i] : 0;
+        int rec = clip8((int)(int16_t)((int)ws.pred[i] + res));
+        int d = rec - org_at(S, c, bx + x, by + y);
+        ssd += (unsigned)(d * d);
+        if (commit) {
+            if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
+            else RC(S, c, bx + x, by + y) = (uint8_t)rec;
+        }
+    }
+    ssd_out = warp_sumu(ssd);
+    rate_out = rate;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// MPM derivation for the mode-bit estimate (ctu.rs:1498-1635) with the H1 neighbour semantics
+// ---------------------------------------------------------------------------------------------------------------
+__device__ int luma_kind(const Shared &S, const CtuGeom &g, const Node &nd, int mode, int root_mode) {
+    if (mode == MODE_PLANAR) return 0;
+    int left, above;
+    if (nd.x == 0) left = g.cx > 0 ? S.leftModes[(nd.y + nd.w - 1) >> 2] : MODE_PLANAR;
+    else left = root_mode;
+    above = nd.y == 0 ? MODE_PLANAR : root_mode;
+    int cand[5];
+    if (left == above && left > MODE_DC) {
+        int m = left;
+        cand[0] = m; cand[1] = 2 + (m + 61) % 64; cand[2] = 2 + (m - 1) % 64; cand[3] = 2 + (m + 60) % 64; cand[4] = 2 + m % 64;
+    } else if (left != above && (left > MODE_DC || above > MODE_DC)) {
+        int mn = min(left, above), mx = max(left, above);
+        if (mn > MODE_DC) {
+            int d = mx - mn;
+            cand[0] = left; cand[1] = above;
+            if (d == 1) { cand[2] = 2 + (mn + 61) % 64; cand[3] = 2 + (mx - 1) % 64; cand[4] = 2 + (mn + 60) % 64; }
+            else if (d >= 62) { cand[2] = 2 + (mn - 1) % 64; cand[3] = 2 + (mx + 61) % 64; cand[4] = 2 + mn % 64; }
+            else if (d == 2) { cand[2] = 2 + (mn - 1) % 64; cand[3] = 2 + (mn + 61) % 64; cand[4] = 2 + (mx - 1) % 64; }
+            else { cand[2] = 2 + (mn + 61) % 64; cand[3] = 2 + (mn - 1) % 64; cand[4] = 2 + (mx + 61) % 64; }
+        } else {
+            cand[0] = mx; cand[1] = 2 + (mx + 61) % 64; cand[2] = 2 + (mx - 1) % 64; cand[3] = 2 + (mx + 60) % 64; cand[4] = 2 + mx % 64;
+        }
+    } else {
+        cand[0] = MODE_DC; cand[1] = 50; cand[2] = 18; cand[3] = 46; cand[4] = 54;
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++)
+        if (cand[i] == mode) return 1 + i;
+    // remainder = mode - 1 - #(candidates < mode)  (sorted-candidate ladder of ctu.rs:1603-1633)
+    int below = 0;
+#pragma unroll
+    for (int i = 0; i < 5; i++) below += cand[i] < mode;
+    return 6 + mode - 1 - below;
+}
+
+}  // namespace wb

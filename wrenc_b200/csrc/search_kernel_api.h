@@ -1,0 +1,50 @@
+// search_kernel_api.h — what the host side (api.cu) needs to know about the search kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tuning.h"
+
+namespace wb {
+
+struct CtuRecord {
+    uint32_t split_mask;
+    uint8_t luma_mode[64];
+    uint8_t chroma_mode[16];
+    float cost;
+};
+static_assert(sizeof(CtuRecord) == 88, "record layout is part of the C ABI");
+
+struct SearchParams {
+    int W, H, Wc, Hc;      // luma size, CTUs per row / column
+    int max_depth;
+    int n_items;
+    int epoch;             // value a done flag takes when its CTU is final in THIS launch
+    const uint8_t *orig;   // [pic][W*H*3/2] I420
+    uint8_t *rec;          // same geometry
+    int16_t *lev;          // same geometry, int16 per sample
+    uint8_t *mode_map;     // [pic][(W/4)*(H/4)] final luma mode per 4x4 (left-CTU MPM lookups, H1)
+    CtuRecord *records;    // [pic][Wc*Hc]
+    int *done;             // [pic][Wc*Hc]
+    const uint32_t *items; // work list: pic<<16 | cy<<8 | cx
+    unsigned int *counter; // work-list cursor
+    const DevTables *tab;
+};
+
+struct BlockParams {
+    int op;  // 0 predict, 1 forward DCT, 2 inverse DCT, 3 dep-quant (+rate), 4 dequantise
+    int W, H, x, y, w, tree, ar, bl, c, mode;
+    const uint8_t *rec;   // I420 reconstruction picture (op 0)
+    uint8_t *out8;
+    int l2, count;
+    const int16_t *in;
+    int16_t *out16;
+    int *outi;
+    const DevTables *tab;
+};
+cudaError_t launch_block(const BlockParams &P, int grid, cudaStream_t stream);
+size_t search_smem_bytes();
+int search_ctas_per_sm();
+cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream);
+
+}  // namespace wb

@@ -1,0 +1,223 @@
+"""ctypes binding of libwrenc_b200.so (include/wrenc_b200.h) — the host-side mirror of the reference's per-picture driver
+(reference src/main.rs:294-402 -> SliceEncoder::encode -> CtuEncoder::encode -> BlockSplitter::split_ct).
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked on a CPU box), but creating a
+`SearchEncoder` raises unless the CUDA library loads and finds a B200.  Nothing here touches oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwrenc_b200.so")
+
+RECORD_DTYPE = np.dtype([("split_mask", "<u4"), ("luma_mode", "u1", (64,)), ("chroma_mode", "u1", (16,)), ("cost", "<f4")])
+assert RECORD_DTYPE.itemsize == 88
+
+SINGLE_TREE, DUAL_TREE_LUMA, DUAL_TREE_CHROMA = 0, 1, 2
+MODE_LT_CCLM, MODE_L_CCLM, MODE_T_CCLM = 81, 82, 83
+
+EXPORTS = [
+    "wrenc_b200_create", "wrenc_b200_destroy", "wrenc_b200_last_error", "wrenc_b200_submit", "wrenc_b200_receive",
+    "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident",
+    "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
+    "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("qp", C.c_int32), ("max_split_depth", C.c_int32),
+                ("device", C.c_int32), ("pictures_in_flight", C.c_int32), ("want_recon", C.c_int32),
+                ("want_decisions", C.c_int32), ("extra_params", C.c_char_p)]
+
+
+class Consts(C.Structure):
+    _fields_ = [("lambda_q", C.c_int64), ("lambda_rd", C.c_float), ("lambda_rd_chroma", C.c_float), ("ls", C.c_int32),
+                ("lv", C.c_int64 * 8), ("dq", C.c_int64 * 8)]
+
+
+class WrencB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load the C-ABI library; raises (never falls back) when it is missing or does not load."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise WrencB200Error(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u8p = C.c_void_p, C.c_int32, C.c_void_p
+    L.wrenc_b200_create.restype = C.c_int
+    L.wrenc_b200_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.wrenc_b200_destroy.restype = None
+    L.wrenc_b200_destroy.argtypes = [vp]
+    L.wrenc_b200_last_error.restype = C.c_char_p
+    L.wrenc_b200_last_error.argtypes = [vp]
+    L.wrenc_b200_submit.restype = C.c_int
+    L.wrenc_b200_submit.argtypes = [vp, C.c_uint64, u8p, u8p, u8p]
+    L.wrenc_b200_receive.restype = C.c_int
+    L.wrenc_b200_receive.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.wrenc_b200_decisions.restype = C.c_int
+    L.wrenc_b200_decisions.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.wrenc_b200_flush.restype = C.c_int
+    L.wrenc_b200_flush.argtypes = [vp]
+    L.wrenc_b200_pending.restype = C.c_int
+    L.wrenc_b200_pending.argtypes = [vp]
+    L.wrenc_b200_search_resident.restype = C.c_int
+    L.wrenc_b200_search_resident.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.wrenc_b200_workspace_bytes.restype = C.c_size_t
+    L.wrenc_b200_workspace_bytes.argtypes = [vp, i32]
+    L.wrenc_b200_get_consts.restype = C.c_int
+    L.wrenc_b200_get_consts.argtypes = [vp, C.POINTER(Consts)]
+    L.wrenc_b200_block_predict.restype = C.c_int
+    L.wrenc_b200_block_predict.argtypes = [vp, vp] + [C.c_int] * 8 + [vp]
+    for name in ("fwd_dct", "inv_dct", "dequantize"):
+        f = getattr(L, "wrenc_b200_block_" + name)
+        f.restype = C.c_int
+        f.argtypes = [vp, vp, C.c_int, C.c_int, vp]
+    L.wrenc_b200_block_quantize.restype = C.c_int
+    L.wrenc_b200_block_quantize.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+    L.wrenc_b200_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class SearchEncoder:
+    """One handle per GPU.  Mirrors the reference flags: --qp, --max-split-depth, --extra-params, --reconst."""
+
+    def __init__(self, width, height, qp=26, max_split_depth=3, device=0, pictures_in_flight=8, want_recon=True,
+                 want_decisions=True, extra_params=None):
+        self.L = load_library()
+        self.h = C.c_void_p()
+        self.width, self.height = int(width), int(height)
+        self._extra = extra_params.encode() if extra_params else None
+        cfg = Config(self.width, self.height, int(qp), int(max_split_depth), int(device), int(pictures_in_flight),
+                     int(bool(want_recon)), int(bool(want_decisions)), self._extra)
+        rc = self.L.wrenc_b200_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            msg = self.L.wrenc_b200_last_error(None).decode()
+            self.h = C.c_void_p()
+            if rc == -1:
+                raise ValueError(msg)
+            raise WrencB200Error(f"wrenc_b200_create failed ({rc}): {msg}")
+        self.want_recon, self.want_decisions = bool(want_recon), bool(want_decisions)
+        self.pictures_in_flight = max(1, int(pictures_in_flight))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h:
+            self.L.wrenc_b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc < 0:
+            raise WrencB200Error(f"wrenc_b200 error {rc}: {self.L.wrenc_b200_last_error(self.h).decode()}")
+        return rc
+
+    def consts(self):
+        c = Consts()
+        self._check(self.L.wrenc_b200_get_consts(self.h, C.byref(c)))
+        return dict(lambda_q=c.lambda_q, lambda_rd=c.lambda_rd, lambda_rd_chroma=c.lambda_rd_chroma, ls=c.ls,
+                    lv=np.array(list(c.lv), np.int64), dq=np.array(list(c.dq), np.int64))
+
+    # ---- host-plane path (the reference-facing call) ----
+    def submit(self, pic_idx, y, cb, cr):
+        y, cb, cr = (np.ascontiguousarray(a, np.uint8) for a in (y, cb, cr))
+        assert y.shape == (self.height, self.width) and cb.shape == (self.height // 2, self.width // 2) and cr.shape == cb.shape
+        self._check(self.L.wrenc_b200_submit(self.h, int(pic_idx), _ptr(y), _ptr(cb), _ptr(cr)))
+
+    def pending(self):
+        return self.L.wrenc_b200_pending(self.h)
+
+    def flush(self):
+        self._check(self.L.wrenc_b200_flush(self.h))
+
+    def receive(self, copy=True):
+        idx = C.c_uint64()
+        sd, ry, rcb, rcr = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n = C.c_size_t()
+        self._check(self.L.wrenc_b200_receive(self.h, C.byref(idx), C.byref(sd), C.byref(n), C.byref(ry), C.byref(rcb), C.byref(rcr)))
+        W, H = self.width, self.height
+        out = {"pic_idx": idx.value, "slice_data": C.string_at(sd, n.value) if sd and n.value else b""}
+
+        def view(p, shape, dt):
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=shape)
+            return a.copy() if copy else a
+
+        if self.want_recon:
+            out["rec"] = [view(ry, (H, W), np.uint8), view(rcb, (H // 2, W // 2), np.uint8), view(rcr, (H // 2, W // 2), np.uint8)]
+        rec_p, ly, lcb, lcr = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self.L.wrenc_b200_decisions(self.h, C.byref(rec_p), C.byref(ly), C.byref(lcb), C.byref(lcr)))
+        nctu = (H // 32) * (W // 32)
+        raw = np.ctypeslib.as_array(C.cast(rec_p, C.POINTER(C.c_uint8)), shape=(nctu * 88,))
+        out["records"] = raw.view(RECORD_DTYPE).copy() if copy else raw.view(RECORD_DTYPE)
+        if self.want_decisions:
+            out["coef"] = [view(ly, (H, W), np.int16), view(lcb, (H // 2, W // 2), np.int16), view(lcr, (H // 2, W // 2), np.int16)]
+        return out
+
+    def encode_pictures(self, frames):
+        """frames: iterable of (y, cb, cr).  Returns the per-picture results in order (batches of pictures_in_flight)."""
+        results = []
+        for i, (y, cb, cr) in enumerate(frames):
+            self.submit(i, y, cb, cr)
+            if self.pending() == self.pictures_in_flight:
+                while self.pending():
+                    results.append(self.receive())
+        while self.pending():
+            results.append(self.receive())
+        return results
+
+    # ---- device-resident path (torch tensors or raw device pointers) ----
+    def search_resident(self, n_pictures, d_yuv, d_rec, d_levels, d_records, stream=None):
+        def p(t):
+            return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+        st = C.c_void_p(int(stream)) if stream else None
+        return self._check(self.L.wrenc_b200_search_resident(self.h, int(n_pictures), p(d_yuv), p(d_rec), p(d_levels), p(d_records), st))
+
+    # ---- per-block entry points ----
+    def block_predict(self, rec, x, y, w, tree, ar, bl, c, mode):
+        i420 = np.concatenate([np.ascontiguousarray(a, np.uint8).ravel() for a in rec])
+        n = w if c == 0 else w // 2
+        out = np.zeros((n, n), np.uint8)
+        self._check(self.L.wrenc_b200_block_predict(self.h, _ptr(i420), x, y, w, tree, int(ar), int(bl), c, mode, _ptr(out)))
+        return out
+
+    def _block16(self, fn, blocks):
+        b = np.ascontiguousarray(blocks, np.int16)
+        if b.ndim == 2:
+            b = b[None]
+        n = b.shape[-1]
+        out = np.zeros_like(b)
+        self._check(fn(self.h, _ptr(b), int(np.log2(n)), b.shape[0], _ptr(out)))
+        return out
+
+    def block_fwd_dct(self, res):
+        return self._block16(self.L.wrenc_b200_block_fwd_dct, res)
+
+    def block_inv_dct(self, deq):
+        return self._block16(self.L.wrenc_b200_block_inv_dct, deq)
+
+    def block_dequantize(self, lev):
+        return self._block16(self.L.wrenc_b200_block_dequantize, lev)
+
+    def block_quantize(self, coef):
+        b = np.ascontiguousarray(coef, np.int16)
+        if b.ndim == 2:
+            b = b[None]
+        n = b.shape[-1]
+        out = np.zeros_like(b)
+        rates = np.zeros(b.shape[0], np.int32)
+        self._check(self.L.wrenc_b200_block_quantize(self.h, _ptr(b), int(np.log2(n)), b.shape[0], _ptr(out), _ptr(rates)))
+        return out, rates
