@@ -95,6 +95,12 @@ typedef struct {
     int64_t lv[8], dq[8];
 } wrenc_b200_consts;
 int wrenc_b200_get_consts(const wrenc_b200 *h, wrenc_b200_consts *out);
+/* The same derivation without a handle or a GPU (pure host code), plus the header-bit tables
+ * ((bits * 16384.0) as i64; src/block_splitter.rs:377-406,695-712): hdr_single[67][4] indexed [luma kind][cclm kind],
+ * hdr_dual[67], hdr_chroma[4]; luma kind 0 = planar, 1..5 = MPM index 0..4, 6..66 = MPM remainder 0..60;
+ * cclm kind 0 = not CCLM, 1..3 = cclm_mode_idx 0..2.  Any table pointer may be NULL. */
+int wrenc_b200_derive_consts(int32_t qp, const char *extra_params, wrenc_b200_consts *out, int64_t *hdr_single, int64_t *hdr_dual,
+                             int64_t *hdr_chroma);
 
 /* Per-block entry points (host pointers): the block operations of the search, exposed for bit-exactness tests against
  * IntraPredictor::predict (src/intra_predictor.rs:56-144), Transformer::transform / inverse_transform
@@ -107,6 +113,10 @@ int wrenc_b200_block_fwd_dct(wrenc_b200 *h, const int16_t *res, int log2n, int c
 int wrenc_b200_block_inv_dct(wrenc_b200 *h, const int16_t *deq, int log2n, int count, int16_t *out);
 int wrenc_b200_block_quantize(wrenc_b200 *h, const int16_t *coef, int log2n, int count, int16_t *levels, int32_t *rates);
 int wrenc_b200_block_dequantize(wrenc_b200 *h, const int16_t *levels, int log2n, int count, int16_t *out);
+
+/* INT32 multiply-add issue rate of the device, measured with independent IMAD chains on every SM (the roofline
+ * denominator of SURVEY.md §8d; one multiply-add = 2 integer ops). */
+int wrenc_b200_measure_int32_peak(int device, double *imad_per_s);
 
 const char *wrenc_b200_version(void);
 

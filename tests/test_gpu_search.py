@@ -1,0 +1,129 @@
+"""GPU (-m gpu): the CUDA search, called through the C ABI, is bit-exact against the oracle / the committed golden
+fixtures: reconstruction, quantised levels, split decisions, modes and the f32 RD cost of every CTU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import wrenc_b200
+from oracle_lib import Oracle
+
+pytestmark = pytest.mark.gpu
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def assert_same(o, r, what=""):
+    for c in range(3):
+        assert np.array_equal(o["rec"][c], r["rec"][c]), f"{what}: reconstruction differs (component {c})"
+        assert np.array_equal(o["coef"][c], r["coef"][c]), f"{what}: levels differ (component {c})"
+    a, b = o["records"], r["records"]
+    assert np.array_equal(a["split_mask"], b["split_mask"]), what
+    assert np.array_equal(a["luma_mode"], b["luma_mode"]) and np.array_equal(a["chroma_mode"], b["chroma_mode"]), what
+    assert a["cost"].tobytes() == b["cost"].tobytes(), f"{what}: f32 RD cost differs"
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_golden_fixtures(path):
+    g = np.load(path)
+    H, W = g["y"].shape
+    enc = wrenc_b200.SearchEncoder(W, H, qp=int(g["qp"]), max_split_depth=int(g["depth"]), pictures_in_flight=1, extra_params=str(g["extra"]) or None)
+    r = enc.encode_pictures([(g["y"], g["cb"], g["cr"])])[0]
+    enc.close()
+    o = {"rec": [g["rec_y"], g["rec_cb"], g["rec_cr"]], "coef": [g["coef_y"], g["coef_cb"], g["coef_cr"]],
+         "records": g["records"].view(wrenc_b200.RECORD_DTYPE)}
+    assert_same(o, r, os.path.basename(path))
+
+
+def test_cif_two_frames_qp32():
+    """BASELINE.json configs[0] shape (352x288, QP32, default depth), synthetic content; 2 of the 30 frames."""
+    frames = [wrenc_b200.synth_frame(352, 288, frame=f) for f in (0, 17)]
+    enc = wrenc_b200.SearchEncoder(352, 288, qp=32, pictures_in_flight=2)
+    res = enc.encode_pictures(frames)
+    ora = Oracle(32, 3)
+    for i, (f, r) in enumerate(zip(frames, res)):
+        assert_same(ora.encode_picture(*f), r, f"frame {i}")
+    enc.close()
+
+
+@pytest.mark.parametrize("qp", [22, 27, 37])
+def test_qp_sweep(qp):
+    """BASELINE.json configs[1]: QP sweep with dependent quantisation."""
+    f = wrenc_b200.synth_frame(160, 96, seed=0xB2000001, frame=qp)
+    enc = wrenc_b200.SearchEncoder(160, 96, qp=qp, pictures_in_flight=1)
+    r = enc.encode_pictures([f])[0]
+    enc.close()
+    assert_same(Oracle(qp, 3).encode_picture(*f), r, f"qp {qp}")
+
+
+def test_random_and_flat_content_and_batching_independence():
+    frames = [wrenc_b200.random_frame(128, 96, 1), wrenc_b200.synth_frame(128, 96, frame=3),
+              (np.zeros((96, 128), np.uint8), np.full((48, 64), 255, np.uint8), np.full((48, 64), 1, np.uint8)),
+              wrenc_b200.random_frame(128, 96, 2)]
+    ora = Oracle(32, 3)
+    want = [ora.encode_picture(*f) for f in frames]
+    for inflight in (1, 3, 4):
+        enc = wrenc_b200.SearchEncoder(128, 96, qp=32, pictures_in_flight=inflight)
+        res = enc.encode_pictures(frames)
+        enc.close()
+        assert [r["pic_idx"] for r in res] == [0, 1, 2, 3]
+        for i, (o, r) in enumerate(zip(want, res)):
+            assert_same(o, r, f"in flight {inflight}, frame {i}")
+
+
+def test_single_ctu_and_single_row_and_single_column_pictures():
+    for (W, H) in ((32, 32), (128, 32), (32, 128)):
+        f = wrenc_b200.synth_frame(W, H, frame=W + H)
+        enc = wrenc_b200.SearchEncoder(W, H, qp=32, pictures_in_flight=1)
+        r = enc.encode_pictures([f])[0]
+        enc.close()
+        assert_same(Oracle(32, 3).encode_picture(*f), r, f"{W}x{H}")
+
+
+def test_api_errors():
+    enc = wrenc_b200.SearchEncoder(64, 64, qp=32, pictures_in_flight=1)
+    with pytest.raises(wrenc_b200.WrencB200Error):
+        enc.receive()  # nothing submitted
+    f = wrenc_b200.synth_frame(64, 64)
+    enc.submit(7, *f)
+    with pytest.raises(wrenc_b200.WrencB200Error):
+        enc.submit(8, *f)  # pictures_in_flight exceeded
+    assert enc.receive()["pic_idx"] == 7
+    enc.close()
+
+
+def test_full_size_properties_1080p():
+    """1920x1088 (BASELINE.json configs[2] geometry): the oracle takes ~25 s per frame, so parity is checked on the top-left
+    640x352 region of the picture searched as its own picture, and the full size through size-independent properties:
+    determinism across launches / batch positions, and split-mask / mode-map consistency of every CTU record."""
+    y, cb, cr = wrenc_b200.synth_frame(1920, 1088, seed=0xB2000002, frame=0)
+    enc = wrenc_b200.SearchEncoder(1920, 1088, qp=32, pictures_in_flight=2)
+    a, b = enc.encode_pictures([(y, cb, cr), (y, cb, cr)])
+    c = enc.encode_pictures([(y, cb, cr)])[0]
+    enc.close()
+    for other in (b, c):
+        assert_same(a, other, "determinism")
+    rec = a["records"]
+    assert len(rec) == 60 * 34
+    for r in rec:
+        m = int(r["split_mask"])
+        lm = r["luma_mode"].reshape(8, 8)
+        if not (m & 1):
+            assert m == 0 and (lm == lm[0, 0]).all()
+        for i in range(4):
+            if not (m >> (1 + i)) & 1:
+                assert ((m >> (5 + 4 * i)) & 15) == 0
+                if m & 1:
+                    blk = lm[(i >> 1) * 4:(i >> 1) * 4 + 4, (i & 1) * 4:(i & 1) * 4 + 4]
+                    assert (blk == blk[0, 0]).all()
+        assert (lm <= 66).all() and np.isin(r["chroma_mode"], list(range(67)) + [81, 82, 83]).all() and np.isfinite(r["cost"])
+    # PSNR sanity of the full frame
+    mse = ((a["rec"][0].astype(float) - y) ** 2).mean()
+    assert 10 * np.log10(255 ** 2 / mse) > 28
+    # parity on a sub-picture the oracle finishes in a few seconds
+    sw, sh = 640, 352
+    sub = (y[:sh, :sw].copy(), cb[:sh // 2, :sw // 2].copy(), cr[:sh // 2, :sw // 2].copy())
+    enc = wrenc_b200.SearchEncoder(sw, sh, qp=32, pictures_in_flight=1)
+    r = enc.encode_pictures([sub])[0]
+    enc.close()
+    assert_same(Oracle(32, 3).encode_picture(*sub), r, "640x352 sub-picture")

@@ -1,0 +1,109 @@
+"""CPU: pins the oracle (oracle/) with the known-answer values of SURVEY.md §5.9-H4, VVC spec identities and the committed
+golden fixtures.  The reference holds no golden vectors for this path: parity is 'unpinned' beyond these."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from oracle_lib import Oracle
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("qp,lrd,lq,ls", [(22, 35.980415, 34, 9216), (27, 79.03267, 56, 16384), (32, 173.59894, 100, 29184), (37, 381.31808, 184, 52224)])
+def test_libm_constants(qp, lrd, lq, ls):
+    c = Oracle(qp).consts()
+    assert c["lambda_rd"] == np.float32(lrd)
+    assert c["lambda_q"] == lq and c["ls"] == ls
+    assert c["dq"].tolist() == [0, 128, 181, 222, 257, 287, 314, 340]
+    assert c["lv"].tolist() == [6548, 17546, 23774, 28619, 32720, 36338, 39610, 42618]
+
+
+def test_dct_matrix_is_the_vvc_table():
+    t4 = oracle_lib.dct_matrix(2)
+    assert t4.tolist() == [[64, 64, 64, 64], [83, 36, -36, -83], [64, -64, -64, 64], [36, -83, 83, -36]]
+    t8 = oracle_lib.dct_matrix(3)
+    assert t8[1].tolist() == [89, 75, 50, 18, -18, -50, -75, -89]
+    t32 = oracle_lib.dct_matrix(5)
+    assert t32[1, :4].tolist() == [90, 90, 88, 85] and t32[31, 0] == 4
+    for l2 in (2, 3, 4, 5):  # sub-sampling identity T_N[i][x] = T_32[i*32/N][x-th odd multiple]: rows are near-orthogonal
+        t = oracle_lib.dct_matrix(l2).astype(np.int64)
+        g = t @ t.T
+        n = 1 << l2
+        assert np.all(np.abs(g - np.diag(np.diag(g))) <= 4096 * n // 100)
+        assert np.all(np.abs(np.diag(g) - 4096 * n) <= 4096 * n // 50)
+
+
+def test_scan_is_subblock_diagonal():
+    s = oracle_lib.scan(3)
+    pos = [(int(v) & 255, int(v) >> 8) for v in s]  # (x, y)
+    assert pos[:6] == [(0, 0), (0, 1), (1, 0), (0, 2), (1, 1), (2, 0)]
+    assert pos[16] == (0, 4) and pos[32] == (4, 0) and pos[48] == (4, 4)
+    assert sorted(pos) == sorted((x, y) for x in range(8) for y in range(8))
+
+
+def test_transform_round_trip_and_dequant(oracle32):
+    rng = np.random.default_rng(0)
+    for n in (4, 8, 16, 32):
+        res = rng.integers(-60, 61, (n, n)).astype(np.int16)
+        coef = oracle32.fwd_dct(res)
+        # with a unit quantiser the inverse of the forward transform reproduces the residual up to rounding
+        sh = int(np.log2(n)) + 4
+        # emulate "dequantised" coefficients = coefficients (skip quantisation)
+        back = oracle32.inv_dct(coef)
+        assert np.abs(back.astype(int) - res).max() <= 2, n
+        q = np.zeros((n, n), np.int16); q[0, 0] = 3; q[1, 0] = -2
+        d = oracle32.dequantize(q)
+        assert d[0, 0] == (3 * 29184 + (1 << (sh - 1))) >> sh and d[1, 0] == (-2 * 29184 + (1 << (sh - 1))) >> sh
+
+
+def test_trellis_properties(oracle32):
+    for n in (4, 8, 16, 32):
+        z = np.zeros((n, n), np.int16)
+        assert not oracle32.quantize(z).any() and oracle32.rate(z) == 0
+    # a single large DC coefficient quantises to a level whose reconstruction is within one step
+    c = np.zeros((8, 8), np.int16); c[0, 0] = 500
+    q = oracle32.quantize(c)
+    assert q[0, 0] != 0 and abs(int(oracle32.dequantize(q)[0, 0]) - 500) <= 29184 // 128 + 1
+    assert not q.flatten()[1:].any()
+    # sign symmetry is NOT exact (asymmetric rounding, H2) but magnitudes stay within one level
+    q2 = oracle32.quantize(-c)
+    assert abs(abs(int(q2[0, 0])) - abs(int(q[0, 0]))) <= 1
+
+
+def test_h3_dc_wrap_is_reachable_and_signed(oracle32):
+    """H3: at the DC leaf with state > 1 and a0 == 0 the reference's usize arithmetic yields q = -1 (sign-flipped for tc < 0)."""
+    rng = np.random.default_rng(3)
+    seen = 0
+    for _ in range(300):
+        c = (rng.normal(0, 700, (4, 4))).astype(np.int16)
+        c[0, 0] = rng.integers(-40, 41)
+        q = oracle32.quantize(c)
+        d = int(oracle32.dequantize(q)[0, 0])
+        if c[0, 0] != 0 and q[0, 0] != 0 and np.sign(q[0, 0]) != np.sign(c[0, 0]):
+            seen += 1
+            assert abs(int(q[0, 0])) == 1 and abs(d) <= 29184 // 64 + 1
+    assert seen > 0
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_matches_golden(path):
+    g = np.load(path)
+    o = Oracle(int(g["qp"]), int(g["depth"]), str(g["extra"]) or None).encode_picture(g["y"], g["cb"], g["cr"])
+    for c, k in enumerate(("y", "cb", "cr")):
+        assert np.array_equal(o["rec"][c], g["rec_" + k])
+        assert np.array_equal(o["coef"][c], g["coef_" + k])
+    assert o["records"].tobytes() == g["records"].tobytes()
+
+
+def test_oracle_reconstruction_is_plausible():
+    from wrenc_b200.synth import synth_frame
+    y, cb, cr = synth_frame(96, 64, frame=0)
+    psnr = []
+    for qp in (22, 37):
+        o = Oracle(qp).encode_picture(y, cb, cr)
+        mse = ((o["rec"][0].astype(float) - y) ** 2).mean()
+        psnr.append(10 * np.log10(255 ** 2 / mse))
+    assert psnr[0] > psnr[1] + 4 and psnr[1] > 25

@@ -322,6 +322,23 @@ int wrenc_b200_get_consts(const wrenc_b200 *h, wrenc_b200_consts *out) {
     return WRENC_B200_OK;
 }
 
+int wrenc_b200_derive_consts(int32_t qp, const char *extra_params, wrenc_b200_consts *out, int64_t *hdr_single /*67*4 or NULL*/,
+                             int64_t *hdr_dual /*67 or NULL*/, int64_t *hdr_chroma /*4 or NULL*/) {
+    if (!out || qp < 0 || qp > 63) return WRENC_B200_EINVAL;
+    Tuning t;
+    HostConsts hc;
+    if (!t.parse(extra_params, g_create_err) || !hc.init(qp, t, g_create_err)) return WRENC_B200_EINVAL;
+    out->lambda_q = hc.lambda_q;
+    out->lambda_rd = hc.t.lambda_rd;
+    out->lambda_rd_chroma = hc.t.lambda_rd_c;
+    out->ls = hc.t.ls;
+    for (int i = 0; i < 8; i++) { out->lv[i] = hc.lv64[i]; out->dq[i] = hc.dq64[i]; }
+    if (hdr_single) for (int i = 0; i < 67; i++) for (int j = 0; j < 4; j++) hdr_single[i * 4 + j] = hc.t.hdr_single[i][j];
+    if (hdr_dual) for (int i = 0; i < 67; i++) hdr_dual[i] = hc.t.hdr_dual[i];
+    if (hdr_chroma) for (int i = 0; i < 4; i++) hdr_chroma[i] = hc.t.hdr_chroma[i];
+    return WRENC_B200_OK;
+}
+
 // ---- per-block entry points (host pointers; parity tests of the block kernels) ----
 static int run_block(wrenc_b200 *h, BlockParams &P, const void *in, size_t in_bytes, void *out, size_t out_bytes, int *outi, int n_outi, bool is_pred) {
     CK(cudaSetDevice(h->cfg.device));

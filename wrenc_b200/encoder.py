@@ -23,6 +23,7 @@ EXPORTS = [
     "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident",
     "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
+    "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts",
 ]
 
 
@@ -85,8 +86,33 @@ def load_library():
     L.wrenc_b200_block_quantize.restype = C.c_int
     L.wrenc_b200_block_quantize.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.wrenc_b200_version.restype = C.c_char_p
+    L.wrenc_b200_derive_consts.restype = C.c_int
+    L.wrenc_b200_derive_consts.argtypes = [C.c_int32, C.c_char_p, C.POINTER(Consts), vp, vp, vp]
+    L.wrenc_b200_measure_int32_peak.restype = C.c_int
+    L.wrenc_b200_measure_int32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
+
+
+def measure_int32_peak(device=0):
+    """IMAD/s of the device (wrenc_b200_measure_int32_peak)."""
+    v = C.c_double()
+    rc = load_library().wrenc_b200_measure_int32_peak(int(device), C.byref(v))
+    if rc != 0:
+        raise WrencB200Error(f"wrenc_b200_measure_int32_peak failed ({rc})")
+    return v.value
+
+
+def derive_consts(qp, extra_params=None):
+    """Host-only derivation of the search constants (no GPU needed): wrenc_b200_derive_consts."""
+    c = Consts()
+    hs, hd, hc = np.zeros((67, 4), np.int64), np.zeros(67, np.int64), np.zeros(4, np.int64)
+    rc = load_library().wrenc_b200_derive_consts(int(qp), extra_params.encode() if extra_params else None, C.byref(c),
+                                                 hs.ctypes.data_as(C.c_void_p), hd.ctypes.data_as(C.c_void_p), hc.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise ValueError(f"wrenc_b200_derive_consts failed ({rc})")
+    return dict(lambda_q=c.lambda_q, lambda_rd=c.lambda_rd, lambda_rd_chroma=c.lambda_rd_chroma, ls=c.ls,
+                lv=np.array(list(c.lv), np.int64), dq=np.array(list(c.dq), np.int64), hdr_single=hs, hdr_dual=hd, hdr_chroma=hc)
 
 
 def _ptr(a):
