@@ -175,7 +175,10 @@ def run_ours(args):
 
     enc = wrenc_b200.SearchEncoder(W, H, qp=QP, max_split_depth=DEPTH, device=local, pictures_in_flight=args.e2e_batch,
                                    want_recon=False, want_decisions=True)
-    stream = torch.cuda.current_stream().cuda_stream
+    tstream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: its handle goes through the C ABI
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
 
     def step():
         return enc.search_resident(F, d_yuv, d_rec, d_lev, d_records, stream)

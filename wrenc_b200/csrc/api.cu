@@ -2,6 +2,7 @@
 // Host-side counterpart of the reference's per-picture driver (src/main.rs:294-402) for the part that moves behind the FFI.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -79,8 +80,15 @@ static int ensure_workspace(wrenc_b200 *h, int n_pics) {
 static int ensure_items(wrenc_b200 *h, int n_pics) {
     if (h->items_for == n_pics) return 0;
     const int Wc = h->Wc, Hc = h->Hc;
-    const double target = 1.5 * h->grid;
-    const double stagger = std::max(0.0, (double)Wc * Hc / target);
+    // Items of one key level never depend on each other; an item of level K+1 depends on two level-K items of its own
+    // picture.  With `factor` x grid items per level those were handed out (factor-1) CTU latencies earlier, so nobody
+    // waits.  All pictures in lockstep (stagger 0) gives the widest levels; pictures are staggered only when there are so
+    // many that a level would exceed factor x grid items (keeps the live working set of pictures bounded).
+    double factor = 8.0;
+    if (const char *e = getenv("WRENC_B200_LEVEL_FACTOR")) factor = atof(e) > 0 ? atof(e) : factor;
+    const double avg_diag = (double)Wc * Hc / (Wc + 2 * Hc);
+    double stagger = 0.0;
+    if (n_pics * avg_diag > factor * h->grid) stagger = (double)Wc * Hc / (factor * h->grid);
     struct It { int key, pic, cy, cx; };
     std::vector<It> v;
     v.reserve((size_t)n_pics * Wc * Hc);

@@ -1,5 +1,6 @@
 // search.cu — CTU tree search kernel (persistent, wavefront work list) + launch wrapper.  See search_kernel.cuh.
 #include <cfloat>
+#include <cstdlib>
 
 #include "search_kernel.cuh"
 
@@ -15,26 +16,26 @@ __device__ __forceinline__ long long luma_hdr(const Shared &S, const DevTables *
 
 __device__ __forceinline__ void fill_lm(Shared &S, const Node &nd, int mode, int tid) {
     int cells = nd.w >> 2;
-    if (tid < cells * cells) {
-        int yy = tid / cells, xx = tid - yy * cells;
+    for (int i = tid; i < cells * cells; i += NTHREADS) {
+        int yy = i / cells, xx = i - yy * cells;
         S.lm[((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx] = (uint8_t)mode;
     }
 }
 __device__ __forceinline__ void fill_cm(Shared &S, const Node &nd, int mode, int tid) {
     int cells = nd.w >> 3;
-    if (tid < cells * cells) {
-        int yy = tid / cells, xx = tid - yy * cells;
+    for (int i = tid; i < cells * cells; i += NTHREADS) {
+        int yy = i / cells, xx = i - yy * cells;
         S.cm[((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx] = (uint8_t)mode;
     }
 }
 
-__device__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, const Node &nd, int &root_mode, bool is_root) {
+__device__ __noinline__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, const Node &nd, int &root_mode, bool is_root) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DevTables *tab = P.tab;
     const WarpScratch ws = warp_scratch(S, warp);
     const int ncomp = nd.tree == DUAL_TREE_LUMA ? 1 : 3;
     // ---- phase 0: reference samples
-    if (warp < ncomp) build_refs(S, g, nd, warp, lane);
+    for (int t = warp; t < ncomp; t += NW) build_refs(S, g, nd, t, lane);
     __syncthreads();
     // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs
     {
@@ -144,10 +145,10 @@ __device__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, c
     const int mode = cost_pl == min_cost ? 0 : (cost_dc == min_cost ? 1 : dir);
     if (is_root) root_mode = mode;
     // ---- phase 5: luma redo (commit) + chroma DM full evaluation (commit)
-    if (warp < ncomp) {
+    for (int t = warp; t < ncomp; t += NW) {
         unsigned ssd; int rate;
-        full_task(S, tab, g, nd, warp, mode, true, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[warp] = ssd; S.r_rate[warp] = rate; }
+        full_task(S, tab, g, nd, t, mode, true, ws, lane, ssd, rate);
+        if (lane == 0) { S.r_ssd[t] = ssd; S.r_rate[t] = rate; }
     }
     fill_lm(S, nd, mode, tid);
     __syncthreads();
@@ -156,14 +157,14 @@ __device__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, c
     const long long rateY = S.r_rate[0], rateDM = (long long)S.r_rate[1] + S.r_rate[2];
     const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
     // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
-    if (warp == 0) cclm_downsample(S, g, nd, lane);
+    if (warp == NW - 1) cclm_downsample(S, g, nd, lane);
     __syncthreads();
     // ---- phase 6: CCLM SADs in the order LT, T, L
-    if (warp < 6) {
-        const int mi = warp >> 1, c = 1 + (warp & 1);
+    for (int t = warp; t < 6; t += NW) {
+        const int mi = t >> 1, c = 1 + (t & 1);
         const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
         unsigned sad = sad_task(S, g, nd, c, cm, ws, lane);
-        if (lane == 0) S.r_sad[warp] = sad;
+        if (lane == 0) S.r_sad[t] = sad;
     }
     __syncthreads();
     int cclm_mode;
@@ -174,10 +175,10 @@ __device__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, c
         else cclm_mode = MODE_L_CCLM;
     }
     // ---- phase 7: CCLM full evaluation (no commit)
-    if (warp < 2) {
+    for (int t = warp; t < 2; t += NW) {
         unsigned ssd; int rate;
-        full_task(S, tab, g, nd, 1 + warp, cclm_mode, false, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[8 + warp] = ssd; S.r_rate[8 + warp] = rate; }
+        full_task(S, tab, g, nd, 1 + t, cclm_mode, false, ws, lane, ssd, rate);
+        if (lane == 0) { S.r_ssd[8 + t] = ssd; S.r_rate[8 + t] = rate; }
     }
     __syncthreads();
     const unsigned ssdCC = S.r_ssd[8] + S.r_ssd[9];
@@ -191,9 +192,9 @@ __device__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, c
         final_cost = rd_cost(ssdY + ssdDM, rateY + rateDM + luma_hdr(S, tab, g, nd, mode, 0, root_mode), tab->lambda_rd);
     } else {
         // ---- phase 8: commit the CCLM chroma
-        if (warp < 2) {
+        for (int t = warp; t < 2; t += NW) {
             unsigned ssd; int rate;
-            full_task(S, tab, g, nd, 1 + warp, cclm_mode, true, ws, lane, ssd, rate);
+            full_task(S, tab, g, nd, 1 + t, cclm_mode, true, ws, lane, ssd, rate);
         }
         fill_cm(S, nd, cclm_mode, tid);
         final_cost = rd_cost(ssdY + ssdCC, rateY + rateCC + luma_hdr(S, tab, g, nd, mode, ck, root_mode), tab->lambda_rd);
@@ -205,25 +206,29 @@ __device__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, c
 // ---------------------------------------------------------------------------------------------------------------
 // the 8x8 DUAL_TREE_CHROMA coding tree that follows four 4x4 luma CUs (block_splitter.rs:794-885)
 // ---------------------------------------------------------------------------------------------------------------
-__device__ float chroma_ct_eval(Shared &S, const SearchParams &P, const CtuGeom &g, const Node &nd) {
+__device__ __noinline__ float chroma_ct_eval(Shared &S, const SearchParams &P, const CtuGeom &g, const Node &nd) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DevTables *tab = P.tab;
     const WarpScratch ws = warp_scratch(S, warp);
     // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396)
     const int dm = S.lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
-    if (warp == 0 || warp == 1) build_refs(S, g, nd, 1 + warp, lane);
-    else if (warp == 2) cclm_downsample(S, g, nd, lane);
+    for (int t = warp; t < 3; t += NW) {
+        if (t < 2) build_refs(S, g, nd, 1 + t, lane);
+        else cclm_downsample(S, g, nd, lane);
+    }
     __syncthreads();
-    if (warp < 2) {
-        unsigned ssd; int rate;
-        full_task(S, tab, g, nd, 1 + warp, dm, true, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[warp] = ssd; S.r_rate[warp] = rate; }
-    } else {
-        const int u = warp - 2;
-        const int mi = u >> 1, c = 1 + (u & 1);
-        const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-        unsigned sad = sad_task(S, g, nd, c, cm, ws, lane);
-        if (lane == 0) S.r_sad[u] = sad;
+    for (int t = warp; t < 8; t += NW) {
+        if (t < 2) {
+            unsigned ssd; int rate;
+            full_task(S, tab, g, nd, 1 + t, dm, true, ws, lane, ssd, rate);
+            if (lane == 0) { S.r_ssd[t] = ssd; S.r_rate[t] = rate; }
+        } else {
+            const int u = t - 2;
+            const int mi = u >> 1, c = 1 + (u & 1);
+            const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
+            unsigned sad = sad_task(S, g, nd, c, cm, ws, lane);
+            if (lane == 0) S.r_sad[u] = sad;
+        }
     }
     __syncthreads();
     int cclm_mode;
@@ -233,10 +238,10 @@ __device__ float chroma_ct_eval(Shared &S, const SearchParams &P, const CtuGeom 
         else if (t <= l) cclm_mode = MODE_T_CCLM;
         else cclm_mode = MODE_L_CCLM;
     }
-    if (warp < 2) {
+    for (int t = warp; t < 2; t += NW) {
         unsigned ssd; int rate;
-        full_task(S, tab, g, nd, 1 + warp, cclm_mode, false, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[8 + warp] = ssd; S.r_rate[8 + warp] = rate; }
+        full_task(S, tab, g, nd, 1 + t, cclm_mode, false, ws, lane, ssd, rate);
+        if (lane == 0) { S.r_ssd[8 + t] = ssd; S.r_rate[8 + t] = rate; }
     }
     __syncthreads();
     const float cost_dm = rd_cost(S.r_ssd[0] + S.r_ssd[1], (long long)S.r_rate[0] + S.r_rate[1] + tab->hdr_chroma[0], tab->lambda_rd_c);
@@ -246,9 +251,9 @@ __device__ float chroma_ct_eval(Shared &S, const SearchParams &P, const CtuGeom 
     if (cost_dm == mn) {
         fill_cm(S, nd, dm, tid);
     } else {
-        if (warp < 2) {
+        for (int t = warp; t < 2; t += NW) {
             unsigned ssd; int rate;
-            full_task(S, tab, g, nd, 1 + warp, cclm_mode, true, ws, lane, ssd, rate);
+            full_task(S, tab, g, nd, 1 + t, cclm_mode, true, ws, lane, ssd, rate);
         }
         fill_cm(S, nd, cclm_mode, tid);
     }
@@ -263,7 +268,7 @@ __device__ float chroma_ct_eval(Shared &S, const SearchParams &P, const CtuGeom 
 __device__ __forceinline__ int sv_off_y(int d) { return d == 0 ? 0 : (d == 1 ? 1024 : 1280); }
 __device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 256 : 320); }
 
-__device__ void save_node(Shared &S, const Node &nd, int d, int tid) {
+__device__ __noinline__ void save_node(Shared &S, const Node &nd, int d, int tid) {
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i / w, x = i - y * w;
@@ -277,10 +282,10 @@ __device__ void save_node(Shared &S, const Node &nd, int d, int tid) {
         S.svRecC[c][oc + j] = RC(S, 1 + c, bx + x, by + y);
         S.svLvC[c][oc + j] = S.lvC[c][(by + y) * 16 + bx + x];
     }
-    if (tid < 64) S.svLm[d][tid] = S.lm[tid];
-    if (tid < 16) S.svCm[d][tid] = S.cm[tid];
+    for (int i = tid; i < 64; i += NTHREADS) S.svLm[d][i] = S.lm[i];
+    for (int i = tid; i < 16; i += NTHREADS) S.svCm[d][i] = S.cm[i];
 }
-__device__ void restore_node(Shared &S, const Node &nd, int d, int tid) {
+__device__ __noinline__ void restore_node(Shared &S, const Node &nd, int d, int tid) {
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i / w, x = i - y * w;
@@ -295,14 +300,14 @@ __device__ void restore_node(Shared &S, const Node &nd, int d, int tid) {
         S.lvC[c][(by + y) * 16 + bx + x] = S.svLvC[c][oc + j];
     }
     const int cells = w >> 2;
-    if (tid < cells * cells) {
-        int yy = tid / cells, xx = tid - yy * cells;
+    for (int i = tid; i < cells * cells; i += NTHREADS) {
+        int yy = i / cells, xx = i - yy * cells;
         int idx = ((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx;
         S.lm[idx] = S.svLm[d][idx];
     }
     const int cc = w >> 3;
-    if (tid < cc * cc) {
-        int yy = tid / cc, xx = tid - yy * cc;
+    for (int i = tid; i < cc * cc; i += NTHREADS) {
+        int yy = i / cc, xx = i - yy * cc;
         int idx = ((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx;
         S.cm[idx] = S.svCm[d][idx];
     }
@@ -452,7 +457,7 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
             y = x; x = 0;
         }
     }
-    if (tid < 64) { S.tb.ldq[tid] = tab->ldq[tid]; S.tb.lv[tid] = tab->lv[tid]; }
+    for (int i = tid; i < 64; i += NTHREADS) { S.tb.ldq[i] = tab->ldq[i]; S.tb.lv[i] = tab->lv[i]; }
     if (tid < 32) {
         unsigned pk = 0;
         for (int i = 0; i < 4; i++) pk |= ((unsigned)(uint8_t)c_fC[tid][i]) << (8 * i);
@@ -460,14 +465,14 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
     }
 }
 
-__device__ __forceinline__ int ld_acquire(const int *p) {
+__device__ __forceinline__ int ld_relaxed(const int *p) {  // polling load: no L1 invalidation per poll (the acquire fence follows the loop)
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-extern "C" __global__ void __launch_bounds__(NTHREADS, 2) wrenc_b200_search_kernel(SearchParams P) {
+extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_search_kernel(SearchParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared &S = *reinterpret_cast<Shared *>(smem_raw);
     const int tid = threadIdx.x;
@@ -488,21 +493,24 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) wrenc_b200_search_kern
         int *done = P.done + (size_t)pic * Wc * P.Hc;
         // wavefront dependencies: left CTU and above-right CTU (above when in the last column) must be final
         if (tid == 0) {
-            if (cxi > 0) while (ld_acquire(&done[cyi * Wc + cxi - 1]) != P.epoch) __nanosleep(200);
+            if (cxi > 0) while (ld_relaxed(&done[cyi * Wc + cxi - 1]) != P.epoch) __nanosleep(1000);
             if (cyi > 0) {
                 const int ax = min(cxi + 1, Wc - 1);
-                while (ld_acquire(&done[(cyi - 1) * Wc + ax]) != P.epoch) __nanosleep(200);
+                while (ld_relaxed(&done[(cyi - 1) * Wc + ax]) != P.epoch) __nanosleep(1000);
             }
+            __threadfence();  // acquire side: order the halo loads after the flag observation
         }
         __syncthreads();
         const uint8_t *oY = P.orig + (size_t)pic * pic_samples, *oCb = oY + (size_t)W * H, *oCr = oCb + (size_t)cw * chh;
         uint8_t *rY = P.rec + (size_t)pic * pic_samples, *rCb = rY + (size_t)W * H, *rCr = rCb + (size_t)cw * chh;
         // ---- stage the CTU: source samples, neighbouring reconstruction, left-CTU modes
         {
-            int y = tid >> 3, x4 = (tid & 7) * 4;  // 32 rows x 8 words
-            *reinterpret_cast<uint32_t *>(&S.orgY[y * 32 + x4]) = __ldg(reinterpret_cast<const uint32_t *>(oY + (size_t)(g.cy + y) * W + g.cx + x4));
-            if (tid < 128) {
-                int c = tid >> 6, t = tid & 63, yy = t >> 2, xx = (t & 3) * 4;
+            for (int i = tid; i < 256; i += NTHREADS) {  // 32 rows x 8 words
+                int y = i >> 3, x4 = (i & 7) * 4;
+                *reinterpret_cast<uint32_t *>(&S.orgY[y * 32 + x4]) = __ldg(reinterpret_cast<const uint32_t *>(oY + (size_t)(g.cy + y) * W + g.cx + x4));
+            }
+            for (int i = tid; i < 128; i += NTHREADS) {
+                int c = i >> 6, t = i & 63, yy = t >> 2, xx = (t & 3) * 4;
                 const uint8_t *src = (c ? oCr : oCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx;
                 *reinterpret_cast<uint32_t *>(&S.orgC[c][yy * 16 + xx]) = __ldg(reinterpret_cast<const uint32_t *>(src));
             }
@@ -528,9 +536,9 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) wrenc_b200_search_kern
             }
             if (tid < 8) S.leftModes[tid] = g.cx > 0 ? __ldcg(P.mode_map + (size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + tid) * (W >> 2) + (g.cx >> 2) - 1) : 0;
             for (int i = tid; i < 1024; i += NTHREADS) S.lvY[i] = 0;
-            for (int i = tid; i < 512; i += NTHREADS) S.lvC[0][i] = 0;
-            if (tid < 64) S.lm[tid] = 0;
-            if (tid < 16) S.cm[tid] = 0;
+            for (int i = tid; i < 256; i += NTHREADS) { S.lvC[0][i] = 0; S.lvC[1][i] = 0; }
+            for (int i = tid; i < 64; i += NTHREADS) S.lm[i] = 0;
+            for (int i = tid; i < 16; i += NTHREADS) S.cm[i] = 0;
         }
         __syncthreads();
         unsigned split_mask;
@@ -539,31 +547,33 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 2) wrenc_b200_search_kern
         __syncthreads();
         // ---- write back: reconstruction, levels, modes, record
         {
-            int y = tid >> 3, x4 = (tid & 7) * 4;
-            uint32_t v = (uint32_t)RY(S, x4, y) | ((uint32_t)RY(S, x4 + 1, y) << 8) | ((uint32_t)RY(S, x4 + 2, y) << 16) | ((uint32_t)RY(S, x4 + 3, y) << 24);
-            *reinterpret_cast<uint32_t *>(rY + (size_t)(g.cy + y) * W + g.cx + x4) = v;
-            if (tid < 128) {
-                int c = tid >> 6, t = tid & 63, yy = t >> 2, xx = (t & 3) * 4;
+            for (int i = tid; i < 256; i += NTHREADS) {
+                int y = i >> 3, x4 = (i & 7) * 4;
+                uint32_t v = (uint32_t)RY(S, x4, y) | ((uint32_t)RY(S, x4 + 1, y) << 8) | ((uint32_t)RY(S, x4 + 2, y) << 16) | ((uint32_t)RY(S, x4 + 3, y) << 24);
+                *reinterpret_cast<uint32_t *>(rY + (size_t)(g.cy + y) * W + g.cx + x4) = v;
+            }
+            for (int i = tid; i < 128; i += NTHREADS) {
+                int c = i >> 6, t = i & 63, yy = t >> 2, xx = (t & 3) * 4;
                 uint32_t u = (uint32_t)RC(S, 1 + c, xx, yy) | ((uint32_t)RC(S, 1 + c, xx + 1, yy) << 8) | ((uint32_t)RC(S, 1 + c, xx + 2, yy) << 16) |
                              ((uint32_t)RC(S, 1 + c, xx + 3, yy) << 24);
                 *reinterpret_cast<uint32_t *>((c ? rCr : rCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx) = u;
             }
             int16_t *lY = P.lev + (size_t)pic * pic_samples, *lCb = lY + (size_t)W * H, *lCr = lCb + (size_t)cw * chh;
-            for (int i = tid; i < 512; i += NTHREADS) {  // luma levels, 2 per thread-iteration
+            for (int i = tid; i < 512; i += NTHREADS) {  // luma levels, 2 per iteration
                 int yy = i >> 4, xx = (i & 15) * 2;
                 *reinterpret_cast<uint32_t *>(lY + (size_t)(g.cy + yy) * W + g.cx + xx) = *reinterpret_cast<const uint32_t *>(&S.lvY[yy * 32 + xx]);
             }
-            {
-                int c = tid >> 7, t = tid & 127, yy = t >> 3, xx = (t & 7) * 2;
+            for (int i = tid; i < 256; i += NTHREADS) {
+                int c = i >> 7, t = i & 127, yy = t >> 3, xx = (t & 7) * 2;
                 *reinterpret_cast<uint32_t *>((c ? lCr : lCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx) =
                     *reinterpret_cast<const uint32_t *>(&S.lvC[c][yy * 16 + xx]);
             }
             CtuRecord *r = P.records + (size_t)pic * Wc * P.Hc + cyi * Wc + cxi;
-            if (tid < 64) {
-                r->luma_mode[tid] = S.lm[tid];
-                P.mode_map[(size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + (tid >> 3)) * (W >> 2) + (g.cx >> 2) + (tid & 7)] = S.lm[tid];
+            for (int i = tid; i < 64; i += NTHREADS) {
+                r->luma_mode[i] = S.lm[i];
+                P.mode_map[(size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + (i >> 3)) * (W >> 2) + (g.cx >> 2) + (i & 7)] = S.lm[i];
             }
-            if (tid < 16) r->chroma_mode[tid] = S.cm[tid];
+            for (int i = tid; i < 16; i += NTHREADS) r->chroma_mode[i] = S.cm[i];
             if (tid == 0) { r->split_mask = split_mask; r->cost = cost; }
         }
         __threadfence();
@@ -653,21 +663,27 @@ cudaError_t launch_block(const BlockParams &P, int grid, cudaStream_t stream) {
 
 size_t search_smem_bytes() { return sizeof(Shared); }
 
+static size_t smem_request() {  // dev-time knob: WRENC_B200_SMEM_PAD bytes of extra dynamic shared memory lower the CTAs per SM
+    size_t pad = 0;
+    if (const char *e = getenv("WRENC_B200_SMEM_PAD")) pad = (size_t)atol(e);
+    return sizeof(Shared) + pad;
+}
+
 cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wrenc_b200_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
+        cudaError_t e = cudaFuncSetAttribute(wrenc_b200_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    wrenc_b200_search_kernel<<<grid, NTHREADS, sizeof(Shared), stream>>>(P);
+    wrenc_b200_search_kernel<<<grid, NTHREADS, smem_request(), stream>>>(P);
     return cudaGetLastError();
 }
 
 int search_ctas_per_sm() {
     int n = 0;
-    cudaFuncSetAttribute(wrenc_b200_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Shared));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wrenc_b200_search_kernel, NTHREADS, sizeof(Shared));
+    cudaFuncSetAttribute(wrenc_b200_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request());
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, wrenc_b200_search_kernel, NTHREADS, smem_request());
     return n;
 }
 

@@ -23,9 +23,15 @@
 
 namespace wb {
 
-constexpr int NW = 8;        // warps per CTA
+#ifndef WB_NW
+#define WB_NW 8
+#endif
+#ifndef WB_MINB
+#define WB_MINB 2
+#endif
+constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
-constexpr int NBIG = 3;      // warps with scratch large enough for a 32x32 luma pipeline
+constexpr int NBIG = NW < 3 ? NW : 3;  // warps with scratch large enough for a 32x32 luma pipeline (those tasks are listed first)
 
 enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
 enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
@@ -109,9 +115,9 @@ struct Shared {
     int16_t bigA[NBIG][1024], bigB[NBIG][1024];
     uint16_t bigW[NBIG][1024];
     uint8_t bigP[NBIG][1024];
-    int16_t smA[NW - NBIG][256], smB[NW - NBIG][256];
-    uint16_t smW[NW - NBIG][256];
-    uint8_t smP[NW - NBIG][256];
+    int16_t smA[NW - NBIG + 1][256], smB[NW - NBIG + 1][256];
+    uint16_t smW[NW - NBIG + 1][256];
+    uint8_t smP[NW - NBIG + 1][256];
     int16_t refx[NW][100];
 };
 
@@ -167,7 +173,7 @@ __device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float la
 // ---------------------------------------------------------------------------------------------------------------
 // reference samples (intra_predictor.rs:146-353), one warp per component
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void build_refs(Shared &S, const CtuGeom &g, const Node &nd, int c, int lane) {
+__device__ __noinline__ void build_refs(Shared &S, const CtuGeom &g, const Node &nd, int c, int lane) {
     const int cs = c != 0;
     const int n = nd.w >> cs, xt = nd.x >> cs, yt = nd.y >> cs;
     const int nl = 2 * n + 1, na = 2 * n, tot = nl + na;
@@ -285,7 +291,7 @@ __device__ __forceinline__ int cclm_ds6(Shared &S, int bx, int by, bool avail_l,
 }
 
 // down-sampled luma of the node (intra_predictor.rs:1854-1868), one warp
-__device__ void cclm_downsample(Shared &S, const CtuGeom &g, const Node &nd, int lane) {
+__device__ __noinline__ void cclm_downsample(Shared &S, const CtuGeom &g, const Node &nd, int lane) {
     Node tmp = nd;
     bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
     int tw = nd.w >> 1;
@@ -296,7 +302,7 @@ __device__ void cclm_downsample(Shared &S, const CtuGeom &g, const Node &nd, int
 }
 
 // derive (a,k,b) for one CCLM mode / component (intra_predictor.rs:1604-2031); uniform across the warp
-__device__ void cclm_params(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, PredCtx &pc) {
+__device__ __noinline__ void cclm_params(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, PredCtx &pc) {
     const int tw = nd.w >> 1, th = tw, tx = nd.x >> 1, ty = nd.y >> 1;
     bool avail_l = nb_avail(g, nd, nd.x - 1, nd.y, false, false);
     bool avail_t = nb_avail(g, nd, nd.x, nd.y - 1, false, false);
@@ -385,7 +391,7 @@ __device__ void cclm_params(Shared &S, const CtuGeom &g, const Node &nd, int c, 
 }
 
 // per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
-__device__ void pred_setup(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+__device__ __noinline__ void pred_setup(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
     const int cs = c != 0;
     const int n = nd.w >> cs;
     pc.mode = mode; pc.c = c; pc.n = n; pc.l2 = ilog2i(n);
@@ -449,7 +455,7 @@ __device__ void pred_setup(Shared &S, const CtuGeom &g, const Node &nd, int c, i
     __syncwarp();
 }
 
-__device__ __forceinline__ int pred_sample(Shared &S, const PredCtx &pc, int x, int y) {
+__device__ __noinline__ int pred_sample(Shared &S, const PredCtx &pc, int x, int y) {
     const int n = pc.n;
     int p;
     if (pc.kind == 3) {
@@ -511,8 +517,9 @@ __device__ __forceinline__ int pred_sample(Shared &S, const PredCtx &pc, int x, 
 // transforms (transformer.rs:2040-2378 forward, 2380-2737 inverse), one warp per TB, direct matrix multiply
 // ---------------------------------------------------------------------------------------------------------------
 // out[y][i] = (sum_x T[i][x] * in[y][x] + rnd) >> sh              (rows; lanes over i, Tt makes the T read conflict-free)
-__device__ __forceinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+__device__ __noinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
     const int nn = n * n;
+#pragma unroll 1
     for (int o = lane; o < nn; o += 32) {
         int y = o >> l2, i = o & (n - 1);
         const int16_t *row = in + y * n;
@@ -525,8 +532,9 @@ __device__ __forceinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int
     }
 }
 // out[i][x] = (sum_y T[i][y] * in[y][x] + rnd) >> sh              (columns; lanes over x)
-__device__ __forceinline__ void mm_cols(const int8_t *T, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+__device__ __noinline__ void mm_cols(const int8_t *T, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
     const int nn = n * n;
+#pragma unroll 1
     for (int o = lane; o < nn; o += 32) {
         int i = o >> l2, x = o & (n - 1);
         const int8_t *trow = T + i * n;
@@ -552,16 +560,102 @@ __device__ __forceinline__ unsigned map_compose(unsigned a, unsigned b) {  // ap
     return r;
 }
 
+// Local candidate costs of one scan position (quantizer.rs:436-503): for delta = (state > 1) in {0,1} the two candidate
+// levels a0 = (x + delta) / 2 and a1 = a0 + 1, cost_i = 128 * |tc - dequant(q_i)| + lambda * dq_table[bits_i].
+struct LC {
+    int L00, L10, L01, L11;  // [candidate][delta]
+    int L0s0;                // candidate 0 as seen by state 0 (first-visit is_trailing_zeros flag, H2)
+    unsigned pk;             // bit0: parity of a0 (delta 0), bit1: parity of a0 (delta 1), bit2: sub-block-start adjustment applies to state 0
+};
+constexpr int TR_INF = 1 << 28;
+
+__device__ __noinline__ LC local_costs(Shared &S, const DevTables *__restrict__ tab, int tc, unsigned w, int k, int kstar, int ls, int sh, int off, int ldq1) {
+    LC r;
+    const bool flagged = k > kstar;
+    if (w & 2048u) {
+        const unsigned x = w & 2047u;
+        int a0 = (int)(x >> 1);
+        int q0 = 2 * a0, q1 = 2 * a0 + 2;
+        if (tc < 0) { q0 = -q0; q1 = -q1; }
+        int d0 = abs(tc - ((q0 * ls + off) >> sh));
+        int d1 = abs(tc - ((q1 * ls + off) >> sh));
+        r.L00 = 128 * d0 + WB_LDQ(a0 + 1);
+        r.L10 = 128 * d1 + WB_LDQ(a0 + 2);
+        r.L0s0 = (flagged && a0 == 0) ? 128 * d0 : r.L00;
+        r.pk = a0 & 1;
+        a0 = (int)((x + 1) >> 1);
+        q0 = a0 > 0 ? 2 * a0 - 1 : 0;
+        q1 = 2 * a0 + 1;
+        if (tc < 0) { q0 = -q0; q1 = -q1; }
+        d0 = abs(tc - ((q0 * ls + off) >> sh));
+        d1 = abs(tc - ((q1 * ls + off) >> sh));
+        r.L01 = 128 * d0 + WB_LDQ(a0 + 1);
+        r.L11 = 128 * d1 + WB_LDQ(a0 + 2);
+        r.pk |= (a0 & 1) << 1;
+    } else {
+        r.L00 = r.L01 = ldq1;
+        r.L10 = r.L11 = TR_INF;
+        r.L0s0 = flagged ? 0 : ldq1;
+        r.pk = 0;
+    }
+    if (flagged && (k & 15) == 0) r.pk |= 4;
+    return r;
+}
+
+// One trellis step on the 4 state costs (states 0,1 move to {0,2}, states 2,3 to {1,3}; encoder_context.rs:339).
+// Returns the 4 decision bits (1 = candidate a1; ties keep a0, quantizer.rs:505).
+__device__ __forceinline__ unsigned vstep(const LC &l, int ldq1, int &C0, int &C1, int &C2, int &C3) {
+    int X = (l.pk & 1) ? C2 : C0, Y = (l.pk & 1) ? C0 : C2;
+    int c0 = l.L0s0 + X, c1 = l.L10 + Y;
+    const bool d_0 = c1 < c0;
+    int n0 = d_0 ? c1 : c0;
+    if ((l.pk & 4) && !d_0) n0 -= ldq1;  // quantizer.rs:512-514, applied after the comparison
+    c0 = l.L00 + Y; c1 = l.L10 + X;
+    const bool d_1 = c1 < c0;
+    const int n1 = d_1 ? c1 : c0;
+    X = (l.pk & 2) ? C3 : C1; Y = (l.pk & 2) ? C1 : C3;
+    c0 = l.L01 + X; c1 = l.L11 + Y;
+    const bool d_2 = c1 < c0;
+    const int n2 = d_2 ? c1 : c0;
+    c0 = l.L01 + Y; c1 = l.L11 + X;
+    const bool d_3 = c1 < c0;
+    const int n3 = d_3 ? c1 : c0;
+    C0 = n0; C1 = n1; C2 = n2; C3 = n3;
+    return (unsigned)d_0 | ((unsigned)d_1 << 1) | ((unsigned)d_2 << 2) | ((unsigned)d_3 << 3);
+}
+
+// next-state map (4 x 2 bits) of one position for the walk: next(s) = 2 * (parity(a_s) ^ (s & 1)) + (s >> 1)
+__device__ __forceinline__ unsigned pos_map(unsigned pk, unsigned dec, bool nz) {
+    if (!nz) return 0xD8u;  // a = 0 for every state: 0->0, 1->2, 2->1, 3->3
+    unsigned m = 0;
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        unsigned par = ((pk >> (s >> 1)) ^ (dec >> s)) & 1u;
+        m |= (2u * (par ^ (s & 1u)) + (s >> 1)) << (2 * s);
+    }
+    return m;
+}
+
 // coef (raster, n x n) -> lev (raster).  Returns rate (sum of lv[] per block_splitter.rs:415-460) and whether any level != 0.
-__device__ void trellis(Shared &S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
+//
+// The reference's memoised DFS (quantizer.rs:338-517) equals a backward Viterbi pass from DC upwards in which the entries
+// (k, state 0) for k above the highest position k* whose state-0 lower candidate is non-zero carry the first-visit
+// is_trailing_zeros flag.  Every step is (min,+)-linear in the 4 state costs except the post-comparison
+// adjustment at sub-block starts, so the pass is split into chunks: (B) each lane folds the steps of its chunk into a 4x4
+// (min,+) matrix, (C) the chunk heads (which carry the non-linear step) and matrices are applied in sequence, one chunk per
+// iteration, (D) each lane replays its chunk from its true entry costs to record the decisions, (F) the walk from the last
+// position (quantizer.rs:686-721) is a prefix scan over per-chunk next-state maps followed by a per-lane walk.  Costs are
+// int32 relative to the running minimum; the decisions are identical to the reference's i64 comparisons.
+__device__ __noinline__ void trellis(Shared &S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
                         int &rate_out, bool &any_out) {
     const int n = 1 << l2, nn = n * n, sh = l2 + 4, off = 1 << (sh - 1);
     const int ls = tab->ls;
     const uint16_t *scan = S.tb.scan + tab_off(l2);
     const int ldq1 = S.tb.ldq[1];
-    // ---- pre-pass: x = S / ls per position; k* = highest scan position whose state-0 lower candidate is non-zero (H2)
+    // ---- A: x = S / ls per position; k* (H2)
     int kstar = -1;
     bool anytc = false;
+#pragma unroll 1
     for (int k = lane; k < nn; k += 32) {
         int tc = coef[scan[k]];
         unsigned x = 0, nz = tc != 0;
@@ -583,26 +677,23 @@ __device__ void trellis(Shared &S, const DevTables *__restrict__ tab, const int1
         __syncwarp();
         return;
     }
-    // ---- backward DP from DC upwards; costs are int32 relative values compared by wrapped difference (exact: the true
-    //      differences between state costs stay far below 2^31)
-    const int INF = 1 << 29;
-    int C0, C1, C2, C3;
-    {   // DC leaf (quantizer.rs:367-409), computed uniformly
-        int tc = coef[0];
-        unsigned x = Wd[0] & 2047u;
+    // ---- DC leaf (quantizer.rs:367-409), computed uniformly
+    int Lf0, Lf1, Lf2, Lf3;
+    unsigned leafdec = 0;
+    {
+        const int tc = coef[0];
+        const unsigned x = Wd[0] & 2047u;
         int Cs[4];
-        unsigned dec = 0;
 #pragma unroll
         for (int s = 0; s < 4; s++) {
             const bool itz = (s == 0) && (kstar < 0);
             int cost;
             if (tc == 0) {
-                cost = itz ? 0 : ldq1;
-                if (itz) cost -= ldq1;
+                cost = itz ? -ldq1 : ldq1;
             } else {
                 const int delta = s > 1;
                 int a0 = (int)(x >> 1);
-                int q0 = (int)(int16_t)(2 * a0 - delta);
+                int q0 = (int)(int16_t)(2 * a0 - delta);  // H3: usize wrap gives -1 for a0 == 0, delta == 1
                 if (tc < 0) q0 = -q0;
                 int d0 = abs(tc - ((q0 * ls + off) >> sh));
                 int bits0 = (a0 != 0 || !itz) ? a0 + 1 : 0;
@@ -617,132 +708,142 @@ __device__ void trellis(Shared &S, const DevTables *__restrict__ tab, const int1
                     if (itz && a0 == 0) cost -= ldq1;
                 } else {
                     cost = cost1;
-                    dec |= 1u << s;
+                    leafdec |= 1u << s;
                 }
             }
             Cs[s] = cost;
         }
-        C0 = Cs[0]; C1 = Cs[1]; C2 = Cs[2]; C3 = Cs[3];
-        if (lane == 0) Wd[0] = (uint16_t)(Wd[0] | (dec << 12));
+        Lf0 = Cs[0]; Lf1 = Cs[1]; Lf2 = Cs[2]; Lf3 = Cs[3];
     }
-    for (int base = 0; base < nn; base += 32) {
-        const int k = base + lane;
-        int L00 = 0, L10 = INF, L01 = 0, L11 = INF, L0s0 = 0;
-        unsigned pk = 0;
-        if (k < nn) {
-            unsigned w = Wd[k];
-            unsigned x = w & 2047u;
-            const bool flagged = k > kstar;
-            if (w & 2048u) {
-                int tc = coef[scan[k]];
-                // delta = 0
-                int a0 = (int)(x >> 1);
-                int q0 = 2 * a0;  // a0 > 0 ? 2*a0 - 0 : 0
-                int q1 = 2 * a0 + 2;
-                if (tc < 0) { q0 = -q0; q1 = -q1; }
-                int d0 = abs(tc - ((q0 * ls + off) >> sh));
-                int d1 = abs(tc - ((q1 * ls + off) >> sh));
-                L00 = 128 * d0 + WB_LDQ(a0 + 1);
-                L10 = 128 * d1 + WB_LDQ(a0 + 2);
-                L0s0 = (flagged && a0 == 0) ? 128 * d0 : L00;
-                pk = a0 & 1;
-                // delta = 1
-                a0 = (int)((x + 1) >> 1);
-                q0 = a0 > 0 ? 2 * a0 - 1 : 0;
-                q1 = 2 * a0 + 1;
-                if (tc < 0) { q0 = -q0; q1 = -q1; }
-                d0 = abs(tc - ((q0 * ls + off) >> sh));
-                d1 = abs(tc - ((q1 * ls + off) >> sh));
-                L01 = 128 * d0 + WB_LDQ(a0 + 1);
-                L11 = 128 * d1 + WB_LDQ(a0 + 2);
-                pk |= (a0 & 1) << 1;
-            } else {
-                L00 = L01 = ldq1;
-                L0s0 = flagged ? 0 : ldq1;
+    const int CS = nn >= 256 ? 16 : 4, nch = nn / CS, rounds = (nch + 31) >> 5;
+    int carry0 = 0, carry1 = 0, carry2 = 0, carry3 = 0;
+    unsigned cmaps = 0;
+    for (int r = 0; r < rounds; r++) {
+        const int c = r * 32 + lane;
+        const bool vc = c < nch;
+        const int k0 = c * CS;
+        // ---- B: chunk head costs and the (min,+) matrix of the remaining CS-1 steps
+        LC head;
+        head.L00 = head.L01 = head.L0s0 = 0; head.L10 = head.L11 = TR_INF; head.pk = 0;
+        int M[4][4];
+#pragma unroll
+        for (int s = 0; s < 4; s++)
+#pragma unroll
+            for (int t = 0; t < 4; t++) M[s][t] = s == t ? 0 : TR_INF;
+        if (vc) {
+            head = local_costs(S, tab, coef[scan[k0]], Wd[k0], k0, kstar, ls, sh, off, ldq1);
+#pragma unroll 1
+            for (int i = 1; i < CS; i++) {
+                const int k = k0 + i;
+                const LC l = local_costs(S, tab, coef[scan[k]], Wd[k], k, kstar, ls, sh, off, ldq1);
+#pragma unroll
+                for (int t = 0; t < 4; t++) {
+                    int X = (l.pk & 1) ? M[2][t] : M[0][t], Y = (l.pk & 1) ? M[0][t] : M[2][t];
+                    const int n0 = min(l.L0s0 + X, l.L10 + Y), n1 = min(l.L00 + Y, l.L10 + X);
+                    X = (l.pk & 2) ? M[3][t] : M[1][t]; Y = (l.pk & 2) ? M[1][t] : M[3][t];
+                    const int n2 = min(l.L01 + X, l.L11 + Y), n3 = min(l.L01 + Y, l.L11 + X);
+                    M[0][t] = n0; M[1][t] = n1; M[2][t] = n2; M[3][t] = n3;
+                }
             }
-            if (flagged && (k & 15) == 0) pk |= 4;
         }
-        unsigned mydec = 0;
-        const int cnt = min(32, nn - base);
-        for (int j = (base == 0 ? 1 : 0); j < cnt; j++) {
-            const int l0s0 = __shfl_sync(0xffffffffu, L0s0, j);
-            const int l00 = __shfl_sync(0xffffffffu, L00, j);
-            const int l10 = __shfl_sync(0xffffffffu, L10, j);
-            const int l01 = __shfl_sync(0xffffffffu, L01, j);
-            const int l11 = __shfl_sync(0xffffffffu, L11, j);
-            const unsigned p = __shfl_sync(0xffffffffu, pk, j);
-            // states 0,1 move to {0,2}; states 2,3 move to {1,3}   (q_state_trans_table, encoder_context.rs:339)
-            int X = (p & 1) ? C2 : C0, Y = (p & 1) ? C0 : C2;
-            int c0 = l0s0 + X, c1 = l10 + Y;
-            bool d_0 = (c1 - c0) < 0;
-            int n0 = d_0 ? c1 : c0;
-            if ((p & 4) && !d_0) n0 -= ldq1;
-            c0 = l00 + Y; c1 = l10 + X;
-            bool d_1 = (c1 - c0) < 0;
-            int n1 = d_1 ? c1 : c0;
-            X = (p & 2) ? C3 : C1; Y = (p & 2) ? C1 : C3;
-            c0 = l01 + X; c1 = l11 + Y;
-            bool d_2 = (c1 - c0) < 0;
-            int n2 = d_2 ? c1 : c0;
-            c0 = l01 + Y; c1 = l11 + X;
-            bool d_3 = (c1 - c0) < 0;
-            int n3 = d_3 ? c1 : c0;
-            C0 = n0; C1 = n1; C2 = n2; C3 = n3;
-            if (lane == j) mydec = (unsigned)d_0 | ((unsigned)d_1 << 1) | ((unsigned)d_2 << 2) | ((unsigned)d_3 << 3);
+        // ---- C: apply head + matrix chunk by chunk; lane j owns chunk r*32 + j
+        int O0 = 0, O1 = 0, O2 = 0, O3 = 0, my0 = 0, my1 = 0, my2 = 0, my3 = 0;
+        const int cnt = min(32, nch - r * 32);
+#pragma unroll 1
+        for (int j = 0; j < cnt; j++) {
+            int I0, I1, I2, I3;
+            if (j == 0) { I0 = carry0; I1 = carry1; I2 = carry2; I3 = carry3; }
+            else {
+                I0 = __shfl_sync(0xffffffffu, O0, j - 1); I1 = __shfl_sync(0xffffffffu, O1, j - 1);
+                I2 = __shfl_sync(0xffffffffu, O2, j - 1); I3 = __shfl_sync(0xffffffffu, O3, j - 1);
+            }
+            int H0 = I0, H1 = I1, H2 = I2, H3 = I3;
+            if (r == 0 && j == 0) { H0 = Lf0; H1 = Lf1; H2 = Lf2; H3 = Lf3; }
+            else vstep(head, ldq1, H0, H1, H2, H3);
+            int T0 = min(min(M[0][0] + H0, M[0][1] + H1), min(M[0][2] + H2, M[0][3] + H3));
+            int T1 = min(min(M[1][0] + H0, M[1][1] + H1), min(M[1][2] + H2, M[1][3] + H3));
+            int T2 = min(min(M[2][0] + H0, M[2][1] + H1), min(M[2][2] + H2, M[2][3] + H3));
+            int T3 = min(min(M[3][0] + H0, M[3][1] + H1), min(M[3][2] + H2, M[3][3] + H3));
+            const int mn = min(min(T0, T1), min(T2, T3));
+            O0 = T0 - mn; O1 = T1 - mn; O2 = T2 - mn; O3 = T3 - mn;
+            if (lane == j) { my0 = I0; my1 = I1; my2 = I2; my3 = I3; }
         }
-        if (k < nn && k > 0) Wd[k] = (uint16_t)(Wd[k] | (mydec << 12));
+        carry0 = __shfl_sync(0xffffffffu, O0, cnt - 1); carry1 = __shfl_sync(0xffffffffu, O1, cnt - 1);
+        carry2 = __shfl_sync(0xffffffffu, O2, cnt - 1); carry3 = __shfl_sync(0xffffffffu, O3, cnt - 1);
+        // ---- D: replay the chunk from its true entry costs, record decisions and the chunk's walk map
+        if (vc) {
+            int C0 = my0, C1 = my1, C2 = my2, C3 = my3;
+            unsigned cm = 0xE4u;
+#pragma unroll 1
+            for (int i = 0; i < CS; i++) {
+                const int k = k0 + i;
+                const unsigned w = Wd[k];
+                unsigned dec, pk;
+                if (k == 0) {
+                    C0 = Lf0; C1 = Lf1; C2 = Lf2; C3 = Lf3;
+                    dec = leafdec;
+                    pk = ((w >> 1) & 1u) * 3u;  // DC: a0 = x / 2 for both deltas
+                } else {
+                    const LC l = i == 0 ? head : local_costs(S, tab, coef[scan[k]], w, k, kstar, ls, sh, off, ldq1);
+                    dec = vstep(l, ldq1, C0, C1, C2, C3);
+                    pk = l.pk;
+                }
+                Wd[k] = (uint16_t)(w | (dec << 12));
+                cm = map_compose(pos_map(pk, dec, (w & 2048u) != 0), cm);
+            }
+            cmaps |= cm << (8 * r);
+        }
     }
     __syncwarp();
-    // ---- walk from the last scan position with state 0 (quantizer.rs:686-721): parallel prefix over next-state maps
+    // ---- F: walk from the last scan position with state 0 (quantizer.rs:686-721) + rate (block_splitter.rs:415-460)
     unsigned state = 0;
     bool seen_nz = false;
     int rate = 0;
-    for (int top = nn - 1; top >= 0; top -= 32) {
-        const int k = top - lane;
-        unsigned m = 0xE4u;  // identity
-        unsigned w = 0, x = 0, dec = 0;
-        bool nz = false;
-        if (k >= 0) {
-            w = Wd[k];
-            x = w & 2047u;
-            nz = (w & 2048u) != 0;
-            dec = w >> 12;
-            m = 0;
-#pragma unroll
-            for (int s = 0; s < 4; s++) {
-                unsigned a = nz ? (((k == 0) ? (x >> 1) : ((x + (s > 1)) >> 1)) + ((dec >> s) & 1u)) : 0u;
-                unsigned nx = 2u * ((a & 1u) ^ (s & 1u)) + (s >> 1);
-                m |= nx << (2 * s);
-            }
-        }
-        unsigned inc = m;
+    const int lv0 = S.tb.lv[0];
+    for (int r = rounds - 1; r >= 0; r--) {
+        const int c = r * 32 + lane;
+        const bool vc = c < nch;
+        const int k0 = c * CS;
+        unsigned inc = vc ? ((cmaps >> (8 * r)) & 255u) : 0xE4u;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc = map_compose(t, inc);
+            unsigned t = __shfl_down_sync(0xffffffffu, inc, d);
+            if (lane + d < 32) inc = map_compose(t, inc);
         }
-        unsigned exc = __shfl_up_sync(0xffffffffu, inc, 1);
-        const unsigned s_in = (lane == 0) ? state : ((exc >> (2 * state)) & 3u);
-        const unsigned last = __shfl_sync(0xffffffffu, inc, 31);
-        state = (last >> (2 * state)) & 3u;
-        int q = 0;
-        const int delta = s_in > 1;
-        if (k >= 0 && nz) {
-            int a = (int)(((k == 0) ? (x >> 1) : ((x + delta) >> 1)) + ((dec >> s_in) & 1u));
-            if (k == 0) q = (int)(int16_t)(2 * a - delta);  // H3: a == 0, delta == 1 gives -1
-            else q = a > 0 ? 2 * a - delta : 0;
-            if (coef[scan[k]] < 0) q = -q;
-        }
-        if (k >= 0) lev[scan[k]] = (int16_t)q;
-        const bool isnz = q != 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, isnz);
-        if (k >= 0) {
-            if (isnz) {
-                int ar = (abs(q) + delta) >> 1;
-                rate += WB_LV(ar);
-            } else if (seen_nz || (bal & ((1u << lane) - 1u))) {
-                rate += S.tb.lv[0];
+        const unsigned exc = __shfl_down_sync(0xffffffffu, inc, 1);
+        unsigned s = (lane == 31) ? state : ((exc >> (2 * state)) & 3u);
+        const unsigned all = __shfl_sync(0xffffffffu, inc, 0);
+        state = (all >> (2 * state)) & 3u;
+        int lead = 0, irate = 0;
+        bool has = false;
+        if (vc) {
+#pragma unroll 1
+            for (int i = CS - 1; i >= 0; i--) {
+                const int k = k0 + i;
+                const unsigned w = Wd[k];
+                const unsigned x = w & 2047u, dec = w >> 12;
+                const int delta = s > 1;
+                int q = 0;
+                unsigned a = 0;
+                if (w & 2048u) {
+                    a = ((k == 0) ? (x >> 1) : ((x + delta) >> 1)) + ((dec >> s) & 1u);
+                    if (k == 0) q = (int)(int16_t)(2 * (int)a - delta);
+                    else q = a > 0 ? 2 * (int)a - delta : 0;
+                    if (coef[scan[k]] < 0) q = -q;
+                }
+                lev[scan[k]] = (int16_t)q;
+                if (q != 0) {
+                    irate += WB_LV((abs(q) + delta) >> 1);
+                    has = true;
+                } else if (has) irate += lv0;
+                else lead++;
+                s = 2u * ((a & 1u) ^ (s & 1u)) + (s >> 1);
             }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, has);
+        if (vc) {
+            rate += irate;
+            if (seen_nz || (lane < 31 && (bal >> (lane + 1)) != 0)) rate += lead * lv0;
         }
         seen_nz = seen_nz || bal != 0;
     }
@@ -766,11 +867,12 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
 }
 
 // SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
-__device__ unsigned sad_task(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, const WarpScratch &ws, int lane) {
+__device__ __noinline__ unsigned sad_task(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, const WarpScratch &ws, int lane) {
     PredCtx pc;
     pred_setup(S, g, nd, c, mode, ws.refx, lane, pc);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
+#pragma unroll 1
     for (int i = lane; i < n * n; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int p = pred_sample(S, pc, x, y);
@@ -781,13 +883,14 @@ __device__ unsigned sad_task(Shared &S, const CtuGeom &g, const Node &nd, int c,
 
 // full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
 // commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
-__device__ void full_task(Shared &S, const DevTables *__restrict__ tab, const CtuGeom &g, const Node &nd, int c, int mode, bool commit,
+__device__ __noinline__ void full_task(Shared &S, const DevTables *__restrict__ tab, const CtuGeom &g, const Node &nd, int c, int mode, bool commit,
                           const WarpScratch &ws, int lane, unsigned &ssd_out, int &rate_out) {
     PredCtx pc;
     pred_setup(S, g, nd, c, mode, ws.refx, lane, pc);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2, nn = n * n;
     int16_t *A = ws.A, *B = ws.B;
     bool anyres = false;
+#pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int p = pred_sample(S, pc, x, y);
@@ -831,6 +934,7 @@ __device__ void full_task(Shared &S, const DevTables *__restrict__ tab, const Ct
         __syncwarp();
     }
     unsigned ssd = 0;
+#pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int res = anylev ? (int)A[i] : 0;
@@ -850,7 +954,7 @@ __device__ void full_task(Shared &S, const DevTables *__restrict__ tab, const Ct
 // ---------------------------------------------------------------------------------------------------------------
 // MPM derivation for the mode-bit estimate (ctu.rs:1498-1635) with the H1 neighbour semantics
 // ---------------------------------------------------------------------------------------------------------------
-__device__ int luma_kind(const Shared &S, const CtuGeom &g, const Node &nd, int mode, int root_mode) {
+__device__ __noinline__ int luma_kind(const Shared &S, const CtuGeom &g, const Node &nd, int mode, int root_mode) {
     if (mode == MODE_PLANAR) return 0;
     int left, above;
     if (nd.x == 0) left = g.cx > 0 ? S.leftModes[(nd.y + nd.w - 1) >> 2] : MODE_PLANAR;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwrenc_b200.so")
+LIB_PATH = os.environ.get("WRENC_B200_LIB") or os.path.join(_HERE, "libwrenc_b200.so")  # env override: dev-time kernel variants
 
 RECORD_DTYPE = np.dtype([("split_mask", "<u4"), ("luma_mode", "u1", (64,)), ("chroma_mode", "u1", (16,)), ("cost", "<f4")])
 assert RECORD_DTYPE.itemsize == 88
