@@ -88,7 +88,7 @@ def run_reference(args):
     sample = f"{cores} processes x {rows} CTU rows (1920x{rows * 32}) of a 1920x1088 QP32 frame per step; frames = CTUs/2040"
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32-cost",
-            "data": "synthetic", "config": workload_config(args, 0),
+            "data": "synthetic", "config": workload_config(args, args.frames),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
@@ -310,9 +310,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=240, help="frames per GPU per step")
     ap.add_argument("--unique", type=int, default=12, help="unique synthetic frames generated on the host (repeated on device)")
-    ap.add_argument("--e2e-frames", type=int, default=48)
-    ap.add_argument("--e2e-batch", type=int, default=24)
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-frames", type=int, default=120)
+    ap.add_argument("--e2e-batch", type=int, default=120)
+    ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
