@@ -29,6 +29,7 @@ struct wrenc_b200 {
     uint8_t *d_mode_map = nullptr;
     int *d_done = nullptr;
     uint32_t *d_items = nullptr;
+    size_t items_cap = 0;
     unsigned int *d_counter = nullptr;
     int items_for = -1;  // n_pictures the uploaded work list was built for
     int n_items = 0;
@@ -60,12 +61,11 @@ static int ensure_workspace(wrenc_b200 *h, int n_pics) {
     if (n_pics <= h->ws_pics) return 0;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_mode_map); cudaFree(h->d_done); cudaFree(h->d_items);
-    h->d_mode_map = nullptr; h->d_done = nullptr; h->d_items = nullptr;
+    cudaFree(h->d_mode_map); cudaFree(h->d_done);
+    h->d_mode_map = nullptr; h->d_done = nullptr;
     size_t nctu = (size_t)h->Wc * h->Hc * n_pics;
     CK(cudaMalloc(&h->d_mode_map, (size_t)(h->W / 4) * (h->H / 4) * n_pics));
     CK(cudaMalloc(&h->d_done, nctu * sizeof(int)));
-    CK(cudaMalloc(&h->d_items, nctu * sizeof(uint32_t)));
     CK(cudaMemsetAsync(h->d_done, 0, nctu * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_mode_map, 0, (size_t)(h->W / 4) * (h->H / 4) * n_pics, h->stream));
     h->ws_pics = n_pics;
@@ -96,8 +96,24 @@ static int ensure_items(wrenc_b200 *h, int n_pics) {
         for (int cy = 0; cy < Hc; cy++)
             for (int cx = 0; cx < Wc; cx++) v.push_back({cx + 2 * cy + (int)(stagger * p), p, cy, cx});
     std::stable_sort(v.begin(), v.end(), [](const It &a, const It &b) { return a.key < b.key; });
-    std::vector<uint32_t> items(v.size());
-    for (size_t i = 0; i < v.size(); i++) items[i] = ((uint32_t)v[i].pic << 16) | ((uint32_t)v[i].cy << 8) | (uint32_t)v[i].cx;
+    // Batches of KC mutually independent CTUs (one CTA searches a batch in lock step).  Items of one key level never
+    // depend on each other, so a batch never crosses a level boundary; short levels leave empty slots.
+    const int KC = search_ctus_per_cta();
+    std::vector<uint32_t> items;
+    items.reserve(v.size() + (size_t)KC * (Wc + 2 * Hc + n_pics));
+    for (size_t i = 0; i < v.size();) {
+        size_t j = i;
+        while (j < v.size() && j - i < (size_t)KC && v[j].key == v[i].key) j++;
+        for (size_t q = i; q < j; q++) items.push_back(((uint32_t)v[q].pic << 16) | ((uint32_t)v[q].cy << 8) | (uint32_t)v[q].cx);
+        for (size_t q = j - i; q < (size_t)KC; q++) items.push_back(0xffffffffu);
+        i = j;
+    }
+    if (items.size() > h->items_cap) {
+        cudaFree(h->d_items);
+        h->d_items = nullptr;
+        CK(cudaMalloc(&h->d_items, items.size() * sizeof(uint32_t)));
+        h->items_cap = items.size();
+    }
     CK(cudaMemcpyAsync(h->d_items, items.data(), items.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));  // `items` is pageable and goes out of scope
     h->items_for = n_pics;
@@ -118,7 +134,7 @@ static int enqueue_search(wrenc_b200 *h, int n_pics, const uint8_t *d_yuv, uint8
     P.orig = d_yuv; P.rec = d_rec; P.lev = d_lev; P.mode_map = h->d_mode_map; P.records = d_records;
     P.done = h->d_done; P.items = h->d_items; P.counter = h->d_counter; P.tab = h->d_tab;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
-    int grid = std::min(h->grid, h->n_items);
+    int grid = std::min(h->grid, h->n_items / search_ctus_per_cta());
     CK(launch_search(P, grid, st));
     h->launches++;
     return 0;

@@ -7,311 +7,17 @@
 namespace wb {
 
 // ---------------------------------------------------------------------------------------------------------------
-// leaf evaluation (block_splitter.rs:886-1078) for SINGLE_TREE 32/16/8 and DUAL_TREE_LUMA 4x4 nodes
+// Lock-step execution of KC independent CTUs per CTA.
+//
+// The search is exhaustive (no early termination), so every CTU walks the same node sequence; only the data-dependent
+// decisions differ.  A CTA therefore runs the phases of KC CTUs together: the task list of a phase is the union of the
+// CTUs' tasks (t-major, so the large luma tasks are listed first and land on the warps that own large scratch), and the
+// decision after a phase is taken by one thread per CTU (thread k for CTU k) and published through shared memory.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ long long luma_hdr(const Shared &S, const DevTables *tab, const CtuGeom &g, const Node &nd, int mode, int ck, int root_mode) {
-    int lk = luma_kind(S, g, nd, mode, root_mode);
-    return nd.tree == SINGLE_TREE ? tab->hdr_single[lk][ck] : tab->hdr_dual[lk];
-}
-
-__device__ __forceinline__ void fill_lm(Shared &S, const Node &nd, int mode, int tid) {
-    int cells = nd.w >> 2;
-    for (int i = tid; i < cells * cells; i += NTHREADS) {
-        int yy = i / cells, xx = i - yy * cells;
-        S.lm[((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx] = (uint8_t)mode;
-    }
-}
-__device__ __forceinline__ void fill_cm(Shared &S, const Node &nd, int mode, int tid) {
-    int cells = nd.w >> 3;
-    for (int i = tid; i < cells * cells; i += NTHREADS) {
-        int yy = i / cells, xx = i - yy * cells;
-        S.cm[((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx] = (uint8_t)mode;
-    }
-}
-
-__device__ __noinline__ float leaf_eval(Shared &S, const SearchParams &P, const CtuGeom &g, const Node &nd, int &root_mode, bool is_root) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const DevTables *tab = P.tab;
-    const WarpScratch ws = warp_scratch(S, warp);
-    const int ncomp = nd.tree == DUAL_TREE_LUMA ? 1 : 3;
-    // ---- phase 0: reference samples
-    for (int t = warp; t < ncomp; t += NW) build_refs(S, g, nd, t, lane);
-    __syncthreads();
-    // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs
-    {
-        const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
-        for (int t = warp; t < ntask; t += NW) {
-            if (t < nfull) {
-                int mode, c;
-                if (t < 2) { mode = t; c = 0; }
-                else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
-                unsigned ssd; int rate;
-                full_task(S, tab, g, nd, c, mode, false, ws, lane, ssd, rate);
-                if (lane == 0) { S.r_ssd[t] = ssd; S.r_rate[t] = rate; }
-            } else {
-                int u = t - nfull;
-                int c = u / 13, mi = u - c * 13;
-                unsigned sad = sad_task(S, g, nd, c, c_cand15[2 + mi], ws, lane);
-                if (lane == 0) S.r_sad[t] = sad;
-            }
-        }
-    }
-    __syncthreads();
-    float cost_pl, cost_dc;
-    int cur;
-    float cur_cost;
-    {
-        unsigned ssd0 = S.r_ssd[0], ssd1 = S.r_ssd[1];
-        long long r0 = S.r_rate[0], r1 = S.r_rate[1];
-        if (ncomp == 3) {
-            ssd0 += S.r_ssd[2] + S.r_ssd[3]; r0 += (long long)S.r_rate[2] + S.r_rate[3];
-            ssd1 += S.r_ssd[4] + S.r_ssd[5]; r1 += (long long)S.r_rate[4] + S.r_rate[5];
-        }
-        cost_pl = rd_cost(ssd0, r0 + luma_hdr(S, tab, g, nd, 0, 0, root_mode), tab->lambda_rd);
-        cost_dc = rd_cost(ssd1, r1 + luma_hdr(S, tab, g, nd, 1, 0, root_mode), tab->lambda_rd);
-        const int nfull = 2 * ncomp;
-        int best = 0;
-        float bc = 0.f;
-        for (int i = 0; i < 13; i++) {
-            unsigned s = S.r_sad[nfull + i];
-            if (ncomp == 3) s += S.r_sad[nfull + 13 + i] + S.r_sad[nfull + 26 + i];
-            float c = __uint2float_rn(s);
-            if (i == 0 || c < bc) { bc = c; best = i; }
-        }
-        cur = c_cand15[2 + best];
-        cur_cost = bc;
-    }
-    __syncthreads();  // results consumed before the next phase overwrites them
-    // ---- phases 2,3: SAD refinement +-2, +-1 (step_search aux=true, block_splitter.rs:905-973)
-    for (int step = 2; step >= 1; step >>= 1) {
-        const bool v0 = !(cur < 2 + step), v1 = !(cur + step > 66);
-        for (int t = warp; t < 2 * ncomp; t += NW) {
-            int cand = t / ncomp, c = t - cand * ncomp;
-            if (cand == 0 ? v0 : v1) {
-                unsigned sad = sad_task(S, g, nd, c, cand == 0 ? cur - step : cur + step, ws, lane);
-                if (lane == 0) S.r_sad[t] = sad;
-            }
-        }
-        __syncthreads();
-        float c0 = FLT_MAX, c1 = FLT_MAX;
-        if (v0) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += S.r_sad[c]; c0 = __uint2float_rn(s); }
-        if (v1) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += S.r_sad[ncomp + c]; c1 = __uint2float_rn(s); }
-        float mn = fminf(fminf(cur_cost, c0), c1);
-        if (cur_cost == mn) {
-        } else if (c0 == mn) { cur -= step; cur_cost = c0; }
-        else { cur += step; cur_cost = c1; }
-        __syncthreads();
-    }
-    // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false)
-    int dir = cur;
-    float dir_cost;
-    {
-        const bool v0 = !(dir < 3), v1 = !(dir + 1 > 66);
-        const int ntask = 3 * ncomp;
-        for (int t = warp; t < ntask; t += NW) {
-            int cand, c;
-            if (t < 3) { cand = t; c = 0; }
-            else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
-            bool valid = cand == 0 || (cand == 1 ? v0 : v1);
-            if (valid) {
-                int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
-                unsigned ssd; int rate;
-                full_task(S, tab, g, nd, c, mode, false, ws, lane, ssd, rate);
-                if (lane == 0) { S.r_ssd[t] = ssd; S.r_rate[t] = rate; }
-            }
-        }
-        __syncthreads();
-        float cc[3];
-#pragma unroll
-        for (int cand = 0; cand < 3; cand++) {
-            bool valid = cand == 0 || (cand == 1 ? v0 : v1);
-            cc[cand] = FLT_MAX;
-            if (valid) {
-                unsigned ssd = S.r_ssd[cand];
-                long long r = S.r_rate[cand];
-                if (ncomp == 3) { ssd += S.r_ssd[3 + 2 * cand] + S.r_ssd[4 + 2 * cand]; r += (long long)S.r_rate[3 + 2 * cand] + S.r_rate[4 + 2 * cand]; }
-                int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
-                cc[cand] = rd_cost(ssd, r + luma_hdr(S, tab, g, nd, mode, 0, root_mode), tab->lambda_rd);
-            }
-        }
-        float mn = fminf(fminf(cc[0], cc[1]), cc[2]);
-        if (cc[0] == mn) { dir_cost = cc[0]; }
-        else if (cc[1] == mn) { dir -= 1; dir_cost = cc[1]; }
-        else { dir += 1; dir_cost = cc[2]; }
-        __syncthreads();
-    }
-    // ---- winner among planar, DC, dir (first minimum)
-    float min_cost = fminf(fminf(cost_pl, cost_dc), dir_cost);
-    const int mode = cost_pl == min_cost ? 0 : (cost_dc == min_cost ? 1 : dir);
-    if (is_root) root_mode = mode;
-    // ---- phase 5: luma redo (commit) + chroma DM full evaluation (commit)
-    for (int t = warp; t < ncomp; t += NW) {
-        unsigned ssd; int rate;
-        full_task(S, tab, g, nd, t, mode, true, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[t] = ssd; S.r_rate[t] = rate; }
-    }
-    fill_lm(S, nd, mode, tid);
-    __syncthreads();
-    if (ncomp == 1) return min_cost;
-    const unsigned ssdY = S.r_ssd[0], ssdDM = S.r_ssd[1] + S.r_ssd[2];
-    const long long rateY = S.r_rate[0], rateDM = (long long)S.r_rate[1] + S.r_rate[2];
-    const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
-    // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
-    if (warp == NW - 1) cclm_downsample(S, g, nd, lane);
-    __syncthreads();
-    // ---- phase 6: CCLM SADs in the order LT, T, L
-    for (int t = warp; t < 6; t += NW) {
-        const int mi = t >> 1, c = 1 + (t & 1);
-        const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-        unsigned sad = sad_task(S, g, nd, c, cm, ws, lane);
-        if (lane == 0) S.r_sad[t] = sad;
-    }
-    __syncthreads();
-    int cclm_mode;
-    {
-        float lt = __uint2float_rn(S.r_sad[0] + S.r_sad[1]), t = __uint2float_rn(S.r_sad[2] + S.r_sad[3]), l = __uint2float_rn(S.r_sad[4] + S.r_sad[5]);
-        if (lt <= t && lt <= l) cclm_mode = MODE_LT_CCLM;
-        else if (t <= l) cclm_mode = MODE_T_CCLM;
-        else cclm_mode = MODE_L_CCLM;
-    }
-    // ---- phase 7: CCLM full evaluation (no commit)
-    for (int t = warp; t < 2; t += NW) {
-        unsigned ssd; int rate;
-        full_task(S, tab, g, nd, 1 + t, cclm_mode, false, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[8 + t] = ssd; S.r_rate[8 + t] = rate; }
-    }
-    __syncthreads();
-    const unsigned ssdCC = S.r_ssd[8] + S.r_ssd[9];
-    const long long rateCC = (long long)S.r_rate[8] + S.r_rate[9];
-    const int ck = 1 + (cclm_mode - MODE_LT_CCLM);
-    const float cost_cclm = rd_cost(ssdCC, rateCC + tab->hdr_chroma[ck], tab->lambda_rd_c);
-    const float cmn = fminf(cost_dm, cost_cclm);
-    float final_cost;
-    if (cost_dm == cmn) {
-        fill_cm(S, nd, mode, tid);
-        final_cost = rd_cost(ssdY + ssdDM, rateY + rateDM + luma_hdr(S, tab, g, nd, mode, 0, root_mode), tab->lambda_rd);
-    } else {
-        // ---- phase 8: commit the CCLM chroma
-        for (int t = warp; t < 2; t += NW) {
-            unsigned ssd; int rate;
-            full_task(S, tab, g, nd, 1 + t, cclm_mode, true, ws, lane, ssd, rate);
-        }
-        fill_cm(S, nd, cclm_mode, tid);
-        final_cost = rd_cost(ssdY + ssdCC, rateY + rateCC + luma_hdr(S, tab, g, nd, mode, ck, root_mode), tab->lambda_rd);
-    }
-    __syncthreads();
-    return final_cost;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// the 8x8 DUAL_TREE_CHROMA coding tree that follows four 4x4 luma CUs (block_splitter.rs:794-885)
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ float chroma_ct_eval(Shared &S, const SearchParams &P, const CtuGeom &g, const Node &nd) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const DevTables *tab = P.tab;
-    const WarpScratch ws = warp_scratch(S, warp);
-    // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396)
-    const int dm = S.lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
-    for (int t = warp; t < 3; t += NW) {
-        if (t < 2) build_refs(S, g, nd, 1 + t, lane);
-        else cclm_downsample(S, g, nd, lane);
-    }
-    __syncthreads();
-    for (int t = warp; t < 8; t += NW) {
-        if (t < 2) {
-            unsigned ssd; int rate;
-            full_task(S, tab, g, nd, 1 + t, dm, true, ws, lane, ssd, rate);
-            if (lane == 0) { S.r_ssd[t] = ssd; S.r_rate[t] = rate; }
-        } else {
-            const int u = t - 2;
-            const int mi = u >> 1, c = 1 + (u & 1);
-            const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-            unsigned sad = sad_task(S, g, nd, c, cm, ws, lane);
-            if (lane == 0) S.r_sad[u] = sad;
-        }
-    }
-    __syncthreads();
-    int cclm_mode;
-    {
-        float lt = __uint2float_rn(S.r_sad[0] + S.r_sad[1]), t = __uint2float_rn(S.r_sad[2] + S.r_sad[3]), l = __uint2float_rn(S.r_sad[4] + S.r_sad[5]);
-        if (lt <= t && lt <= l) cclm_mode = MODE_LT_CCLM;
-        else if (t <= l) cclm_mode = MODE_T_CCLM;
-        else cclm_mode = MODE_L_CCLM;
-    }
-    for (int t = warp; t < 2; t += NW) {
-        unsigned ssd; int rate;
-        full_task(S, tab, g, nd, 1 + t, cclm_mode, false, ws, lane, ssd, rate);
-        if (lane == 0) { S.r_ssd[8 + t] = ssd; S.r_rate[8 + t] = rate; }
-    }
-    __syncthreads();
-    const float cost_dm = rd_cost(S.r_ssd[0] + S.r_ssd[1], (long long)S.r_rate[0] + S.r_rate[1] + tab->hdr_chroma[0], tab->lambda_rd_c);
-    const int ck = 1 + (cclm_mode - MODE_LT_CCLM);
-    const float cost_cclm = rd_cost(S.r_ssd[8] + S.r_ssd[9], (long long)S.r_rate[8] + S.r_rate[9] + tab->hdr_chroma[ck], tab->lambda_rd_c);
-    const float mn = fminf(cost_dm, cost_cclm);
-    if (cost_dm == mn) {
-        fill_cm(S, nd, dm, tid);
-    } else {
-        for (int t = warp; t < 2; t += NW) {
-            unsigned ssd; int rate;
-            full_task(S, tab, g, nd, 1 + t, cclm_mode, true, ws, lane, ssd, rate);
-        }
-        fill_cm(S, nd, cclm_mode, tid);
-    }
-    __syncthreads();
-    return mn;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// no-split state save / restore (block_splitter.rs:1085-1109, 1125-1145) — here also levels and modes, because the
-// CUDA path keeps the tree as flat arrays instead of cloning CodingTree objects
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sv_off_y(int d) { return d == 0 ? 0 : (d == 1 ? 1024 : 1280); }
-__device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 256 : 320); }
-
-__device__ __noinline__ void save_node(Shared &S, const Node &nd, int d, int tid) {
-    const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
-    for (int i = tid; i < w * w; i += NTHREADS) {
-        int y = i / w, x = i - y * w;
-        S.svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
-        S.svLvY[oy + i] = S.lvY[(nd.y + y) * 32 + nd.x + x];
-    }
-    const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
-    for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
-        int c = i >= cw * cw, j = i - c * cw * cw;
-        int y = j / cw, x = j - y * cw;
-        S.svRecC[c][oc + j] = RC(S, 1 + c, bx + x, by + y);
-        S.svLvC[c][oc + j] = S.lvC[c][(by + y) * 16 + bx + x];
-    }
-    for (int i = tid; i < 64; i += NTHREADS) S.svLm[d][i] = S.lm[i];
-    for (int i = tid; i < 16; i += NTHREADS) S.svCm[d][i] = S.cm[i];
-}
-__device__ __noinline__ void restore_node(Shared &S, const Node &nd, int d, int tid) {
-    const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
-    for (int i = tid; i < w * w; i += NTHREADS) {
-        int y = i / w, x = i - y * w;
-        RY(S, nd.x + x, nd.y + y) = S.svRecY[oy + i];
-        S.lvY[(nd.y + y) * 32 + nd.x + x] = S.svLvY[oy + i];
-    }
-    const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
-    for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
-        int c = i >= cw * cw, j = i - c * cw * cw;
-        int y = j / cw, x = j - y * cw;
-        RC(S, 1 + c, bx + x, by + y) = S.svRecC[c][oc + j];
-        S.lvC[c][(by + y) * 16 + bx + x] = S.svLvC[c][oc + j];
-    }
-    const int cells = w >> 2;
-    for (int i = tid; i < cells * cells; i += NTHREADS) {
-        int yy = i / cells, xx = i - yy * cells;
-        int idx = ((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx;
-        S.lm[idx] = S.svLm[d][idx];
-    }
-    const int cc = w >> 3;
-    for (int i = tid; i < cc * cc; i += NTHREADS) {
-        int yy = i / cc, xx = i - yy * cc;
-        int idx = ((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx;
-        S.cm[idx] = S.svCm[d][idx];
-    }
-}
+struct NodeId {
+    int depth, a, b, c;  // position in the quad tree: child indices at depth 1, 2, 3
+    int tree;            // SINGLE_TREE, DUAL_TREE_LUMA (depth 3) or DUAL_TREE_CHROMA (the 8x8 chroma CT: depth 2 geometry)
+};
 
 // CodingTree::split(SPLIT_QT) child geometry + availability flags (ctu.rs:1960-2064, 2083-2188; H9)
 __device__ __forceinline__ Node qt_child(const CtuGeom &g, const Node &p, int i, int tree) {
@@ -333,80 +39,510 @@ __device__ __forceinline__ Node qt_child(const CtuGeom &g, const Node &p, int i,
     return c;
 }
 
+// geometry and availability flags of a node of one CTU (the flags depend on the CTU's position in the picture)
+__device__ __forceinline__ Node make_node(const CtuGeom &g, const NodeId &id) {
+    Node n;
+    n.x = 0; n.y = 0; n.w = 32; n.tree = SINGLE_TREE;
+    n.bl = false;
+    n.ar = (g.cx + 32 >= g.W) ? false : (0 < g.cy && g.cx + 32 < g.W);
+    if (id.depth >= 1) n = qt_child(g, n, id.a, SINGLE_TREE);
+    if (id.depth >= 2) n = qt_child(g, n, id.b, SINGLE_TREE);
+    if (id.tree == DUAL_TREE_CHROMA) {  // local dual tree: chroma CT of the 8x8 parent's size (ctu.rs:2031-2055)
+        Node c = n;
+        c.tree = DUAL_TREE_CHROMA;
+        c.ar = (g.cx + c.x + c.w >= g.W) ? false : n.ar;
+        c.bl = (g.cy + c.y + c.w >= g.H) ? false : n.bl;
+        return c;
+    }
+    if (id.depth >= 3) n = qt_child(g, n, id.c, DUAL_TREE_LUMA);
+    return n;
+}
+
+__device__ __forceinline__ long long luma_hdr(const Ctx S, const DevTables *tab, const Node &nd, int mode, int ck) {
+    int lk = luma_kind(S, S.c->g, nd, mode, S.c->root_mode);
+    return nd.tree == SINGLE_TREE ? tab->hdr_single[lk][ck] : tab->hdr_dual[lk];
+}
+
+__device__ __forceinline__ void fill_lm(const Ctx S, const Node &nd, int mode, int lane) {
+    int cells = nd.w >> 2;
+    for (int i = lane; i < cells * cells; i += 32) {
+        int yy = i / cells, xx = i - yy * cells;
+        S.c->lm[((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx] = (uint8_t)mode;
+    }
+}
+__device__ __forceinline__ void fill_cm(const Ctx S, const Node &nd, int mode, int lane) {
+    int cells = nd.w >> 3;
+    for (int i = lane; i < cells * cells; i += 32) {
+        int yy = i / cells, xx = i - yy * cells;
+        S.c->cm[((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx] = (uint8_t)mode;
+    }
+}
+
+// Tasks of a phase are handed out in list order (the large luma tasks first) to whichever warp is free: a shared-memory
+// ticket per phase (S.ticket[phase parity], reset two phases later).  32x32 luma tasks need the large scratch buffers that
+// only the first NBIG warps own, so nodes of that size keep the static round-robin assignment.
+__device__ __forceinline__ int next_task(Shared &S, int &slot, bool dyn, int prev, int warp, int lane) {
+    if (!dyn) return prev < 0 ? warp : prev + NW;
+    int t = 0;
+    if (lane == 0) t = atomicAdd(&S.ticket[slot], 1);
+    return __shfl_sync(0xffffffffu, t, 0);
+}
+#define WB_FOR_TASKS(ntask)                                                                            \
+    for (int tt = next_task(S, S_slot, dyn, -1, warp, lane); tt < (ntask) * KC; tt = next_task(S, S_slot, dyn, tt, warp, lane)) \
+        if (S.c[tt % KC].active)
+// called by every thread between two phases (after the barrier that ends a phase): switch to the other ticket and
+// clear the one used two phases ago
+#define WB_NEXT_PHASE()                                       \
+    do {                                                      \
+        S_slot ^= 1;                                          \
+        if (threadIdx.x == 0) S.ticket[S_slot ^ 1] = 0;       \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
-// one CTU: split_ct(root, max_depth)  (block_splitter.rs:782-1154)
+// leaf evaluation (block_splitter.rs:886-1078) for SINGLE_TREE 32/16/8 and DUAL_TREE_LUMA 4x4 nodes; the cost of
+// CTU k is left in S.c[k].leaf_cost
 // ---------------------------------------------------------------------------------------------------------------
-__device__ void ctu_search(Shared &S, const SearchParams &P, const CtuGeom &g, unsigned &split_mask_out, float &cost_out) {
-    const int tid = threadIdx.x;
-    const int md = P.max_depth;
-    int root_mode = 0;
-    unsigned mask = 0;
-    Node n32;
-    n32.x = 0; n32.y = 0; n32.w = 32; n32.tree = SINGLE_TREE;
-    n32.bl = false;
-    n32.ar = (g.cx + 32 >= g.W) ? false : (0 < g.cy && g.cx + 32 < g.W);
-    float cost32 = leaf_eval(S, P, g, n32, root_mode, true);
-    if (md >= 1) {
-        save_node(S, n32, 0, tid);
-        __syncthreads();
-        const unsigned mask32 = mask;
-        float split32 = 0.0f;
-        for (int a = 0; a < 4; a++) {
-            Node n16 = qt_child(g, n32, a, SINGLE_TREE);
-            float cost16 = leaf_eval(S, P, g, n16, root_mode, false);
-            if (md >= 2) {
-                save_node(S, n16, 1, tid);
-                __syncthreads();
-                const unsigned mask16 = mask;
-                float split16 = 0.0f;
-                for (int b = 0; b < 4; b++) {
-                    Node n8 = qt_child(g, n16, b, SINGLE_TREE);
-                    float cost8 = leaf_eval(S, P, g, n8, root_mode, false);
-                    if (md >= 3) {
-                        save_node(S, n8, 2, tid);
-                        __syncthreads();
-                        float split8 = 0.0f;
-                        for (int c = 0; c < 4; c++) {
-                            Node n4 = qt_child(g, n8, c, DUAL_TREE_LUMA);
-                            split8 = __fadd_rn(split8, leaf_eval(S, P, g, n4, root_mode, false));
-                        }
-                        Node nc = n8;  // local dual tree: chroma CT of the parent's size (ctu.rs:2031-2055)
-                        nc.tree = DUAL_TREE_CHROMA;
-                        nc.ar = (g.cx + nc.x + nc.w >= g.W) ? false : n8.ar;
-                        nc.bl = (g.cy + nc.y + nc.w >= g.H) ? false : n8.bl;
-                        split8 = __fadd_rn(split8, chroma_ct_eval(S, P, g, nc));
-                        if (split8 > cost8) {
-                            restore_node(S, n8, 2, tid);
-                            __syncthreads();
-                        } else {
-                            mask |= 1u << (5 + a * 4 + b);
-                            cost8 = split8;
-                        }
-                    }
-                    split16 = __fadd_rn(split16, cost8);
-                }
-                if (split16 > cost16) {
-                    restore_node(S, n16, 1, tid);
-                    mask = mask16;
-                    __syncthreads();
-                } else {
-                    mask |= 1u << (1 + a);
-                    cost16 = split16;
-                }
+__device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const NodeId id, int &S_slot) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const DevTables *tab = P.tab;
+    const WarpScratch ws = warp_scratch(S, warp);
+    const int ncomp = id.tree == DUAL_TREE_LUMA ? 1 : 3;
+    const bool is_root = id.depth == 0;
+    const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
+    // ---- phase 0: reference samples
+    WB_FOR_TASKS(ncomp) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        build_refs(V, V.c->g, make_node(V.c->g, id), t, lane);
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs
+    {
+        const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
+        WB_FOR_TASKS(ntask) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            const Node nd = make_node(V.c->g, id);
+            if (t < nfull) {
+                int mode, c;
+                if (t < 2) { mode = t; c = 0; }
+                else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
+                unsigned ssd; int rate;
+                full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate);
+                if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+            } else {
+                int u = t - nfull;
+                int c = u / 13, mi = u - c * 13;
+                unsigned sad = sad_task(V, V.c->g, nd, c, c_cand15[2 + mi], ws, lane);
+                if (lane == 0) V.c->r_sad[t] = sad;
             }
-            split32 = __fadd_rn(split32, cost16);
-        }
-        if (split32 > cost32) {
-            restore_node(S, n32, 0, tid);
-            mask = mask32;
-            __syncthreads();
-        } else {
-            mask |= 1u;
-            cost32 = split32;
         }
     }
-    split_mask_out = mask;
-    cost_out = cost32;
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (tid < KC && S.c[tid].active) {
+        Ctx V{&S.tb, &S.c[tid]};
+        CtuCtx &C = *V.c;
+        const Node nd = make_node(C.g, id);
+        unsigned ssd0 = C.r_ssd[0], ssd1 = C.r_ssd[1];
+        long long r0 = C.r_rate[0], r1 = C.r_rate[1];
+        if (ncomp == 3) {
+            ssd0 += C.r_ssd[2] + C.r_ssd[3]; r0 += (long long)C.r_rate[2] + C.r_rate[3];
+            ssd1 += C.r_ssd[4] + C.r_ssd[5]; r1 += (long long)C.r_rate[4] + C.r_rate[5];
+        }
+        C.cost_pl = rd_cost(ssd0, r0 + luma_hdr(V, tab, nd, 0, 0), tab->lambda_rd);
+        C.cost_dc = rd_cost(ssd1, r1 + luma_hdr(V, tab, nd, 1, 0), tab->lambda_rd);
+        const int nfull = 2 * ncomp;
+        int best = 0;
+        float bc = 0.f;
+        for (int i = 0; i < 13; i++) {
+            unsigned s = C.r_sad[nfull + i];
+            if (ncomp == 3) s += C.r_sad[nfull + 13 + i] + C.r_sad[nfull + 26 + i];
+            float c = __uint2float_rn(s);
+            if (i == 0 || c < bc) { bc = c; best = i; }
+        }
+        C.cur = c_cand15[2 + best];
+        C.cur_cost = bc;
+        C.v0 = !(C.cur < 2 + 2);
+        C.v1 = !(C.cur + 2 > 66);
+    }
+    __syncthreads();
+    // ---- phases 2,3: SAD refinement +-2, +-1 (step_search aux=true, block_splitter.rs:905-973)
+    for (int step = 2; step >= 1; step >>= 1) {
+        WB_FOR_TASKS(2 * ncomp) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            int cand = t / ncomp, c = t - cand * ncomp;
+            if (cand == 0 ? V.c->v0 : V.c->v1) {
+                unsigned sad = sad_task(V, V.c->g, make_node(V.c->g, id), c, cand == 0 ? V.c->cur - step : V.c->cur + step, ws, lane);
+                if (lane == 0) V.c->r_sad[t] = sad;
+            }
+        }
+        __syncthreads();
+        WB_NEXT_PHASE();
+        if (tid < KC && S.c[tid].active) {
+            CtuCtx &C = S.c[tid];
+            float c0 = FLT_MAX, c1 = FLT_MAX;
+            if (C.v0) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += C.r_sad[c]; c0 = __uint2float_rn(s); }
+            if (C.v1) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += C.r_sad[ncomp + c]; c1 = __uint2float_rn(s); }
+            float mn = fminf(fminf(C.cur_cost, c0), c1);
+            if (C.cur_cost == mn) {
+            } else if (c0 == mn) { C.cur -= step; C.cur_cost = c0; }
+            else { C.cur += step; C.cur_cost = c1; }
+            const int ns = step >> 1;
+            if (ns > 0) { C.v0 = !(C.cur < 2 + ns); C.v1 = !(C.cur + ns > 66); }
+            else { C.dir = C.cur; C.v0 = !(C.dir < 3); C.v1 = !(C.dir + 1 > 66); }
+        }
+        __syncthreads();
+    }
+    // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false)
+    WB_FOR_TASKS(3 * ncomp) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        int cand, c;
+        if (t < 3) { cand = t; c = 0; }
+        else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
+        bool valid = cand == 0 || (cand == 1 ? V.c->v0 : V.c->v1);
+        if (valid) {
+            const int dir = V.c->dir;
+            int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, make_node(V.c->g, id), c, mode, false, ws, lane, ssd, rate);
+            if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+        }
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (tid < KC && S.c[tid].active) {
+        Ctx V{&S.tb, &S.c[tid]};
+        CtuCtx &C = *V.c;
+        const Node nd = make_node(C.g, id);
+        float cc[3];
+        for (int cand = 0; cand < 3; cand++) {
+            bool valid = cand == 0 || (cand == 1 ? C.v0 : C.v1);
+            cc[cand] = FLT_MAX;
+            if (valid) {
+                unsigned ssd = C.r_ssd[cand];
+                long long r = C.r_rate[cand];
+                if (ncomp == 3) { ssd += C.r_ssd[3 + 2 * cand] + C.r_ssd[4 + 2 * cand]; r += (long long)C.r_rate[3 + 2 * cand] + C.r_rate[4 + 2 * cand]; }
+                int mode = cand == 0 ? C.dir : (cand == 1 ? C.dir - 1 : C.dir + 1);
+                cc[cand] = rd_cost(ssd, r + luma_hdr(V, tab, nd, mode, 0), tab->lambda_rd);
+            }
+        }
+        float mn = fminf(fminf(cc[0], cc[1]), cc[2]);
+        if (cc[0] == mn) { C.dir_cost = cc[0]; }
+        else if (cc[1] == mn) { C.dir -= 1; C.dir_cost = cc[1]; }
+        else { C.dir += 1; C.dir_cost = cc[2]; }
+        // ---- winner among planar, DC, dir (first minimum)
+        C.min_cost = fminf(fminf(C.cost_pl, C.cost_dc), C.dir_cost);
+        C.mode = C.cost_pl == C.min_cost ? 0 : (C.cost_dc == C.min_cost ? 1 : C.dir);
+        if (is_root) C.root_mode = C.mode;
+        C.leaf_cost = C.min_cost;
+    }
+    __syncthreads();
+    // ---- phase 5: luma redo (commit) + chroma DM full evaluation (commit)
+    WB_FOR_TASKS(ncomp) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = make_node(V.c->g, id);
+        unsigned ssd; int rate;
+        full_task(V, tab, V.c->g, nd, t, V.c->mode, true, ws, lane, ssd, rate);
+        if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+        if (t == 0) fill_lm(V, nd, V.c->mode, lane);
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (ncomp == 1) return;
+    // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
+    WB_FOR_TASKS(1) {
+        const int k = tt % KC;
+        Ctx V{&S.tb, &S.c[k]};
+        cclm_downsample(V, V.c->g, make_node(V.c->g, id), lane);
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    // ---- phase 6: CCLM SADs in the order LT, T, L
+    WB_FOR_TASKS(6) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const int mi = t >> 1, c = 1 + (t & 1);
+        const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
+        unsigned sad = sad_task(V, V.c->g, make_node(V.c->g, id), c, cm, ws, lane);
+        if (lane == 0) V.c->r_sad[t] = sad;
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (tid < KC && S.c[tid].active) {
+        CtuCtx &C = S.c[tid];
+        float lt = __uint2float_rn(C.r_sad[0] + C.r_sad[1]), t = __uint2float_rn(C.r_sad[2] + C.r_sad[3]), l = __uint2float_rn(C.r_sad[4] + C.r_sad[5]);
+        if (lt <= t && lt <= l) C.cclm_mode = MODE_LT_CCLM;
+        else if (t <= l) C.cclm_mode = MODE_T_CCLM;
+        else C.cclm_mode = MODE_L_CCLM;
+    }
+    __syncthreads();
+    // ---- phase 7: CCLM full evaluation (no commit)
+    WB_FOR_TASKS(2) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        unsigned ssd; int rate;
+        full_task(V, tab, V.c->g, make_node(V.c->g, id), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
+        if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (tid < KC && S.c[tid].active) {
+        Ctx V{&S.tb, &S.c[tid]};
+        CtuCtx &C = *V.c;
+        const Node nd = make_node(C.g, id);
+        const unsigned ssdY = C.r_ssd[0], ssdDM = C.r_ssd[1] + C.r_ssd[2];
+        const long long rateY = C.r_rate[0], rateDM = (long long)C.r_rate[1] + C.r_rate[2];
+        const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
+        const unsigned ssdCC = C.r_ssd[8] + C.r_ssd[9];
+        const long long rateCC = (long long)C.r_rate[8] + C.r_rate[9];
+        const int ck = 1 + (C.cclm_mode - MODE_LT_CCLM);
+        const float cost_cclm = rd_cost(ssdCC, rateCC + tab->hdr_chroma[ck], tab->lambda_rd_c);
+        const float cmn = fminf(cost_dm, cost_cclm);
+        if (cost_dm == cmn) {
+            C.cclm_wins = 0;
+            C.leaf_cost = rd_cost(ssdY + ssdDM, rateY + rateDM + luma_hdr(V, tab, nd, C.mode, 0), tab->lambda_rd);
+        } else {
+            C.cclm_wins = 1;
+            C.leaf_cost = rd_cost(ssdY + ssdCC, rateY + rateCC + luma_hdr(V, tab, nd, C.mode, ck), tab->lambda_rd);
+        }
+    }
+    __syncthreads();
+    // ---- phase 8: commit the CCLM chroma where it won; publish the chroma mode
+    WB_FOR_TASKS(2) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = make_node(V.c->g, id);
+        if (V.c->cclm_wins) {
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+        }
+        if (t == 0) fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the 8x8 DUAL_TREE_CHROMA coding tree that follows four 4x4 luma CUs (block_splitter.rs:794-885)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, const NodeId id, int &S_slot) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const bool dyn = true;
+    const DevTables *tab = P.tab;
+    const WarpScratch ws = warp_scratch(S, warp);
+    WB_FOR_TASKS(3) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = make_node(V.c->g, id);
+        if (t < 2) build_refs(V, V.c->g, nd, 1 + t, lane);
+        else cclm_downsample(V, V.c->g, nd, lane);
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    WB_FOR_TASKS(8) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = make_node(V.c->g, id);
+        if (t < 2) {
+            // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396)
+            const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, nd, 1 + t, dm, true, ws, lane, ssd, rate);
+            if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+        } else {
+            const int u = t - 2;
+            const int mi = u >> 1, c = 1 + (u & 1);
+            const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
+            unsigned sad = sad_task(V, V.c->g, nd, c, cm, ws, lane);
+            if (lane == 0) V.c->r_sad[u] = sad;
+        }
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (tid < KC && S.c[tid].active) {
+        CtuCtx &C = S.c[tid];
+        float lt = __uint2float_rn(C.r_sad[0] + C.r_sad[1]), t = __uint2float_rn(C.r_sad[2] + C.r_sad[3]), l = __uint2float_rn(C.r_sad[4] + C.r_sad[5]);
+        if (lt <= t && lt <= l) C.cclm_mode = MODE_LT_CCLM;
+        else if (t <= l) C.cclm_mode = MODE_T_CCLM;
+        else C.cclm_mode = MODE_L_CCLM;
+    }
+    __syncthreads();
+    WB_FOR_TASKS(2) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        unsigned ssd; int rate;
+        full_task(V, tab, V.c->g, make_node(V.c->g, id), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
+        if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+    if (tid < KC && S.c[tid].active) {
+        CtuCtx &C = S.c[tid];
+        const float cost_dm = rd_cost(C.r_ssd[0] + C.r_ssd[1], (long long)C.r_rate[0] + C.r_rate[1] + tab->hdr_chroma[0], tab->lambda_rd_c);
+        const int ck = 1 + (C.cclm_mode - MODE_LT_CCLM);
+        const float cost_cclm = rd_cost(C.r_ssd[8] + C.r_ssd[9], (long long)C.r_rate[8] + C.r_rate[9] + tab->hdr_chroma[ck], tab->lambda_rd_c);
+        const float mn = fminf(cost_dm, cost_cclm);
+        C.cclm_wins = !(cost_dm == mn);
+        C.leaf_cost = mn;
+    }
+    __syncthreads();
+    WB_FOR_TASKS(2) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = make_node(V.c->g, id);
+        if (V.c->cclm_wins) {
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+        }
+        if (t == 0) {
+            const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
+            fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : dm, lane);
+        }
+    }
+    __syncthreads();
+    WB_NEXT_PHASE();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// no-split state save / restore (block_splitter.rs:1085-1109, 1125-1145) — here also levels and modes, because the
+// CUDA path keeps the tree as flat arrays instead of cloning CodingTree objects
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sv_off_y(int d) { return d == 0 ? 0 : (d == 1 ? 1024 : 1280); }
+__device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 256 : 320); }
+
+__device__ __noinline__ void save_node(const Ctx S, const Node &nd, int d, int tid) {
+    const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
+    for (int i = tid; i < w * w; i += NTHREADS) {
+        int y = i / w, x = i - y * w;
+        S.c->svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
+        S.c->svLvY[oy + i] = S.c->lvY[(nd.y + y) * 32 + nd.x + x];
+    }
+    const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
+    for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
+        int c = i >= cw * cw, j = i - c * cw * cw;
+        int y = j / cw, x = j - y * cw;
+        S.c->svRecC[c][oc + j] = RC(S, 1 + c, bx + x, by + y);
+        S.c->svLvC[c][oc + j] = S.c->lvC[c][(by + y) * 16 + bx + x];
+    }
+    for (int i = tid; i < 64; i += NTHREADS) S.c->svLm[d][i] = S.c->lm[i];
+    for (int i = tid; i < 16; i += NTHREADS) S.c->svCm[d][i] = S.c->cm[i];
+}
+__device__ __noinline__ void restore_node(const Ctx S, const Node &nd, int d, int tid) {
+    const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
+    for (int i = tid; i < w * w; i += NTHREADS) {
+        int y = i / w, x = i - y * w;
+        RY(S, nd.x + x, nd.y + y) = S.c->svRecY[oy + i];
+        S.c->lvY[(nd.y + y) * 32 + nd.x + x] = S.c->svLvY[oy + i];
+    }
+    const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
+    for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
+        int c = i >= cw * cw, j = i - c * cw * cw;
+        int y = j / cw, x = j - y * cw;
+        RC(S, 1 + c, bx + x, by + y) = S.c->svRecC[c][oc + j];
+        S.c->lvC[c][(by + y) * 16 + bx + x] = S.c->svLvC[c][oc + j];
+    }
+    const int cells = w >> 2;
+    for (int i = tid; i < cells * cells; i += NTHREADS) {
+        int yy = i / cells, xx = i - yy * cells;
+        int idx = ((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx;
+        S.c->lm[idx] = S.c->svLm[d][idx];
+    }
+    const int cc = w >> 3;
+    for (int i = tid; i < cc * cc; i += NTHREADS) {
+        int yy = i / cc, xx = i - yy * cc;
+        int idx = ((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx;
+        S.c->cm[idx] = S.c->svCm[d][idx];
+    }
+}
+
+// after the leaf evaluation of a node that may still split: remember its cost and state
+__device__ void begin_split(Shared &S, const NodeId &id, int d) {
+    const int tid = threadIdx.x;
+    for (int k = 0; k < KC; k++) {
+        if (!S.c[k].active) continue;
+        Ctx V{&S.tb, &S.c[k]};
+        save_node(V, make_node(V.c->g, id), d, tid);
+    }
+    if (tid < KC && S.c[tid].active) {
+        CtuCtx &C = S.c[tid];
+        C.cost[d] = C.leaf_cost;
+        C.split[d] = 0.0f;
+        if (d < 2) C.mask_sv[d] = C.mask;
+    }
+    __syncthreads();
+}
+// split_cost > no_split_cost keeps the no-split state (block_splitter.rs:1125); otherwise the split is adopted
+__device__ void end_split(Shared &S, const NodeId &id, int d, int bit) {
+    const int tid = threadIdx.x;
+    if (tid < KC && S.c[tid].active) {
+        CtuCtx &C = S.c[tid];
+        if (C.split[d] > C.cost[d]) {
+            C.restore = 1;
+            if (d < 2) C.mask = C.mask_sv[d];
+            C.leaf_cost = C.cost[d];
+        } else {
+            C.restore = 0;
+            C.mask |= 1u << bit;
+            C.leaf_cost = C.split[d];
+        }
+    }
+    __syncthreads();
+    for (int k = 0; k < KC; k++) {
+        if (!S.c[k].active || !S.c[k].restore) continue;
+        Ctx V{&S.tb, &S.c[k]};
+        restore_node(V, make_node(V.c->g, id), d, tid);
+    }
+    __syncthreads();
+}
+// add the cost of the node just finished (leaf_cost) to its parent's running split cost (f32, child order)
+__device__ __forceinline__ void add_to_parent(Shared &S, int d) {
+    const int tid = threadIdx.x;
+    if (tid < KC && S.c[tid].active) S.c[tid].split[d] = __fadd_rn(S.c[tid].split[d], S.c[tid].leaf_cost);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// split_ct(root, max_depth) of KC CTUs  (block_splitter.rs:782-1154)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void ctu_search(Shared &S, const SearchParams &P, int &S_slot) {
+    const int md = P.max_depth;
+    NodeId n32{0, 0, 0, 0, SINGLE_TREE};
+    leaf_eval(S, P, n32, S_slot);
+    if (md >= 1) {
+        begin_split(S, n32, 0);
+        for (int a = 0; a < 4; a++) {
+            NodeId n16{1, a, 0, 0, SINGLE_TREE};
+            leaf_eval(S, P, n16, S_slot);
+            if (md >= 2) {
+                begin_split(S, n16, 1);
+                for (int b = 0; b < 4; b++) {
+                    NodeId n8{2, a, b, 0, SINGLE_TREE};
+                    leaf_eval(S, P, n8, S_slot);
+                    if (md >= 3) {
+                        begin_split(S, n8, 2);
+                        for (int c = 0; c < 4; c++) {
+                            NodeId n4{3, a, b, c, DUAL_TREE_LUMA};
+                            leaf_eval(S, P, n4, S_slot);
+                            add_to_parent(S, 2);
+                        }
+                        NodeId nc{2, a, b, 0, DUAL_TREE_CHROMA};
+                        chroma_ct_eval(S, P, nc, S_slot);
+                        add_to_parent(S, 2);
+                        end_split(S, n8, 2, 5 + a * 4 + b);
+                    }
+                    add_to_parent(S, 1);
+                }
+                end_split(S, n16, 1, 1 + a);
+            }
+            add_to_parent(S, 0);
+        }
+        end_split(S, n32, 0, 0);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -477,42 +613,54 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
     Shared &S = *reinterpret_cast<Shared *>(smem_raw);
     const int tid = threadIdx.x;
     init_tables(S, P.tab, tid);
+    if (tid == 0) { S.ticket[0] = 0; S.ticket[1] = 0; }
+    int S_slot = 0;
     __syncthreads();
     const int W = P.W, H = P.H, Wc = P.Wc;
     const size_t pic_samples = (size_t)W * H * 3 / 2;
     const int cw = W >> 1, chh = H >> 1;
     for (;;) {
-        if (tid == 0) S.item = (int)atomicAdd(P.counter, 1u);
+        if (tid == 0) S.item0 = (int)atomicAdd(P.counter, 1u) * KC;
         __syncthreads();
-        const int item = S.item;
-        if (item >= P.n_items) break;
-        const uint32_t it = P.items[item];
-        const int pic = it >> 16, cyi = (it >> 8) & 255, cxi = it & 255;
-        CtuGeom g;
-        g.cx = cxi * 32; g.cy = cyi * 32; g.W = W; g.H = H;
-        int *done = P.done + (size_t)pic * Wc * P.Hc;
-        // wavefront dependencies: left CTU and above-right CTU (above when in the last column) must be final
-        if (tid == 0) {
-            if (cxi > 0) while (ld_relaxed(&done[cyi * Wc + cxi - 1]) != P.epoch) __nanosleep(1000);
-            if (cyi > 0) {
-                const int ax = min(cxi + 1, Wc - 1);
-                while (ld_relaxed(&done[(cyi - 1) * Wc + ax]) != P.epoch) __nanosleep(1000);
+        const int item0 = S.item0;
+        if (item0 >= P.n_items) break;
+        // ---- one thread per CTU: decode the item, wait for the wavefront dependencies (left CTU and above-right CTU,
+        //      above when in the last column, of the same picture must be final)
+        if (tid < KC) {
+            CtuCtx &C = S.c[tid];
+            const uint32_t it = P.items[item0 + tid];
+            C.active = it != 0xffffffffu;
+            if (C.active) {
+                C.pic = it >> 16; C.cyi = (it >> 8) & 255; C.cxi = it & 255;
+                C.g.cx = C.cxi * 32; C.g.cy = C.cyi * 32; C.g.W = W; C.g.H = H;
+                C.mask = 0; C.root_mode = 0;
+                int *done = P.done + (size_t)C.pic * Wc * P.Hc;
+                if (C.cxi > 0) while (ld_relaxed(&done[C.cyi * Wc + C.cxi - 1]) != P.epoch) __nanosleep(1000);
+                if (C.cyi > 0) {
+                    const int ax = min(C.cxi + 1, Wc - 1);
+                    while (ld_relaxed(&done[(C.cyi - 1) * Wc + ax]) != P.epoch) __nanosleep(1000);
+                }
             }
             __threadfence();  // acquire side: order the halo loads after the flag observation
         }
         __syncthreads();
-        const uint8_t *oY = P.orig + (size_t)pic * pic_samples, *oCb = oY + (size_t)W * H, *oCr = oCb + (size_t)cw * chh;
-        uint8_t *rY = P.rec + (size_t)pic * pic_samples, *rCb = rY + (size_t)W * H, *rCr = rCb + (size_t)cw * chh;
-        // ---- stage the CTU: source samples, neighbouring reconstruction, left-CTU modes
-        {
+        // ---- stage the CTUs: source samples, neighbouring reconstruction, left-CTU modes
+        for (int k = 0; k < KC; k++) {
+            CtuCtx &C = S.c[k];
+            if (!C.active) continue;
+            Ctx V{&S.tb, &C};
+            const CtuGeom g = C.g;
+            const int pic = C.pic;
+            const uint8_t *oY = P.orig + (size_t)pic * pic_samples, *oCb = oY + (size_t)W * H, *oCr = oCb + (size_t)cw * chh;
+            const uint8_t *rY = P.rec + (size_t)pic * pic_samples, *rCb = rY + (size_t)W * H, *rCr = rCb + (size_t)cw * chh;
             for (int i = tid; i < 256; i += NTHREADS) {  // 32 rows x 8 words
                 int y = i >> 3, x4 = (i & 7) * 4;
-                *reinterpret_cast<uint32_t *>(&S.orgY[y * 32 + x4]) = __ldg(reinterpret_cast<const uint32_t *>(oY + (size_t)(g.cy + y) * W + g.cx + x4));
+                *reinterpret_cast<uint32_t *>(&C.orgY[y * 32 + x4]) = __ldg(reinterpret_cast<const uint32_t *>(oY + (size_t)(g.cy + y) * W + g.cx + x4));
             }
             for (int i = tid; i < 128; i += NTHREADS) {
                 int c = i >> 6, t = i & 63, yy = t >> 2, xx = (t & 3) * 4;
                 const uint8_t *src = (c ? oCr : oCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx;
-                *reinterpret_cast<uint32_t *>(&S.orgC[c][yy * 16 + xx]) = __ldg(reinterpret_cast<const uint32_t *>(src));
+                *reinterpret_cast<uint32_t *>(&C.orgC[c][yy * 16 + xx]) = __ldg(reinterpret_cast<const uint32_t *>(src));
             }
             // luma halo: rows -2,-1 (cols -4..63) and cols -4..-1 of rows 0..31
             for (int i = tid; i < 2 * RY_STRIDE + 32 * 4; i += NTHREADS) {
@@ -522,7 +670,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
                 int ax = g.cx + xx, ay = g.cy + yy;
                 uint8_t v = 0;
                 if (ax >= 0 && ax < W && ay >= 0) v = __ldcg(rY + (size_t)ay * W + ax);
-                RY(S, xx, yy) = v;
+                RY(V, xx, yy) = v;
             }
             for (int i = tid; i < 2 * (RC_STRIDE + 16 * 4); i += NTHREADS) {
                 int c = i >= (RC_STRIDE + 16 * 4), j = i - c * (RC_STRIDE + 16 * 4);
@@ -532,53 +680,62 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
                 int ax = (g.cx >> 1) + xx, ay = (g.cy >> 1) + yy;
                 uint8_t v = 0;
                 if (ax >= 0 && ax < cw && ay >= 0) v = __ldcg((c ? rCr : rCb) + (size_t)ay * cw + ax);
-                RC(S, 1 + c, xx, yy) = v;
+                RC(V, 1 + c, xx, yy) = v;
             }
-            if (tid < 8) S.leftModes[tid] = g.cx > 0 ? __ldcg(P.mode_map + (size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + tid) * (W >> 2) + (g.cx >> 2) - 1) : 0;
-            for (int i = tid; i < 1024; i += NTHREADS) S.lvY[i] = 0;
-            for (int i = tid; i < 256; i += NTHREADS) { S.lvC[0][i] = 0; S.lvC[1][i] = 0; }
-            for (int i = tid; i < 64; i += NTHREADS) S.lm[i] = 0;
-            for (int i = tid; i < 16; i += NTHREADS) S.cm[i] = 0;
+            for (int i = tid; i < 8; i += NTHREADS)
+                C.leftModes[i] = g.cx > 0 ? __ldcg(P.mode_map + (size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + i) * (W >> 2) + (g.cx >> 2) - 1) : 0;
+            for (int i = tid; i < 1024; i += NTHREADS) C.lvY[i] = 0;
+            for (int i = tid; i < 256; i += NTHREADS) { C.lvC[0][i] = 0; C.lvC[1][i] = 0; }
+            for (int i = tid; i < 64; i += NTHREADS) C.lm[i] = 0;
+            for (int i = tid; i < 16; i += NTHREADS) C.cm[i] = 0;
         }
         __syncthreads();
-        unsigned split_mask;
-        float cost;
-        ctu_search(S, P, g, split_mask, cost);
+        ctu_search(S, P, S_slot);
         __syncthreads();
         // ---- write back: reconstruction, levels, modes, record
-        {
+        for (int k = 0; k < KC; k++) {
+            CtuCtx &C = S.c[k];
+            if (!C.active) continue;
+            Ctx V{&S.tb, &C};
+            const CtuGeom g = C.g;
+            const int pic = C.pic;
+            uint8_t *rY = P.rec + (size_t)pic * pic_samples, *rCb = rY + (size_t)W * H, *rCr = rCb + (size_t)cw * chh;
             for (int i = tid; i < 256; i += NTHREADS) {
                 int y = i >> 3, x4 = (i & 7) * 4;
-                uint32_t v = (uint32_t)RY(S, x4, y) | ((uint32_t)RY(S, x4 + 1, y) << 8) | ((uint32_t)RY(S, x4 + 2, y) << 16) | ((uint32_t)RY(S, x4 + 3, y) << 24);
+                uint32_t v = (uint32_t)RY(V, x4, y) | ((uint32_t)RY(V, x4 + 1, y) << 8) | ((uint32_t)RY(V, x4 + 2, y) << 16) | ((uint32_t)RY(V, x4 + 3, y) << 24);
                 *reinterpret_cast<uint32_t *>(rY + (size_t)(g.cy + y) * W + g.cx + x4) = v;
             }
             for (int i = tid; i < 128; i += NTHREADS) {
                 int c = i >> 6, t = i & 63, yy = t >> 2, xx = (t & 3) * 4;
-                uint32_t u = (uint32_t)RC(S, 1 + c, xx, yy) | ((uint32_t)RC(S, 1 + c, xx + 1, yy) << 8) | ((uint32_t)RC(S, 1 + c, xx + 2, yy) << 16) |
-                             ((uint32_t)RC(S, 1 + c, xx + 3, yy) << 24);
+                uint32_t u = (uint32_t)RC(V, 1 + c, xx, yy) | ((uint32_t)RC(V, 1 + c, xx + 1, yy) << 8) | ((uint32_t)RC(V, 1 + c, xx + 2, yy) << 16) |
+                             ((uint32_t)RC(V, 1 + c, xx + 3, yy) << 24);
                 *reinterpret_cast<uint32_t *>((c ? rCr : rCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx) = u;
             }
             int16_t *lY = P.lev + (size_t)pic * pic_samples, *lCb = lY + (size_t)W * H, *lCr = lCb + (size_t)cw * chh;
             for (int i = tid; i < 512; i += NTHREADS) {  // luma levels, 2 per iteration
                 int yy = i >> 4, xx = (i & 15) * 2;
-                *reinterpret_cast<uint32_t *>(lY + (size_t)(g.cy + yy) * W + g.cx + xx) = *reinterpret_cast<const uint32_t *>(&S.lvY[yy * 32 + xx]);
+                *reinterpret_cast<uint32_t *>(lY + (size_t)(g.cy + yy) * W + g.cx + xx) = *reinterpret_cast<const uint32_t *>(&C.lvY[yy * 32 + xx]);
             }
             for (int i = tid; i < 256; i += NTHREADS) {
                 int c = i >> 7, t = i & 127, yy = t >> 3, xx = (t & 7) * 2;
                 *reinterpret_cast<uint32_t *>((c ? lCr : lCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx) =
-                    *reinterpret_cast<const uint32_t *>(&S.lvC[c][yy * 16 + xx]);
+                    *reinterpret_cast<const uint32_t *>(&C.lvC[c][yy * 16 + xx]);
             }
-            CtuRecord *r = P.records + (size_t)pic * Wc * P.Hc + cyi * Wc + cxi;
+            CtuRecord *r = P.records + (size_t)pic * Wc * P.Hc + C.cyi * Wc + C.cxi;
             for (int i = tid; i < 64; i += NTHREADS) {
-                r->luma_mode[i] = S.lm[i];
-                P.mode_map[(size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + (i >> 3)) * (W >> 2) + (g.cx >> 2) + (i & 7)] = S.lm[i];
+                r->luma_mode[i] = C.lm[i];
+                P.mode_map[(size_t)pic * (W >> 2) * (H >> 2) + (size_t)((g.cy >> 2) + (i >> 3)) * (W >> 2) + (g.cx >> 2) + (i & 7)] = C.lm[i];
             }
-            for (int i = tid; i < 16; i += NTHREADS) r->chroma_mode[i] = S.cm[i];
-            if (tid == 0) { r->split_mask = split_mask; r->cost = cost; }
+            for (int i = tid; i < 16; i += NTHREADS) r->chroma_mode[i] = C.cm[i];
+            if (tid == 0) { r->split_mask = C.mask; r->cost = C.leaf_cost; }
         }
         __threadfence();
         __syncthreads();
-        if (tid == 0) st_release(&done[cyi * Wc + cxi], P.epoch);
+        if (tid < KC && S.c[tid].active) {
+            const CtuCtx &C = S.c[tid];
+            st_release(P.done + (size_t)C.pic * Wc * P.Hc + C.cyi * Wc + C.cxi, P.epoch);
+        }
+        __syncthreads();
     }
 }
 
@@ -592,6 +749,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
     init_tables(S, P.tab, tid);
     __syncthreads();
     const WarpScratch ws = warp_scratch(S, 0);
+    Ctx V{&S.tb, &S.c[0]};
     if (P.op == 0) {  // predict one component of one TU from a picture's reconstruction
         CtuGeom g;
         g.cx = P.x & ~31; g.cy = P.y & ~31; g.W = P.W; g.H = P.H;
@@ -600,25 +758,25 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
         for (int i = tid; i < RY_ROWS * RY_STRIDE; i += NTHREADS) {
             int yy = i / RY_STRIDE - RY_Y0, xx = i % RY_STRIDE - RY_X0;
             int ax = g.cx + xx, ay = g.cy + yy;
-            S.recY[i] = (ax >= 0 && ax < P.W && ay >= 0 && ay < P.H) ? rY[(size_t)ay * P.W + ax] : 0;
+            S.c[0].recY[i] = (ax >= 0 && ax < P.W && ay >= 0 && ay < P.H) ? rY[(size_t)ay * P.W + ax] : 0;
         }
         for (int i = tid; i < 2 * RC_ROWS * RC_STRIDE; i += NTHREADS) {
             int c = i >= RC_ROWS * RC_STRIDE, j = i - c * RC_ROWS * RC_STRIDE;
             int yy = j / RC_STRIDE - RC_Y0, xx = j % RC_STRIDE - RC_X0;
             int ax = (g.cx >> 1) + xx, ay = (g.cy >> 1) + yy;
-            S.recC[c][j] = (ax >= 0 && ax < cw && ay >= 0 && ay < chh) ? (c ? rCr : rCb)[(size_t)ay * cw + ax] : 0;
+            S.c[0].recC[c][j] = (ax >= 0 && ax < cw && ay >= 0 && ay < chh) ? (c ? rCr : rCb)[(size_t)ay * cw + ax] : 0;
         }
         __syncthreads();
         Node nd;
         nd.x = P.x - g.cx; nd.y = P.y - g.cy; nd.w = P.w; nd.tree = P.tree; nd.ar = P.ar != 0; nd.bl = P.bl != 0;
         if (warp == 0) {
             const int c = P.c, n = nd.w >> (c != 0);
-            if (P.mode > 66) cclm_downsample(S, g, nd, lane);
-            else build_refs(S, g, nd, c, lane);
+            if (P.mode > 66) cclm_downsample(V, g, nd, lane);
+            else build_refs(V, g, nd, c, lane);
             __syncwarp();
             PredCtx pc;
-            pred_setup(S, g, nd, c, P.mode, ws.refx, lane, pc);
-            for (int i = lane; i < n * n; i += 32) P.out8[i] = (uint8_t)pred_sample(S, pc, i % n, i / n);
+            pred_setup(V, g, nd, c, P.mode, ws.refx, lane, pc);
+            for (int i = lane; i < n * n; i += 32) P.out8[i] = (uint8_t)pred_sample(V, pc, i % n, i / n);
         }
         return;
     }
@@ -643,7 +801,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
             for (int i = lane; i < nn; i += 32) out[i] = ws.A[i];
         } else if (P.op == 3) {
             int rate; bool any;
-            trellis(S, P.tab, ws.A, l2, ws.Wd, ws.B, lane, rate, any);
+            trellis(V, P.tab, ws.A, l2, ws.Wd, ws.B, lane, rate, any);
             for (int i = lane; i < nn; i += 32) out[i] = ws.B[i];
             if (lane == 0) P.outi[blk] = rate;
         } else if (P.op == 4) {
@@ -662,6 +820,7 @@ cudaError_t launch_block(const BlockParams &P, int grid, cudaStream_t stream) {
 }
 
 size_t search_smem_bytes() { return sizeof(Shared); }
+int search_ctus_per_cta() { return KC; }
 
 static size_t smem_request() {  // dev-time knob: WRENC_B200_SMEM_PAD bytes of extra dynamic shared memory lower the CTAs per SM
     size_t pad = 0;

@@ -24,14 +24,18 @@
 namespace wb {
 
 #ifndef WB_NW
-#define WB_NW 8
+#define WB_NW 16
 #endif
 #ifndef WB_MINB
-#define WB_MINB 2
+#define WB_MINB 1
 #endif
 constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
-constexpr int NBIG = NW < 3 ? NW : 3;  // warps with scratch large enough for a 32x32 luma pipeline (those tasks are listed first)
+#ifndef WB_K
+#define WB_K 4
+#endif
+constexpr int KC = WB_K;     // CTUs searched in lock step by one CTA
+constexpr int NBIG = NW < 3 * KC ? NW : 3 * KC;  // warps with scratch large enough for a 32x32 luma pipeline (those tasks are listed first)
 
 enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
 enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
@@ -84,9 +88,13 @@ struct WarpScratch {  // pointers into the scratch pool
 
 constexpr int MAXTASK = 48;
 
-struct Shared {
-    Tables tb;
-    // CTU state
+struct CtuGeom {
+    int cx, cy;  // absolute luma position of the CTU
+    int W, H;
+};
+
+// Everything that belongs to ONE CTU while it is searched.  A CTA searches WB_K independent CTUs in lock step.
+struct CtuCtx {
     uint8_t orgY[1024];
     uint8_t orgC[2][256];
     uint8_t recY[RY_ROWS * RY_STRIDE];
@@ -110,7 +118,23 @@ struct Shared {
     uint32_t r_ssd[MAXTASK];
     int32_t r_rate[MAXTASK];
     uint32_t r_sad[MAXTASK];
-    int item;
+    // control state: written by the CTU's decision thread, read by everyone after the next barrier
+    CtuGeom g;
+    int active, pic, cxi, cyi;
+    int root_mode;
+    unsigned mask, mask_sv[2];
+    float cost[3], split[3], leaf_cost;
+    int restore;
+    // leaf-evaluation state
+    float cost_pl, cost_dc, cur_cost, dir_cost, min_cost, cost_dm;
+    int cur, dir, mode, cclm_mode, v0, v1, cclm_wins;
+};
+
+struct Shared {
+    Tables tb;
+    CtuCtx c[WB_K];
+    int item0;
+    int ticket[2];            // dynamic task tickets of the current / previous phase
     // per-warp scratch
     int16_t bigA[NBIG][1024], bigB[NBIG][1024];
     uint16_t bigW[NBIG][1024];
@@ -121,15 +145,15 @@ struct Shared {
     int16_t refx[NW][100];
 };
 
+struct Ctx {  // what the per-CTU device functions see
+    Tables *tb;
+    CtuCtx *c;
+};
+
 struct Node {
     int x, y, w;  // CTU-relative luma position / size
     int tree;
     bool ar, bl;
-};
-
-struct CtuGeom {
-    int cx, cy;  // absolute luma position of the CTU
-    int W, H;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -153,10 +177,10 @@ __device__ __forceinline__ int warp_max(int v) {
     return v;
 }
 
-__device__ __forceinline__ uint8_t &RY(Shared &S, int x, int y) { return S.recY[(y + RY_Y0) * RY_STRIDE + x + RY_X0]; }
-__device__ __forceinline__ uint8_t &RC(Shared &S, int c, int x, int y) { return S.recC[c - 1][(y + RC_Y0) * RC_STRIDE + x + RC_X0]; }
-__device__ __forceinline__ int rec_at(Shared &S, int c, int x, int y) { return c == 0 ? RY(S, x, y) : RC(S, c, x, y); }
-__device__ __forceinline__ int org_at(Shared &S, int c, int x, int y) { return c == 0 ? S.orgY[y * 32 + x] : S.orgC[c - 1][y * 16 + x]; }
+__device__ __forceinline__ uint8_t &RY(const Ctx S, int x, int y) { return S.c->recY[(y + RY_Y0) * RY_STRIDE + x + RY_X0]; }
+__device__ __forceinline__ uint8_t &RC(const Ctx S, int c, int x, int y) { return S.c->recC[c - 1][(y + RC_Y0) * RC_STRIDE + x + RC_X0]; }
+__device__ __forceinline__ int rec_at(const Ctx S, int c, int x, int y) { return c == 0 ? RY(S, x, y) : RC(S, c, x, y); }
+__device__ __forceinline__ int org_at(const Ctx S, int c, int x, int y) { return c == 0 ? S.c->orgY[y * 32 + x] : S.c->orgC[c - 1][y * 16 + x]; }
 
 // encoder_context.rs:918-956 derive_neighbouring_block_availability, CTU-relative luma coordinates (H9)
 __device__ __forceinline__ bool nb_avail(const CtuGeom &g, const Node &nd, int xn, int yn, bool ar, bool bl) {
@@ -173,11 +197,11 @@ __device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float la
 // ---------------------------------------------------------------------------------------------------------------
 // reference samples (intra_predictor.rs:146-353), one warp per component
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void build_refs(Shared &S, const CtuGeom &g, const Node &nd, int c, int lane) {
+__device__ __noinline__ void build_refs(const Ctx S, const CtuGeom &g, const Node &nd, int c, int lane) {
     const int cs = c != 0;
     const int n = nd.w >> cs, xt = nd.x >> cs, yt = nd.y >> cs;
     const int nl = 2 * n + 1, na = 2 * n, tot = nl + na;
-    int16_t *seq = S.seq[c];
+    int16_t *seq = S.c->seq[c];
     unsigned masks[5];
     const int rounds = (tot + 31) >> 5;
     // sequence order: left[nl-1] ... left[0], above[0] ... above[na-1]
@@ -207,7 +231,7 @@ __device__ __noinline__ void build_refs(Shared &S, const CtuGeom &g, const Node 
 #pragma unroll
     for (int r = 4; r >= 0; r--)
         if (r < rounds && masks[r]) first = r * 32 + __ffs(masks[r]) - 1;
-    int16_t *L = S.refL[c][0], *A = S.refA[c][0];
+    int16_t *L = S.c->refL[c][0], *A = S.c->refA[c][0];
     int vals[5];
 #pragma unroll
     for (int r = 0; r < 5; r++) {
@@ -241,7 +265,7 @@ __device__ __noinline__ void build_refs(Shared &S, const CtuGeom &g, const Node 
     }
     __syncwarp();
     if (c == 0 && n >= 8) {  // [1 2 1] filtered copy, used by modes 0,2,34,66 (intra_predictor.rs:304-352)
-        int16_t *LF = S.refL[0][1], *AF = S.refA[0][1];
+        int16_t *LF = S.c->refL[0][1], *AF = S.c->refA[0][1];
         for (int i = lane; i < nl; i += 32) {
             int v;
             if (i == 0) v = (L[1] + 2 * L[0] + A[0] + 2) >> 2;
@@ -281,28 +305,28 @@ __device__ __forceinline__ int pdpc_w(int ns, int i) {
 }
 
 // CCLM luma accessor with the replication rules of intra_predictor.rs:1775-1818 (only the reachable cases)
-__device__ __forceinline__ int cclm_py(Shared &S, int bx, int by, bool avail_l, int y, int x) {
+__device__ __forceinline__ int cclm_py(const Ctx S, int bx, int by, bool avail_l, int y, int x) {
     if (x < 0 && !avail_l) x = 0;
     return RY(S, bx + x, by + y);
 }
-__device__ __forceinline__ int cclm_ds6(Shared &S, int bx, int by, bool avail_l, int sy, int sx) {
+__device__ __forceinline__ int cclm_ds6(const Ctx S, int bx, int by, bool avail_l, int sy, int sx) {
     return (cclm_py(S, bx, by, avail_l, sy, sx - 1) + cclm_py(S, bx, by, avail_l, sy + 1, sx - 1) + 2 * cclm_py(S, bx, by, avail_l, sy, sx) +
             2 * cclm_py(S, bx, by, avail_l, sy + 1, sx) + cclm_py(S, bx, by, avail_l, sy, sx + 1) + cclm_py(S, bx, by, avail_l, sy + 1, sx + 1) + 4) >> 3;
 }
 
 // down-sampled luma of the node (intra_predictor.rs:1854-1868), one warp
-__device__ __noinline__ void cclm_downsample(Shared &S, const CtuGeom &g, const Node &nd, int lane) {
+__device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom &g, const Node &nd, int lane) {
     Node tmp = nd;
     bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
     int tw = nd.w >> 1;
     for (int i = lane; i < tw * tw; i += 32) {
         int y = i / tw, x = i - y * tw;
-        S.pds[i] = (uint8_t)cclm_ds6(S, nd.x, nd.y, avail_l, 2 * y, 2 * x);
+        S.c->pds[i] = (uint8_t)cclm_ds6(S, nd.x, nd.y, avail_l, 2 * y, 2 * x);
     }
 }
 
 // derive (a,k,b) for one CCLM mode / component (intra_predictor.rs:1604-2031); uniform across the warp
-__device__ __noinline__ void cclm_params(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, PredCtx &pc) {
+__device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, PredCtx &pc) {
     const int tw = nd.w >> 1, th = tw, tx = nd.x >> 1, ty = nd.y >> 1;
     bool avail_l = nb_avail(g, nd, nd.x - 1, nd.y, false, false);
     bool avail_t = nb_avail(g, nd, nd.x, nd.y - 1, false, false);
@@ -391,7 +415,7 @@ __device__ __noinline__ void cclm_params(Shared &S, const CtuGeom &g, const Node
 }
 
 // per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
-__device__ __noinline__ void pred_setup(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+__device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
     const int cs = c != 0;
     const int n = nd.w >> cs;
     pc.mode = mode; pc.c = c; pc.n = n; pc.l2 = ilog2i(n);
@@ -404,8 +428,8 @@ __device__ __noinline__ void pred_setup(Shared &S, const CtuGeom &g, const Node 
         return;
     }
     const int filt = (c == 0 && n >= 8 && (mode == 0 || mode == 2 || mode == 34 || mode == 66)) ? 1 : 0;
-    pc.lf = S.refL[c][filt];
-    pc.ab = S.refA[c][filt];
+    pc.lf = S.c->refL[c][filt];
+    pc.ab = S.c->refA[c][filt];
     if (mode == MODE_PLANAR) {
         pc.kind = 0; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
         return;
@@ -455,12 +479,12 @@ __device__ __noinline__ void pred_setup(Shared &S, const CtuGeom &g, const Node 
     __syncwarp();
 }
 
-__device__ __noinline__ int pred_sample(Shared &S, const PredCtx &pc, int x, int y) {
+__device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x, int y) {
     const int n = pc.n;
     int p;
     if (pc.kind == 3) {
         if (pc.cclm128) return 128;
-        return clip8(((S.pds[y * n + x] * pc.a) >> pc.k) + pc.b);
+        return clip8(((S.c->pds[y * n + x] * pc.a) >> pc.k) + pc.b);
     }
     const int16_t *lrs = pc.lf + 1, *ars = pc.ab;
     if (pc.kind == 0) {
@@ -480,7 +504,7 @@ __device__ __noinline__ int pred_sample(Shared &S, const PredCtx &pc, int x, int
                 int h = ifact >> 1;
                 f0 = 16 - h; f1 = 32 - h; f2 = 16 + h; f3 = h;
             } else {
-                int pk = S.tb.fc[ifact];
+                int pk = S.tb->fc[ifact];
                 f0 = (int8_t)(pk & 255); f1 = (int8_t)((pk >> 8) & 255); f2 = (int8_t)((pk >> 16) & 255); f3 = (int8_t)((pk >> 24) & 255);
             }
             int s = f0 * r[0] + f1 * r[1] + f2 * r[2] + f3 * r[3];
@@ -550,8 +574,8 @@ __device__ __noinline__ void mm_cols(const int8_t *T, const int16_t *in, int16_t
 // ---------------------------------------------------------------------------------------------------------------
 // dependent quantisation (quantizer.rs:338-517 search_dq + 686-721 walk) and the rate walk (block_splitter.rs:415-460)
 // ---------------------------------------------------------------------------------------------------------------
-#define WB_LDQ(i) ((i) < 64 ? S.tb.ldq[(i)] : __ldg(&tab->ldq[min((i), 1023)]))
-#define WB_LV(i) ((i) < 64 ? S.tb.lv[(i)] : __ldg(&tab->lv[min((i), 1023)]))
+#define WB_LDQ(i) ((i) < 64 ? S.tb->ldq[(i)] : __ldg(&tab->ldq[min((i), 1023)]))
+#define WB_LV(i) ((i) < 64 ? S.tb->lv[(i)] : __ldg(&tab->lv[min((i), 1023)]))
 
 __device__ __forceinline__ unsigned map_compose(unsigned a, unsigned b) {  // apply a first, then b (4 x 2-bit next-state maps)
     unsigned r = 0;
@@ -569,7 +593,7 @@ struct LC {
 };
 constexpr int TR_INF = 1 << 28;
 
-__device__ __noinline__ LC local_costs(Shared &S, const DevTables *__restrict__ tab, int tc, unsigned w, int k, int kstar, int ls, int sh, int off, int ldq1) {
+__device__ __forceinline__ LC local_costs(const Ctx S, const DevTables *__restrict__ tab, int tc, unsigned w, int k, int kstar, int ls, int sh, int off, int ldq1) {
     LC r;
     const bool flagged = k > kstar;
     if (w & 2048u) {
@@ -646,12 +670,12 @@ __device__ __forceinline__ unsigned pos_map(unsigned pk, unsigned dec, bool nz) 
 // iteration, (D) each lane replays its chunk from its true entry costs to record the decisions, (F) the walk from the last
 // position (quantizer.rs:686-721) is a prefix scan over per-chunk next-state maps followed by a per-lane walk.  Costs are
 // int32 relative to the running minimum; the decisions are identical to the reference's i64 comparisons.
-__device__ __noinline__ void trellis(Shared &S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
+__device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
                         int &rate_out, bool &any_out) {
     const int n = 1 << l2, nn = n * n, sh = l2 + 4, off = 1 << (sh - 1);
     const int ls = tab->ls;
-    const uint16_t *scan = S.tb.scan + tab_off(l2);
-    const int ldq1 = S.tb.ldq[1];
+    const uint16_t *scan = S.tb->scan + tab_off(l2);
+    const int ldq1 = S.tb->ldq[1];
     // ---- A: x = S / ls per position; k* (H2)
     int kstar = -1;
     bool anytc = false;
@@ -731,11 +755,11 @@ __device__ __noinline__ void trellis(Shared &S, const DevTables *__restrict__ ta
 #pragma unroll
             for (int t = 0; t < 4; t++) M[s][t] = s == t ? 0 : TR_INF;
         if (vc) {
-            head = local_costs(S, tab, coef[scan[k0]], Wd[k0], k0, kstar, ls, sh, off, ldq1);
 #pragma unroll 1
-            for (int i = 1; i < CS; i++) {
+            for (int i = 0; i < CS; i++) {
                 const int k = k0 + i;
                 const LC l = local_costs(S, tab, coef[scan[k]], Wd[k], k, kstar, ls, sh, off, ldq1);
+                if (i == 0) { head = l; continue; }
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     int X = (l.pk & 1) ? M[2][t] : M[0][t], Y = (l.pk & 1) ? M[0][t] : M[2][t];
@@ -784,7 +808,7 @@ __device__ __noinline__ void trellis(Shared &S, const DevTables *__restrict__ ta
                     dec = leafdec;
                     pk = ((w >> 1) & 1u) * 3u;  // DC: a0 = x / 2 for both deltas
                 } else {
-                    const LC l = i == 0 ? head : local_costs(S, tab, coef[scan[k]], w, k, kstar, ls, sh, off, ldq1);
+                    const LC l = local_costs(S, tab, coef[scan[k]], w, k, kstar, ls, sh, off, ldq1);
                     dec = vstep(l, ldq1, C0, C1, C2, C3);
                     pk = l.pk;
                 }
@@ -799,7 +823,7 @@ __device__ __noinline__ void trellis(Shared &S, const DevTables *__restrict__ ta
     unsigned state = 0;
     bool seen_nz = false;
     int rate = 0;
-    const int lv0 = S.tb.lv[0];
+    const int lv0 = S.tb->lv[0];
     for (int r = rounds - 1; r >= 0; r--) {
         const int c = r * 32 + lane;
         const bool vc = c < nch;
@@ -866,38 +890,41 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
     return ws;
 }
 
-// SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
-__device__ __noinline__ unsigned sad_task(Shared &S, const CtuGeom &g, const Node &nd, int c, int mode, const WarpScratch &ws, int lane) {
+// prediction of one (mode, component) block: the only place pred_sample is instantiated in the search kernel.
+// Writes the samples to pred_out (may be null) and returns the SAD against the source block.
+__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
     PredCtx pc;
-    pred_setup(S, g, nd, c, mode, ws.refx, lane, pc);
+    pred_setup(S, g, nd, c, mode, refx, lane, pc);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
 #pragma unroll 1
     for (int i = lane; i < n * n; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int p = pred_sample(S, pc, x, y);
+        if (pred_out) pred_out[i] = (uint8_t)p;
         sad += abs(p - org_at(S, c, bx + x, by + y));
     }
     return warp_sumu(sad);
 }
 
+// SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
+__device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, const WarpScratch &ws, int lane) {
+    return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane);
+}
+
 // full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
 // commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
-__device__ __noinline__ void full_task(Shared &S, const DevTables *__restrict__ tab, const CtuGeom &g, const Node &nd, int c, int mode, bool commit,
+__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom &g, const Node &nd, int c, int mode, bool commit,
                           const WarpScratch &ws, int lane, unsigned &ssd_out, int &rate_out) {
-    PredCtx pc;
-    pred_setup(S, g, nd, c, mode, ws.refx, lane, pc);
-    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2, nn = n * n;
+    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
+    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
+    __syncwarp();
     int16_t *A = ws.A, *B = ws.B;
-    bool anyres = false;
+    bool anyres = anysad;
 #pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
-        int p = pred_sample(S, pc, x, y);
-        ws.pred[i] = (uint8_t)p;
-        int r = org_at(S, c, bx + x, by + y) - p;
-        A[i] = (int16_t)r;
-        anyres |= r != 0;
+        A[i] = (int16_t)(org_at(S, c, bx + x, by + y) - (int)ws.pred[i]);
     }
     anyres = __any_sync(0xffffffffu, anyres);
     __syncwarp();
@@ -905,9 +932,9 @@ __device__ __noinline__ void full_task(Shared &S, const DevTables *__restrict__ 
     bool anylev = false;
     int rate = 0;
     if (anyres) {
-        mm_rows(S.tb.Tt + to, A, B, n, l2, 1 << (l2 - 2), l2 - 1, false, lane);
+        mm_rows(S.tb->Tt + to, A, B, n, l2, 1 << (l2 - 2), l2 - 1, false, lane);
         __syncwarp();
-        mm_cols(S.tb.T + to, B, A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
+        mm_cols(S.tb->T + to, B, A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
         __syncwarp();
         trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
     } else {
@@ -915,7 +942,7 @@ __device__ __noinline__ void full_task(Shared &S, const DevTables *__restrict__ 
         __syncwarp();
     }
     if (commit) {
-        int16_t *dst = c == 0 ? S.lvY : S.lvC[c - 1];
+        int16_t *dst = c == 0 ? S.c->lvY : S.c->lvC[c - 1];
         const int stride = c == 0 ? 32 : 16;
         for (int i = lane; i < nn; i += 32) {
             int y = i >> l2, x = i & (n - 1);
@@ -927,10 +954,10 @@ __device__ __noinline__ void full_task(Shared &S, const DevTables *__restrict__ 
         for (int i = lane; i < nn; i += 32) A[i] = (int16_t)min(32767, max(-32768, ((int)B[i] * ls + off) >> sh));  // quantizer.rs:1074-1075
         __syncwarp();
         // vertical: V[y][x] = clamp16((sum_i T[i][y] * D[i][x] + 64) >> 7)   (Tt's rows are T's columns)
-        mm_cols(S.tb.Tt + to, A, B, n, l2, 64, 7, true, lane);
+        mm_cols(S.tb->Tt + to, A, B, n, l2, 64, 7, true, lane);
         __syncwarp();
         // horizontal: R[y][x] = (sum_i T[i][x] * V[y][i] + 2048) >> 12
-        mm_rows(S.tb.T + to, B, A, n, l2, 2048, 12, false, lane);
+        mm_rows(S.tb->T + to, B, A, n, l2, 2048, 12, false, lane);
         __syncwarp();
     }
     unsigned ssd = 0;
@@ -954,10 +981,10 @@ __device__ __noinline__ void full_task(Shared &S, const DevTables *__restrict__ 
 // ---------------------------------------------------------------------------------------------------------------
 // MPM derivation for the mode-bit estimate (ctu.rs:1498-1635) with the H1 neighbour semantics
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ int luma_kind(const Shared &S, const CtuGeom &g, const Node &nd, int mode, int root_mode) {
+__device__ __noinline__ int luma_kind(const Ctx S, const CtuGeom &g, const Node &nd, int mode, int root_mode) {
     if (mode == MODE_PLANAR) return 0;
     int left, above;
-    if (nd.x == 0) left = g.cx > 0 ? S.leftModes[(nd.y + nd.w - 1) >> 2] : MODE_PLANAR;
+    if (nd.x == 0) left = g.cx > 0 ? S.c->leftModes[(nd.y + nd.w - 1) >> 2] : MODE_PLANAR;
     else left = root_mode;
     above = nd.y == 0 ? MODE_PLANAR : root_mode;
     int cand[5];

@@ -18,7 +18,7 @@ static_assert(sizeof(CtuRecord) == 88, "record layout is part of the C ABI");
 struct SearchParams {
     int W, H, Wc, Hc;      // luma size, CTUs per row / column
     int max_depth;
-    int n_items;
+    int n_items;           // number of slots (batches x CTUs per CTA)
     int epoch;             // value a done flag takes when its CTU is final in THIS launch
     const uint8_t *orig;   // [pic][W*H*3/2] I420
     uint8_t *rec;          // same geometry
@@ -26,7 +26,7 @@ struct SearchParams {
     uint8_t *mode_map;     // [pic][(W/4)*(H/4)] final luma mode per 4x4 (left-CTU MPM lookups, H1)
     CtuRecord *records;    // [pic][Wc*Hc]
     int *done;             // [pic][Wc*Hc]
-    const uint32_t *items; // work list: pic<<16 | cy<<8 | cx
+    const uint32_t *items; // work list: batches of search_ctus_per_cta() slots, pic<<16 | cy<<8 | cx or 0xffffffff (empty slot)
     unsigned int *counter; // work-list cursor
     const DevTables *tab;
 };
@@ -45,6 +45,7 @@ struct BlockParams {
 cudaError_t launch_block(const BlockParams &P, int grid, cudaStream_t stream);
 size_t search_smem_bytes();
 int search_ctas_per_sm();
+int search_ctus_per_cta();  // CTUs one CTA searches in lock step; the work list is made of batches of this many slots
 cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream);
 
 }  // namespace wb
