@@ -35,7 +35,8 @@ enum {
     WRENC_B200_ENODEV = -2,  /* no CUDA device / not sm_100 capable */
     WRENC_B200_ECUDA = -3,   /* CUDA runtime error */
     WRENC_B200_EAGAIN = -4,  /* receive with nothing submitted */
-    WRENC_B200_EFULL = -5    /* submit while pictures_in_flight pictures are pending (call receive first) */
+    WRENC_B200_EFULL = -5,   /* submit while pictures_in_flight pictures are pending (call receive first) */
+    WRENC_B200_EOVERFLOW = -6 /* slice_data of a picture did not fit the coder's buffers */
 };
 
 typedef struct {
@@ -46,6 +47,7 @@ typedef struct {
     int32_t pictures_in_flight;   /* pictures searched by one kernel launch (CTU wavefronts of all of them interleave) */
     int32_t want_recon;           /* copy reconstructed planes back (--reconst) */
     int32_t want_decisions;       /* copy per-CTU records + quantised levels back (parity / phase-1 consumers) */
+    int32_t want_slice_data;      /* CABAC-code the decided pictures on the device and return slice_data() bytes */
     const char *extra_params;     /* "k=v,k=v" or NULL: keys of reference --extra-params */
 } wrenc_b200_config;
 
@@ -84,6 +86,13 @@ int wrenc_b200_pending(const wrenc_b200 *h);
  * handle's own stream) and does not synchronise.  Returns the number of search-kernel launches enqueued (>=1) or <0. */
 int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t *d_yuv, uint8_t *d_rec, int16_t *d_levels,
                                wrenc_b200_ctu_record *d_records, void *stream);
+/* Phase 2 on resident data: CABAC-codes the pictures the preceding wrenc_b200_search_resident call on this handle decided
+ * (same n_pictures, its d_levels / d_records) into d_out[n_pictures][out_cap] bytes and d_out_len[n_pictures] (-1 = overflow).
+ * Device pointers; runs on `stream` after the search; does not synchronise.  Returns kernel launches enqueued (2) or <0.
+ * Replaces CtuEncoder::encode_coding_tree .. encode_residual + BoolCoder (src/ctu_encoder.rs:227-2269, src/bool_coder.rs:136-296)
+ * and the end_of_slice_one_bit / byte alignment of SliceEncoder::encode (src/slice_encoder.rs:380-388,419). */
+int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d_levels, const wrenc_b200_ctu_record *d_records, uint8_t *d_out,
+                             size_t out_cap, int32_t *d_out_len, void *stream);
 /* Workspace the resident entry needs for n_pictures (bytes of device memory it will allocate once and keep). */
 size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n_pictures);
 

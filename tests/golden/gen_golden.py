@@ -39,9 +39,9 @@ def make_frame(kind, W, H, s):
 def main():
     for name, W, H, qp, depth, kind, s, extra in CASES:
         y, cb, cr = make_frame(kind, W, H, s)
-        o = Oracle(qp, depth, extra).encode_picture(y, cb, cr)
+        o = Oracle(qp, depth, extra).encode_picture(y, cb, cr, want_slice_data=True)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), y=y, cb=cb, cr=cr, rec_y=o["rec"][0], rec_cb=o["rec"][1], rec_cr=o["rec"][2],
-                            coef_y=o["coef"][0], coef_cb=o["coef"][1], coef_cr=o["coef"][2], records=o["records"].view(np.uint8),
+                            coef_y=o["coef"][0], coef_cb=o["coef"][1], coef_cr=o["coef"][2], records=o["records"].view(np.uint8), slice_data=np.frombuffer(o["slice_data"], np.uint8),
                             qp=qp, depth=depth, extra=extra or "")
         print(name, "ok", sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.startswith(name)))
 

@@ -21,6 +21,8 @@ def assert_same(o, r, what=""):
     assert np.array_equal(a["split_mask"], b["split_mask"]), what
     assert np.array_equal(a["luma_mode"], b["luma_mode"]) and np.array_equal(a["chroma_mode"], b["chroma_mode"]), what
     assert a["cost"].tobytes() == b["cost"].tobytes(), f"{what}: f32 RD cost differs"
+    if "slice_data" in o and "slice_data" in r:
+        assert o["slice_data"] == r["slice_data"], f"{what}: CABAC-coded slice_data differs ({len(o['slice_data'])} vs {len(r['slice_data'])} bytes)"
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
@@ -31,7 +33,7 @@ def test_golden_fixtures(path):
     r = enc.encode_pictures([(g["y"], g["cb"], g["cr"])])[0]
     enc.close()
     o = {"rec": [g["rec_y"], g["rec_cb"], g["rec_cr"]], "coef": [g["coef_y"], g["coef_cb"], g["coef_cr"]],
-         "records": g["records"].view(wrenc_b200.RECORD_DTYPE)}
+         "records": g["records"].view(wrenc_b200.RECORD_DTYPE), "slice_data": g["slice_data"].tobytes()}
     assert_same(o, r, os.path.basename(path))
 
 
@@ -42,7 +44,7 @@ def test_cif_two_frames_qp32():
     res = enc.encode_pictures(frames)
     ora = Oracle(32, 3)
     for i, (f, r) in enumerate(zip(frames, res)):
-        assert_same(ora.encode_picture(*f), r, f"frame {i}")
+        assert_same(ora.encode_picture(*f, want_slice_data=True), r, f"frame {i}")
     enc.close()
 
 
@@ -53,7 +55,7 @@ def test_qp_sweep(qp):
     enc = wrenc_b200.SearchEncoder(160, 96, qp=qp, pictures_in_flight=1)
     r = enc.encode_pictures([f])[0]
     enc.close()
-    assert_same(Oracle(qp, 3).encode_picture(*f), r, f"qp {qp}")
+    assert_same(Oracle(qp, 3).encode_picture(*f, want_slice_data=True), r, f"qp {qp}")
 
 
 def test_random_and_flat_content_and_batching_independence():
@@ -61,7 +63,7 @@ def test_random_and_flat_content_and_batching_independence():
               (np.zeros((96, 128), np.uint8), np.full((48, 64), 255, np.uint8), np.full((48, 64), 1, np.uint8)),
               wrenc_b200.random_frame(128, 96, 2)]
     ora = Oracle(32, 3)
-    want = [ora.encode_picture(*f) for f in frames]
+    want = [ora.encode_picture(*f, want_slice_data=True) for f in frames]
     for inflight in (1, 3, 4):
         enc = wrenc_b200.SearchEncoder(128, 96, qp=32, pictures_in_flight=inflight)
         res = enc.encode_pictures(frames)
@@ -77,7 +79,7 @@ def test_single_ctu_and_single_row_and_single_column_pictures():
         enc = wrenc_b200.SearchEncoder(W, H, qp=32, pictures_in_flight=1)
         r = enc.encode_pictures([f])[0]
         enc.close()
-        assert_same(Oracle(32, 3).encode_picture(*f), r, f"{W}x{H}")
+        assert_same(Oracle(32, 3).encode_picture(*f, want_slice_data=True), r, f"{W}x{H}")
 
 
 def test_api_errors():
@@ -126,4 +128,4 @@ def test_full_size_properties_1080p():
     enc = wrenc_b200.SearchEncoder(sw, sh, qp=32, pictures_in_flight=1)
     r = enc.encode_pictures([sub])[0]
     enc.close()
-    assert_same(Oracle(32, 3).encode_picture(*sub), r, "640x352 sub-picture")
+    assert_same(Oracle(32, 3).encode_picture(*sub, want_slice_data=True), r, "640x352 sub-picture")

@@ -91,11 +91,12 @@ def test_h3_dc_wrap_is_reachable_and_signed(oracle32):
 @pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
 def test_oracle_matches_golden(path):
     g = np.load(path)
-    o = Oracle(int(g["qp"]), int(g["depth"]), str(g["extra"]) or None).encode_picture(g["y"], g["cb"], g["cr"])
+    o = Oracle(int(g["qp"]), int(g["depth"]), str(g["extra"]) or None).encode_picture(g["y"], g["cb"], g["cr"], want_slice_data=True)
     for c, k in enumerate(("y", "cb", "cr")):
         assert np.array_equal(o["rec"][c], g["rec_" + k])
         assert np.array_equal(o["coef"][c], g["coef_" + k])
     assert o["records"].tobytes() == g["records"].tobytes()
+    assert o["slice_data"] == g["slice_data"].tobytes()
 
 
 def test_oracle_reconstruction_is_plausible():
@@ -107,3 +108,22 @@ def test_oracle_reconstruction_is_plausible():
         mse = ((o["rec"][0].astype(float) - y) ** 2).mean()
         psnr.append(10 * np.log10(255 ** 2 / mse))
     assert psnr[0] > psnr[1] + 4 and psnr[1] > 25
+
+
+def test_slice_data_structure():
+    """slice_data() is byte aligned, ends with the rbsp stop bit followed by zero bits only, grows when QP drops, and is
+    deterministic (the CABAC engine is re-initialised per picture)."""
+    from wrenc_b200.synth import synth_frame
+    y, cb, cr = synth_frame(96, 64, frame=1)
+    sizes = []
+    for qp in (37, 32, 27, 22):
+        sd = Oracle(qp).encode_picture(y, cb, cr, want_slice_data=True)["slice_data"]
+        assert len(sd) > 0 and sd[-1] != 0
+        last = sd[-1]
+        assert (last & -last) == (last & -last) and last & ((last & -last)) != 0  # lowest set bit is the stop bit
+        sizes.append(len(sd))
+        assert sd == Oracle(qp).encode_picture(y, cb, cr, want_slice_data=True)["slice_data"]
+    assert sizes == sorted(sizes) and sizes[-1] > 3 * sizes[0]
+    flat = (np.full((64, 64), 128, np.uint8), np.full((32, 32), 128, np.uint8), np.full((32, 32), 128, np.uint8))
+    sd = Oracle(32).encode_picture(*flat, want_slice_data=True)["slice_data"]
+    assert len(sd) <= 8  # four CTUs of planar/DM with no residual: a handful of bins

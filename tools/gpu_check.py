@@ -65,7 +65,14 @@ def main():
         frames = [wrenc_b200.synth_frame(W, H, frame=f) if kind == "synth" else wrenc_b200.random_frame(W, H, 100 + f) for f in range(2)]
         t = time.time(); res = enc.encode_pictures(frames); dt = time.time() - t
         for f, ((yy, cbb, crr), r) in enumerate(zip(frames, res)):
-            o = ora.encode_picture(yy, cbb, crr)
+            o = ora.encode_picture(yy, cbb, crr, want_slice_data=True)
+            sdsame = o['slice_data'] == r['slice_data']
+            print('   slice_data', 'same' if sdsame else 'DIFF', len(o['slice_data']), len(r['slice_data']))
+            if not sdsame:
+                a, b = o['slice_data'], r['slice_data']
+                k = next((i for i in range(min(len(a), len(b))) if a[i] != b[i]), min(len(a), len(b)))
+                print('   first differing byte', k)
+            ok &= sdsame
             same = all(np.array_equal(o["rec"][c], r["rec"][c]) for c in range(3)) and all(np.array_equal(o["coef"][c], r["coef"][c]) for c in range(3)) and o["records"].tobytes() == r["records"].tobytes()
             print(kind, "frame", f, "bit-exact" if same else "MISMATCH", "gpu %.3fs" % dt)
             ok &= same

@@ -44,6 +44,15 @@ struct wrenc_b200 {
     std::vector<uint64_t> pic_ids;
     int n_filled = 0, n_returned = 0, last_returned = -1;
     bool launched = false;
+    // phase 2: slice_data coder buffers (sized for coder_pics pictures)
+    int coder_pics = 0;
+    uint16_t *d_bins = nullptr;
+    int *d_bin_count = nullptr;
+    uint8_t *d_out = nullptr;
+    int *d_out_len = nullptr;
+    size_t out_cap = 0;
+    uint8_t *h_out = nullptr;
+    int *h_out_len = nullptr;
     cudaEvent_t ev_done = nullptr;
     unsigned long long launches = 0;
 };
@@ -140,6 +149,39 @@ static int enqueue_search(wrenc_b200 *h, int n_pics, const uint8_t *d_yuv, uint8
     return 0;
 }
 
+static const int kBinCap = 6144;  // 16-bit bin entries per CTU (context bins are bounded by 7/4 per sample = 2688; the rest is bypass)
+
+static int ensure_coder(wrenc_b200 *h, int n_pics) {
+    if (n_pics <= h->coder_pics) return 0;
+    CK(cudaSetDevice(h->cfg.device));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_out); cudaFree(h->d_out_len);
+    h->d_bins = nullptr; h->d_bin_count = nullptr; h->d_out = nullptr; h->d_out_len = nullptr;
+    const size_t nctu = (size_t)h->Wc * h->Hc * n_pics;
+    h->out_cap = (size_t)h->W * h->H * 3 / 4;
+    CK(cudaMalloc(&h->d_bins, nctu * kBinCap * sizeof(uint16_t)));
+    CK(cudaMalloc(&h->d_bin_count, nctu * sizeof(int)));
+    CK(cudaMalloc(&h->d_out, (size_t)n_pics * h->out_cap));
+    CK(cudaMalloc(&h->d_out_len, (size_t)n_pics * sizeof(int)));
+    h->coder_pics = n_pics;
+    return 0;
+}
+
+// CABAC-code the pictures the last search on this handle decided (the mode map lives in the handle's workspace)
+static int enqueue_coder(wrenc_b200 *h, int n_pics, const int16_t *d_lev, const CtuRecord *d_records, uint8_t *d_out, size_t out_cap, int *d_out_len,
+                         cudaStream_t st) {
+    int rc = ensure_coder(h, n_pics);
+    if (rc) return rc;
+    SyntaxParams Q;
+    Q.W = h->W; Q.H = h->H; Q.Wc = h->Wc; Q.Hc = h->Hc; Q.n_pics = n_pics; Q.qp = h->cfg.qp;
+    Q.lev = d_lev; Q.records = d_records; Q.mode_map = h->d_mode_map;
+    Q.bins = h->d_bins; Q.bin_cap = kBinCap; Q.bin_count = h->d_bin_count;
+    Q.out = d_out; Q.out_cap = out_cap; Q.out_len = d_out_len;
+    CK(launch_slice_coder(Q, st));
+    h->launches += 2;
+    return 0;
+}
+
 extern "C" {
 
 const char *wrenc_b200_version(void) { return "wrenc_b200 0.1 (sm_100a)"; }
@@ -211,6 +253,8 @@ void wrenc_b200_destroy(wrenc_b200 *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_tab); cudaFree(h->d_mode_map); cudaFree(h->d_done); cudaFree(h->d_items); cudaFree(h->d_counter);
     cudaFree(h->d_orig); cudaFree(h->d_rec); cudaFree(h->d_lev); cudaFree(h->d_rec_ctu);
+    cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_out); cudaFree(h->d_out_len);
+    cudaFreeHost(h->h_out); cudaFreeHost(h->h_out_len);
     cudaFreeHost(h->h_orig); cudaFreeHost(h->h_rec); cudaFreeHost(h->h_lev); cudaFreeHost(h->h_records);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -262,6 +306,18 @@ int wrenc_b200_flush(wrenc_b200 *h) {
     const size_t ps = h->pic_samples, nctu = (size_t)h->Wc * h->Hc;
     int rc = enqueue_search(h, n, h->d_orig, h->d_rec, h->d_lev, h->d_rec_ctu, h->stream);
     if (rc) return rc;
+    if (h->cfg.want_slice_data) {
+        rc = ensure_coder(h, h->B);
+        if (rc) return rc;
+        if (!h->h_out) {
+            CK(cudaHostAlloc(&h->h_out, (size_t)h->B * h->out_cap, cudaHostAllocDefault));
+            CK(cudaHostAlloc(&h->h_out_len, (size_t)h->B * sizeof(int), cudaHostAllocDefault));
+        }
+        rc = enqueue_coder(h, n, h->d_lev, h->d_rec_ctu, h->d_out, h->out_cap, h->d_out_len, h->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->h_out_len, h->d_out_len, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(h->h_out, h->d_out, (size_t)n * h->out_cap, cudaMemcpyDeviceToHost, h->stream));
+    }
     CK(cudaMemcpyAsync(h->h_records, h->d_rec_ctu, n * nctu * sizeof(CtuRecord), cudaMemcpyDeviceToHost, h->stream));
     if (h->cfg.want_recon) CK(cudaMemcpyAsync(h->h_rec, h->d_rec, n * ps, cudaMemcpyDeviceToHost, h->stream));
     if (h->cfg.want_decisions) CK(cudaMemcpyAsync(h->h_lev, h->d_lev, n * ps * sizeof(int16_t), cudaMemcpyDeviceToHost, h->stream));
@@ -287,8 +343,16 @@ int wrenc_b200_receive(wrenc_b200 *h, uint64_t *pic_idx, const uint8_t **slice_d
     const int i = h->n_returned;
     const size_t ps = h->pic_samples, ny = (size_t)h->W * h->H, nc = ny / 4;
     if (pic_idx) *pic_idx = h->pic_ids[i];
-    if (slice_data) *slice_data = nullptr;  // phase 2 (device CABAC) not built yet: the slice_data coder stays on the caller's side
+    if (slice_data) *slice_data = nullptr;
     if (len) *len = 0;
+    if (h->cfg.want_slice_data) {
+        if (h->h_out_len[i] < 0) {
+            h->err = "slice_data coder overflow (bin arena or output buffer too small for this picture)";
+            return WRENC_B200_EOVERFLOW;
+        }
+        if (slice_data) *slice_data = h->h_out + (size_t)i * h->out_cap;
+        if (len) *len = (size_t)h->h_out_len[i];
+    }
     const uint8_t *r = h->cfg.want_recon ? h->h_rec + (size_t)i * ps : nullptr;
     if (rec_y) *rec_y = r;
     if (rec_cb) *rec_cb = r ? r + ny : nullptr;
@@ -329,6 +393,19 @@ int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t 
     int rc = enqueue_search(h, n_pictures, d_yuv, d_rec, d_levels, reinterpret_cast<CtuRecord *>(d_records), st);
     if (rc) return rc;
     return 1;
+}
+
+int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d_levels, const wrenc_b200_ctu_record *d_records, uint8_t *d_out,
+                             size_t out_cap, int32_t *d_out_len, void *stream) {
+    if (!h || n_pictures <= 0 || !d_levels || !d_records || !d_out || !d_out_len || out_cap == 0) return WRENC_B200_EINVAL;
+    if (n_pictures > h->ws_pics) {
+        h->err = "wrenc_b200_code_resident must follow wrenc_b200_search_resident of the same pictures on this handle";
+        return WRENC_B200_EINVAL;
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    int rc = enqueue_coder(h, n_pictures, d_levels, reinterpret_cast<const CtuRecord *>(d_records), d_out, out_cap, d_out_len, st);
+    return rc ? rc : 2;
 }
 
 size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n) {

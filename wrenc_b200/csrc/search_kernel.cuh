@@ -37,8 +37,6 @@ constexpr int NTHREADS = NW * 32;
 constexpr int KC = WB_K;     // CTUs searched in lock step by one CTA
 constexpr int NBIG = NW < 3 * KC ? NW : 3 * KC;  // warps with scratch large enough for a 32x32 luma pipeline (those tasks are listed first)
 
-enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
-enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // constant tables

@@ -31,6 +31,23 @@ struct SearchParams {
     const DevTables *tab;
 };
 
+enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
+enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
+
+struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_data() per picture
+    int W, H, Wc, Hc, n_pics, qp;
+    const int16_t *lev;        // [pic][W*H*3/2]
+    const CtuRecord *records;  // [pic][Wc*Hc]
+    const uint8_t *mode_map;   // [pic][(W/4)*(H/4)]
+    uint16_t *bins;            // bin arena: [pic][ctu][bin_cap] entries: ctx index | bin << 9 | bypass << 10
+    int bin_cap;
+    int *bin_count;            // [pic][ctu] entries produced (may exceed bin_cap: overflow)
+    uint8_t *out;              // [pic][out_cap] bytes
+    size_t out_cap;
+    int *out_len;              // [pic] bytes written, -1 on overflow
+};
+cudaError_t launch_slice_coder(const SyntaxParams &Q, cudaStream_t stream);
+
 struct BlockParams {
     int op;  // 0 predict, 1 forward DCT, 2 inverse DCT, 3 dep-quant (+rate), 4 dequantise
     int W, H, x, y, w, tree, ar, bl, c, mode;

@@ -20,7 +20,7 @@ MODE_LT_CCLM, MODE_L_CCLM, MODE_T_CCLM = 81, 82, 83
 
 EXPORTS = [
     "wrenc_b200_create", "wrenc_b200_destroy", "wrenc_b200_last_error", "wrenc_b200_submit", "wrenc_b200_receive",
-    "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident",
+    "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident", "wrenc_b200_code_resident",
     "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
     "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts",
@@ -30,7 +30,7 @@ EXPORTS = [
 class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("qp", C.c_int32), ("max_split_depth", C.c_int32),
                 ("device", C.c_int32), ("pictures_in_flight", C.c_int32), ("want_recon", C.c_int32),
-                ("want_decisions", C.c_int32), ("extra_params", C.c_char_p)]
+                ("want_decisions", C.c_int32), ("want_slice_data", C.c_int32), ("extra_params", C.c_char_p)]
 
 
 class Consts(C.Structure):
@@ -73,6 +73,8 @@ def load_library():
     L.wrenc_b200_pending.argtypes = [vp]
     L.wrenc_b200_search_resident.restype = C.c_int
     L.wrenc_b200_search_resident.argtypes = [vp, i32, vp, vp, vp, vp, vp]
+    L.wrenc_b200_code_resident.restype = C.c_int
+    L.wrenc_b200_code_resident.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, vp, vp]
     L.wrenc_b200_workspace_bytes.restype = C.c_size_t
     L.wrenc_b200_workspace_bytes.argtypes = [vp, i32]
     L.wrenc_b200_get_consts.restype = C.c_int
@@ -123,13 +125,13 @@ class SearchEncoder:
     """One handle per GPU.  Mirrors the reference flags: --qp, --max-split-depth, --extra-params, --reconst."""
 
     def __init__(self, width, height, qp=26, max_split_depth=3, device=0, pictures_in_flight=8, want_recon=True,
-                 want_decisions=True, extra_params=None):
+                 want_decisions=True, extra_params=None, want_slice_data=True):
         self.L = load_library()
         self.h = C.c_void_p()
         self.width, self.height = int(width), int(height)
         self._extra = extra_params.encode() if extra_params else None
         cfg = Config(self.width, self.height, int(qp), int(max_split_depth), int(device), int(pictures_in_flight),
-                     int(bool(want_recon)), int(bool(want_decisions)), self._extra)
+                     int(bool(want_recon)), int(bool(want_decisions)), int(bool(want_slice_data)), self._extra)
         rc = self.L.wrenc_b200_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
             msg = self.L.wrenc_b200_last_error(None).decode()
@@ -211,6 +213,12 @@ class SearchEncoder:
             return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
         st = C.c_void_p(int(stream)) if stream else None
         return self._check(self.L.wrenc_b200_search_resident(self.h, int(n_pictures), p(d_yuv), p(d_rec), p(d_levels), p(d_records), st))
+
+    def code_resident(self, n_pictures, d_levels, d_records, d_out, out_cap, d_out_len, stream=None):
+        def p(t):
+            return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+        st = C.c_void_p(int(stream)) if stream else None
+        return self._check(self.L.wrenc_b200_code_resident(self.h, int(n_pictures), p(d_levels), p(d_records), p(d_out), int(out_cap), p(d_out_len), st))
 
     # ---- per-block entry points ----
     def block_predict(self, rec, x, y, w, tree, ar, bl, c, mode):
