@@ -3,11 +3,12 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
 
-A step = one pass of the hot path (the whole RD search of every CTU) over F synthetic 1920x1088 I420 frames per GPU at
+A step = one pass of the hot path (the whole RD search of every CTU, then the CABAC coding of every picture) over F synthetic 1920x1088 I420 frames per GPU at
 QP32, --max-split-depth 3 (BASELINE.json configs[2]).  Frames are independent IDR pictures, so ranks shard picture
 ranges and there is no data-path collective ("scaling": "weak": every rank searches its own F frames per step).
 
-  value        frames/s, inputs resident in HBM, timed with CUDA events on the launching stream, max over ranks
+  value        frames/s of the whole hot path (search kernel + syntax/CABAC kernels), inputs resident in HBM, timed with
+               CUDA events on the launching stream, max over ranks
   e2e          same metric through the C-ABI submit/receive calls with HOST planes: H2D of every frame and D2H of the
                per-CTU records + quantised levels inside the timed region
   roofline     INT32 issue roofline of the search kernel: 8 290 304 nominal integer ops per CTU
@@ -35,7 +36,7 @@ W, H, QP, DEPTH = 1920, 1088, 32, 3
 CTUS_PER_FRAME = (W // 32) * (H // 32)
 OPS_PER_CTU = 8290304          # SURVEY.md §8(d) nominal integer ops per CTU (transforms 4 358 144 + trellis 3 932 160)
 ALG_BYTES_PER_CTU = 1536 + 1536 + 3072 + 88   # source read + recon write + level write + record
-METRIC = "1080p all-intra frames/s (RD search, bit-exact vs oracle)"
+METRIC = "1080p all-intra frames/s (RD search + CABAC slice_data, byte-identical vs oracle)"
 UNIT = "frames/s"
 
 
@@ -174,14 +175,18 @@ def run_ours(args):
     d_records = torch.empty((F * CTUS_PER_FRAME, 88), dtype=torch.uint8, device=dev)
 
     enc = wrenc_b200.SearchEncoder(W, H, qp=QP, max_split_depth=DEPTH, device=local, pictures_in_flight=args.e2e_batch,
-                                   want_recon=False, want_decisions=True)
+                                   want_recon=False, want_decisions=False, want_slice_data=True)
+    out_cap = pic_bytes
+    d_out = torch.empty((F, out_cap), dtype=torch.uint8, device=dev)
+    d_out_len = torch.empty(F, dtype=torch.int32, device=dev)
     tstream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: its handle goes through the C ABI
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
 
-    def step():
-        return enc.search_resident(F, d_yuv, d_rec, d_lev, d_records, stream)
+    def step():  # the whole hot path: RD search of every CTU, then syntax + CABAC coding of every picture
+        n = enc.search_resident(F, d_yuv, d_rec, d_lev, d_records, stream)
+        return n + enc.code_resident(F, d_lev, d_records, d_out, out_cap, d_out_len, stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -216,6 +221,10 @@ def run_ours(args):
         a = d_rec[0]
         b = d_rec[n_unique]
         assert torch.equal(a, b), "repeated input frame produced a different reconstruction"
+        la, lb = int(d_out_len[0]), int(d_out_len[n_unique])
+        assert la == lb and la > 0 and torch.equal(d_out[0, :la], d_out[n_unique, :lb]), "repeated input frame produced different slice_data"
+    coded_bytes = int(d_out_len.to(torch.int64).sum().item())
+    assert int(d_out_len.min().item()) > 0, "slice_data coder reported an overflow"
 
     # ---- e2e: host planes through submit/receive
     planes = [(host[i, :W * H].reshape(H, W), host[i, W * H:W * H * 5 // 4].reshape(H // 2, W // 2), host[i, W * H * 5 // 4:].reshape(H // 2, W // 2))
@@ -233,7 +242,7 @@ def run_ours(args):
                 i += 1
             while enc.pending():
                 r = enc.receive(copy=False)
-                cost += float(r["records"]["cost"][0])
+                cost += float(r["records"]["cost"][0]) + len(r["slice_data"])
                 got += 1
         return cost
 
@@ -287,13 +296,13 @@ def run_ours(args):
                "sample": f"{cores} processes x {rows} CTU rows (1920x{rows * 32}) of a 1920x1088 QP32 frame, {dt:.1f} s wall; frames = CTUs/2040"}
 
     h2d = Fe * pic_bytes
-    d2h = Fe * (pic_bytes * 2 + CTUS_PER_FRAME * 88)
+    d2h = Fe * (CTUS_PER_FRAME * 88) + int(coded_bytes / F * Fe)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32/f32-cost", "data": f"synthetic ({n_unique} unique frames per GPU, repeated to {F})",
-            "config": workload_config(args, F), "ctus_per_s": value * CTUS_PER_FRAME,
+            "config": workload_config(args, F), "ctus_per_s": value * CTUS_PER_FRAME, "coded_bytes_per_frame": coded_bytes / F,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "frames_per_step": Fe,
-                    "steps": args.e2e_steps, "batch": args.e2e_batch, "note": "host numpy planes -> submit/receive; D2H = CTU records + int16 levels"},
+                    "steps": args.e2e_steps, "batch": args.e2e_batch, "note": "host numpy planes -> submit/receive; D2H = CABAC-coded slice_data of every picture + CTU records"},
             "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "clocks": clocks}
     print(json.dumps(line))
     if dist is not None:

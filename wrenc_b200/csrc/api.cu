@@ -47,7 +47,9 @@ struct wrenc_b200 {
     // phase 2: slice_data coder buffers (sized for coder_pics pictures)
     int coder_pics = 0;
     uint16_t *d_bins = nullptr;
+    size_t bins_cap = 0;
     int *d_bin_count = nullptr;
+    unsigned long long *d_bin_offset = nullptr, *d_bin_total = nullptr;
     uint8_t *d_out = nullptr;
     int *d_out_len = nullptr;
     size_t out_cap = 0;
@@ -149,25 +151,27 @@ static int enqueue_search(wrenc_b200 *h, int n_pics, const uint8_t *d_yuv, uint8
     return 0;
 }
 
-static const int kBinCap = 6144;  // 16-bit bin entries per CTU (context bins are bounded by 7/4 per sample = 2688; the rest is bypass)
-
 static int ensure_coder(wrenc_b200 *h, int n_pics) {
     if (n_pics <= h->coder_pics) return 0;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_out); cudaFree(h->d_out_len);
-    h->d_bins = nullptr; h->d_bin_count = nullptr; h->d_out = nullptr; h->d_out_len = nullptr;
+    cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_out); cudaFree(h->d_out_len);
+    h->d_bin_count = nullptr; h->d_bin_offset = nullptr; h->d_out = nullptr; h->d_out_len = nullptr;
     const size_t nctu = (size_t)h->Wc * h->Hc * n_pics;
-    h->out_cap = (size_t)h->W * h->H * 3 / 4;
-    CK(cudaMalloc(&h->d_bins, nctu * kBinCap * sizeof(uint16_t)));
+    h->out_cap = (size_t)h->W * h->H * 3 / 2;
     CK(cudaMalloc(&h->d_bin_count, nctu * sizeof(int)));
+    CK(cudaMalloc(&h->d_bin_offset, nctu * sizeof(unsigned long long)));
     CK(cudaMalloc(&h->d_out, (size_t)n_pics * h->out_cap));
     CK(cudaMalloc(&h->d_out_len, (size_t)n_pics * sizeof(int)));
+    if (!h->d_bin_total) CK(cudaMalloc(&h->d_bin_total, sizeof(unsigned long long)));
     h->coder_pics = n_pics;
     return 0;
 }
 
-// CABAC-code the pictures the last search on this handle decided (the mode map lives in the handle's workspace)
+// CABAC-code the pictures the last search on this handle decided (the mode map lives in the handle's workspace).
+// Pass 1 counts the bins of every CTU, an exclusive scan turns the counts into arena offsets, the host reads the total
+// (the one synchronisation of this path) and grows the arena if needed, pass 2 writes the bin strings, then one thread per
+// picture runs the arithmetic coder.
 static int enqueue_coder(wrenc_b200 *h, int n_pics, const int16_t *d_lev, const CtuRecord *d_records, uint8_t *d_out, size_t out_cap, int *d_out_len,
                          cudaStream_t st) {
     int rc = ensure_coder(h, n_pics);
@@ -175,10 +179,23 @@ static int enqueue_coder(wrenc_b200 *h, int n_pics, const int16_t *d_lev, const 
     SyntaxParams Q;
     Q.W = h->W; Q.H = h->H; Q.Wc = h->Wc; Q.Hc = h->Hc; Q.n_pics = n_pics; Q.qp = h->cfg.qp;
     Q.lev = d_lev; Q.records = d_records; Q.mode_map = h->d_mode_map;
-    Q.bins = h->d_bins; Q.bin_cap = kBinCap; Q.bin_count = h->d_bin_count;
+    Q.bins = nullptr; Q.bin_count = h->d_bin_count; Q.bin_offset = h->d_bin_offset;
     Q.out = d_out; Q.out_cap = out_cap; Q.out_len = d_out_len;
-    CK(launch_slice_coder(Q, st));
-    h->launches += 2;
+    CK(launch_syntax(Q, st));
+    CK(launch_bin_scan(Q, h->d_bin_total, st));
+    unsigned long long total = 0;
+    CK(cudaMemcpyAsync(&total, h->d_bin_total, sizeof(total), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (total + 1 > h->bins_cap) {
+        cudaFree(h->d_bins);
+        h->d_bins = nullptr;
+        h->bins_cap = (size_t)(total + total / 4 + 1024);
+        CK(cudaMalloc(&h->d_bins, h->bins_cap * sizeof(uint16_t)));
+    }
+    Q.bins = h->d_bins;
+    CK(launch_syntax(Q, st));
+    CK(launch_cabac(Q, st));
+    h->launches += 4;
     return 0;
 }
 
@@ -253,7 +270,7 @@ void wrenc_b200_destroy(wrenc_b200 *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_tab); cudaFree(h->d_mode_map); cudaFree(h->d_done); cudaFree(h->d_items); cudaFree(h->d_counter);
     cudaFree(h->d_orig); cudaFree(h->d_rec); cudaFree(h->d_lev); cudaFree(h->d_rec_ctu);
-    cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_out); cudaFree(h->d_out_len);
+    cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_bin_total); cudaFree(h->d_out); cudaFree(h->d_out_len);
     cudaFreeHost(h->h_out); cudaFreeHost(h->h_out_len);
     cudaFreeHost(h->h_orig); cudaFreeHost(h->h_rec); cudaFreeHost(h->h_lev); cudaFreeHost(h->h_records);
     if (h->ev_done) cudaEventDestroy(h->ev_done);
@@ -316,7 +333,10 @@ int wrenc_b200_flush(wrenc_b200 *h) {
         rc = enqueue_coder(h, n, h->d_lev, h->d_rec_ctu, h->d_out, h->out_cap, h->d_out_len, h->stream);
         if (rc) return rc;
         CK(cudaMemcpyAsync(h->h_out_len, h->d_out_len, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaMemcpyAsync(h->h_out, h->d_out, (size_t)n * h->out_cap, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));  // lengths first, then exactly the coded bytes of every picture
+        for (int i = 0; i < n; i++)
+            if (h->h_out_len[i] > 0)
+                CK(cudaMemcpyAsync(h->h_out + (size_t)i * h->out_cap, h->d_out + (size_t)i * h->out_cap, (size_t)h->h_out_len[i], cudaMemcpyDeviceToHost, h->stream));
     }
     CK(cudaMemcpyAsync(h->h_records, h->d_rec_ctu, n * nctu * sizeof(CtuRecord), cudaMemcpyDeviceToHost, h->stream));
     if (h->cfg.want_recon) CK(cudaMemcpyAsync(h->h_rec, h->d_rec, n * ps, cudaMemcpyDeviceToHost, h->stream));
@@ -405,7 +425,7 @@ int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int rc = enqueue_coder(h, n_pictures, d_levels, reinterpret_cast<const CtuRecord *>(d_records), d_out, out_cap, d_out_len, st);
-    return rc ? rc : 2;
+    return rc ? rc : 4;
 }
 
 size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n) {

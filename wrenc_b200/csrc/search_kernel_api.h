@@ -39,14 +39,16 @@ struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_dat
     const int16_t *lev;        // [pic][W*H*3/2]
     const CtuRecord *records;  // [pic][Wc*Hc]
     const uint8_t *mode_map;   // [pic][(W/4)*(H/4)]
-    uint16_t *bins;            // bin arena: [pic][ctu][bin_cap] entries: ctx index | bin << 9 | bypass << 10
-    int bin_cap;
-    int *bin_count;            // [pic][ctu] entries produced (may exceed bin_cap: overflow)
+    uint16_t *bins;            // bin arena (entries: ctx index | bin << 9 | bypass << 10); nullptr = counting pass
+    int *bin_count;            // [pic][ctu] entries of the CTU's bin string
+    unsigned long long *bin_offset;  // [pic][ctu] start of the CTU's bin string in the arena (exclusive scan of bin_count)
     uint8_t *out;              // [pic][out_cap] bytes
     size_t out_cap;
     int *out_len;              // [pic] bytes written, -1 on overflow
 };
-cudaError_t launch_slice_coder(const SyntaxParams &Q, cudaStream_t stream);
+cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream);
+cudaError_t launch_bin_scan(const SyntaxParams &Q, unsigned long long *d_total, cudaStream_t stream);
+cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream);
 
 struct BlockParams {
     int op;  // 0 predict, 1 forward DCT, 2 inverse DCT, 3 dep-quant (+rate), 4 dequantise

@@ -45,9 +45,9 @@ __device__ void build_sb_order(SbOrder &T) {
 
 struct Sink {
     uint16_t *p;
-    int n, cap;
+    int n;
     __device__ __forceinline__ void put(unsigned e) {
-        if (n < cap) p[n] = (uint16_t)e;
+        if (p) p[n] = (uint16_t)e;  // p == nullptr: counting pass
         n++;
     }
     __device__ __forceinline__ void ctx(int c, int b) { put((unsigned)c | ((unsigned)(b & 1) << 9)); }
@@ -370,32 +370,37 @@ __device__ void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuR
     if (tree != DUAL_TREE_CHROMA && ts.mts_zero_out && !ts.mts_dc_only) S.ctx(CTX_MTS, 0);  // mts_idx == 0
 }
 
-// coding_tree() (ctu_encoder.rs:227-438); QT only, local dual tree at 8x8 -> 4x4
-__device__ void code_tree(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, int ctu_x, int ctu_y, int x, int y, int size, int bit, TuState &ts,
-                          uint16_t *pass1, uint16_t *absl) {
-    const int px = ctu_x + x, py = ctu_y + y;
-    const bool split = size > 4 && ((rec.split_mask >> bit) & 1);
-    {   // split_cu_flag: allow_split_qt holds for 32, 16, 8 (encoder_context.rs:958-971); ctxInc bool_coder.rs:2659-2744
-        const bool cl = px > 0 && cu_size_at(P, px - 1, py) < size;
-        const bool ca = py > 0 && cu_size_at(P, px, py - 1) < size;
-        S.ctx(CTX_SPLIT_CU + (int)cl + (int)ca, split);
-    }
-    if (!split) {
-        code_cu(S, SO, P, rec, ctu_x, ctu_y, x, y, size, SINGLE_TREE, ts, pass1, absl);
+// coding_tree() (ctu_encoder.rs:227-438); QT only, local dual tree at 8x8 -> 4x4.  Written as nested loops over the three
+// quad-tree levels (no device recursion: the stack frame stays statically sized).
+__device__ __forceinline__ bool code_split_flag(Sink &S, const PicView &P, const CtuRecord &rec, int px, int py, int size, int bit) {
+    // allow_split_qt holds for 32, 16, 8 (encoder_context.rs:958-971); ctxInc bool_coder.rs:2659-2744
+    const bool split = (rec.split_mask >> bit) & 1;
+    const bool cl = px > 0 && cu_size_at(P, px - 1, py) < size;
+    const bool ca = py > 0 && cu_size_at(P, px, py - 1) < size;
+    S.ctx(CTX_SPLIT_CU + (int)cl + (int)ca, split);
+    return split;
+}
+
+__device__ void code_ctu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, int ctu_x, int ctu_y, TuState &ts, uint16_t *pass1, uint16_t *absl) {
+    if (!code_split_flag(S, P, rec, ctu_x, ctu_y, 32, 0)) {
+        code_cu(S, SO, P, rec, ctu_x, ctu_y, 0, 0, 32, SINGLE_TREE, ts, pass1, absl);
         return;
     }
-    const int h = size >> 1;
-    if (size == 8) {
-        for (int i = 0; i < 4; i++) code_cu(S, SO, P, rec, ctu_x, ctu_y, x + (i & 1) * 4, y + (i >> 1) * 4, 4, DUAL_TREE_LUMA, ts, pass1, absl);
-        code_cu(S, SO, P, rec, ctu_x, ctu_y, x, y, 8, DUAL_TREE_CHROMA, ts, pass1, absl);
-        return;
-    }
-    for (int i = 0; i < 4; i++) {
-        const int cx = x + (i & 1) * h, cy = y + (i >> 1) * h;
-        int cbit;
-        if (size == 32) cbit = 1 + i;
-        else cbit = 5 + 4 * (bit - 1) + i;  // size 16: `bit` is 1 + a
-        code_tree(S, SO, P, rec, ctu_x, ctu_y, cx, cy, h, cbit, ts, pass1, absl);
+    for (int a = 0; a < 4; a++) {
+        const int x16 = (a & 1) * 16, y16 = (a >> 1) * 16;
+        if (!code_split_flag(S, P, rec, ctu_x + x16, ctu_y + y16, 16, 1 + a)) {
+            code_cu(S, SO, P, rec, ctu_x, ctu_y, x16, y16, 16, SINGLE_TREE, ts, pass1, absl);
+            continue;
+        }
+        for (int b = 0; b < 4; b++) {
+            const int x8 = x16 + (b & 1) * 8, y8 = y16 + (b >> 1) * 8;
+            if (!code_split_flag(S, P, rec, ctu_x + x8, ctu_y + y8, 8, 5 + 4 * a + b)) {
+                code_cu(S, SO, P, rec, ctu_x, ctu_y, x8, y8, 8, SINGLE_TREE, ts, pass1, absl);
+                continue;
+            }
+            for (int i = 0; i < 4; i++) code_cu(S, SO, P, rec, ctu_x, ctu_y, x8 + (i & 1) * 4, y8 + (i >> 1) * 4, 4, DUAL_TREE_LUMA, ts, pass1, absl);
+            code_cu(S, SO, P, rec, ctu_x, ctu_y, x8, y8, 8, DUAL_TREE_CHROMA, ts, pass1, absl);
+        }
     }
 }
 
@@ -416,17 +421,35 @@ extern "C" __global__ void __launch_bounds__(64) wrenc_b200_syntax_kernel(Syntax
     P.rec = Q.records + (size_t)pic * nctu;
     P.mode_map = Q.mode_map + (size_t)pic * (Q.W >> 2) * (Q.H >> 2);
     Sink S;
-    S.p = Q.bins + (size_t)gid * Q.bin_cap;
+    S.p = Q.bins ? Q.bins + Q.bin_offset[gid] : nullptr;  // first pass counts, second pass writes at the scanned offsets
     S.n = 0;
-    S.cap = Q.bin_cap;
     uint16_t pass1[1024], absl[1024];
     TuState ts;
     ts.qp_delta_coded = false;  // quantisation group = CTU (cu_qp_delta_subdiv 0, ctu_encoder.rs:305-310)
     ts.mts_dc_only = true;
     ts.mts_zero_out = true;
     const int cx = (ctu % Q.Wc) * 32, cy = (ctu / Q.Wc) * 32;
-    code_tree(S, SO, P, P.rec[ctu], cx, cy, 0, 0, 32, 0, ts, pass1, absl);
-    Q.bin_count[gid] = S.n;
+    code_ctu(S, SO, P, P.rec[ctu], cx, cy, ts, pass1, absl);
+    if (!Q.bins) Q.bin_count[gid] = S.n;
+}
+
+// exclusive prefix sum of the per-CTU bin counts over all pictures (one block; the counts are a few hundred thousand ints)
+extern "C" __global__ void __launch_bounds__(1024) wrenc_b200_bin_scan_kernel(const int *count, unsigned long long *offset, long long n, unsigned long long *total) {
+    __shared__ unsigned long long part[1024];
+    const int t = threadIdx.x;
+    const long long chunk = (n + 1023) / 1024, b = t * chunk, e = min(n, b + chunk);
+    unsigned long long s = 0;
+    for (long long i = b; i < e; i++) s += (unsigned long long)count[i];
+    part[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long acc = 0;
+        for (int i = 0; i < 1024; i++) { unsigned long long v = part[i]; part[i] = acc; acc += v; }
+        *total = acc;
+    }
+    __syncthreads();
+    unsigned long long acc = part[t];
+    for (long long i = b; i < e; i++) { offset[i] = acc; acc += (unsigned long long)count[i]; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -491,10 +514,8 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
     int overflow = 0;
     for (int c = 0; c < nctu; c++) {
         const size_t gid = (size_t)pic * nctu + c;
-        const uint16_t *b = Q.bins + gid * Q.bin_cap;
-        const int cnt = Q.bin_count[gid];
-        if (cnt > Q.bin_cap) overflow = 1;
-        const int lim = min(cnt, Q.bin_cap);
+        const uint16_t *b = Q.bins + Q.bin_offset[gid];
+        const int lim = Q.bin_count[gid];
         for (int i = 0; i < lim; i++) {
             const unsigned e = b[i];
             const int bin = (e >> 9) & 1;
@@ -536,11 +557,17 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
     Q.out_len[pic] = overflow ? -1 : (int)E.out.n;
 }
 
-cudaError_t launch_slice_coder(const SyntaxParams &Q, cudaStream_t stream) {
+cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream) {  // Q.bins == nullptr: counting pass
     const long long total = (long long)Q.n_pics * Q.Wc * Q.Hc;
     wrenc_b200_syntax_kernel<<<(unsigned)((total + 63) / 64), 64, 0, stream>>>(Q);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+cudaError_t launch_bin_scan(const SyntaxParams &Q, unsigned long long *d_total, cudaStream_t stream) {
+    const long long total = (long long)Q.n_pics * Q.Wc * Q.Hc;
+    wrenc_b200_bin_scan_kernel<<<1, 1024, 0, stream>>>(Q.bin_count, Q.bin_offset, total, d_total);
+    return cudaGetLastError();
+}
+cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream) {
     wrenc_b200_cabac_kernel<<<Q.n_pics, 32, 0, stream>>>(Q);
     return cudaGetLastError();
 }
