@@ -92,14 +92,16 @@ static int ensure_items(wrenc_b200 *h, int n_pics) {
     if (h->items_for == n_pics) return 0;
     const int Wc = h->Wc, Hc = h->Hc;
     // Items of one key level never depend on each other; an item of level K+1 depends on two level-K items of its own
-    // picture.  With `factor` x grid items per level those were handed out (factor-1) CTU latencies earlier, so nobody
-    // waits.  All pictures in lockstep (stagger 0) gives the widest levels; pictures are staggered only when there are so
-    // many that a level would exceed factor x grid items (keeps the live working set of pictures bounded).
-    double factor = 8.0;
-    if (const char *e = getenv("WRENC_B200_LEVEL_FACTOR")) factor = atof(e) > 0 ? atof(e) : factor;
-    const double avg_diag = (double)Wc * Hc / (Wc + 2 * Hc);
+    // picture.  All pictures advance in lock step (stagger 0): a level then holds n_pics x (diagonal length) items, so once
+    // it is several grids wide every dependency was handed out whole CTU latencies earlier and nobody waits.  Measured on
+    // B200 (profiles/r1_variants.txt): staggering the pictures only lengthens the ramp; WRENC_B200_LEVEL_FACTOR=f re-enables
+    // it (pictures are staggered so that a level holds about f x grid items) for experiments with a bounded working set.
     double stagger = 0.0;
-    if (n_pics * avg_diag > factor * h->grid) stagger = (double)Wc * Hc / (factor * h->grid);
+    if (const char *e = getenv("WRENC_B200_LEVEL_FACTOR")) {
+        const double factor = atof(e);
+        const double avg_diag = (double)Wc * Hc / (Wc + 2 * Hc);
+        if (factor > 0 && n_pics * avg_diag > factor * h->grid) stagger = (double)Wc * Hc / (factor * h->grid);
+    }
     struct It { int key, pic, cy, cx; };
     std::vector<It> v;
     v.reserve((size_t)n_pics * Wc * Hc);
