@@ -29,6 +29,8 @@ def lib():
         L.wo_num_predictions.restype = C.c_uint64
         L.wo_num_predictions.argtypes = [C.c_void_p]
         L.wo_rate.restype = C.c_int64
+        L.wo_decode_picture.restype = C.c_int
+        L.wo_decode_picture.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t] + [C.c_void_p] * 7 + [C.POINTER(C.c_size_t)]
         _LIB = L
     return _LIB
 
@@ -123,3 +125,17 @@ def scan(log2n):
     out = np.zeros(n * n, np.uint16)
     lib().wo_scan(log2n, _p(out))
     return out
+
+
+def decode_picture(qp, W, H, slice_data):
+    """Minimal intra decoder of the emitted subset (oracle/wrenc_decode.cpp).  Returns dict(rec, coef, records) or None."""
+    L = lib()
+    rec = [np.zeros((H, W), np.uint8), np.zeros((H // 2, W // 2), np.uint8), np.zeros((H // 2, W // 2), np.uint8)]
+    coef = [np.zeros((H, W), np.int16), np.zeros((H // 2, W // 2), np.int16), np.zeros((H // 2, W // 2), np.int16)]
+    records = np.zeros((H // 32) * (W // 32), RECORD_DTYPE)
+    used = C.c_size_t()
+    rc = L.wo_decode_picture(qp, W, H, slice_data, len(slice_data), _p(rec[0]), _p(rec[1]), _p(rec[2]), _p(coef[0]), _p(coef[1]), _p(coef[2]),
+                             _p(records), C.byref(used))
+    if rc != 0:
+        return None
+    return dict(rec=rec, coef=coef, records=records, bits=used.value)

@@ -129,3 +129,19 @@ def test_full_size_properties_1080p():
     r = enc.encode_pictures([sub])[0]
     enc.close()
     assert_same(Oracle(32, 3).encode_picture(*sub, want_slice_data=True), r, "640x352 sub-picture")
+
+
+def test_decoded_gpu_slice_data_equals_gpu_reconstruction():
+    """Independent of the oracle's encoder: the GPU's slice_data, parsed by the minimal decoder (oracle/wrenc_decode.cpp),
+    must reproduce the GPU's own reconstruction, levels and decisions (--reconst == decoder output)."""
+    import oracle_lib
+    for (W, H, qp, f) in ((160, 96, 32, wrenc_b200.synth_frame(160, 96, frame=11)), (64, 64, 24, wrenc_b200.random_frame(64, 64, 9))):
+        enc = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=1)
+        r = enc.encode_pictures([f])[0]
+        enc.close()
+        d = oracle_lib.decode_picture(qp, W, H, r["slice_data"])
+        assert d is not None
+        for c in range(3):
+            assert np.array_equal(d["rec"][c], r["rec"][c]) and np.array_equal(d["coef"][c], r["coef"][c])
+        for k in ("split_mask", "luma_mode", "chroma_mode"):
+            assert np.array_equal(d["records"][k], r["records"][k])

@@ -127,3 +127,33 @@ def test_slice_data_structure():
     flat = (np.full((64, 64), 128, np.uint8), np.full((32, 32), 128, np.uint8), np.full((32, 32), 128, np.uint8))
     sd = Oracle(32).encode_picture(*flat, want_slice_data=True)["slice_data"]
     assert len(sd) <= 8  # four CTUs of planar/DM with no residual: a handful of bins
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_decoder_reproduces_the_encoder_state(path):
+    """oracle/wrenc_decode.cpp: a standard CABAC decoder + VVC intra syntax parser for the emitted subset rebuilds trees,
+    modes and levels from slice_data alone and reconstructs the picture: it must equal the encoder's reconstruction
+    (the stand-in for the reference's VTM integration test, scripts/intergration_test.sh)."""
+    g = np.load(path)
+    if str(g["extra"]):
+        pytest.skip("tuning only changes decisions, not syntax; the decoder takes no extra params")
+    H, W = g["y"].shape
+    d = oracle_lib.decode_picture(int(g["qp"]), W, H, g["slice_data"].tobytes())
+    assert d is not None
+    for c, k in enumerate(("y", "cb", "cr")):
+        assert np.array_equal(d["rec"][c], g["rec_" + k]), f"decoded reconstruction differs ({k})"
+        assert np.array_equal(d["coef"][c], g["coef_" + k]), f"decoded levels differ ({k})"
+    rec = g["records"].view(oracle_lib.RECORD_DTYPE)
+    for k in ("split_mask", "luma_mode", "chroma_mode"):
+        assert np.array_equal(d["records"][k], rec[k]), k
+    assert len(g["slice_data"]) * 8 - 8 < d["bits"] <= len(g["slice_data"]) * 8
+
+
+def test_decoder_rejects_or_diverges_on_corrupted_streams():
+    from wrenc_b200.synth import synth_frame
+    y, cb, cr = synth_frame(96, 64, frame=5)
+    o = Oracle(27).encode_picture(y, cb, cr, want_slice_data=True)
+    sd = bytearray(o["slice_data"])
+    sd[len(sd) // 3] ^= 0x10
+    d = oracle_lib.decode_picture(27, 96, 64, bytes(sd))
+    assert d is None or not all(np.array_equal(d["rec"][c], o["rec"][c]) for c in range(3))

@@ -20,7 +20,7 @@ struct NodeId {
 };
 
 // CodingTree::split(SPLIT_QT) child geometry + availability flags (ctu.rs:1960-2064, 2083-2188; H9)
-__device__ __forceinline__ Node qt_child(const CtuGeom &g, const Node &p, int i, int tree) {
+__device__ __forceinline__ Node qt_child(const CtuGeom g, const Node p, int i, int tree) {
     Node c;
     c.w = p.w >> 1;
     c.x = p.x + (i & 1) * c.w;
@@ -40,7 +40,7 @@ __device__ __forceinline__ Node qt_child(const CtuGeom &g, const Node &p, int i,
 }
 
 // geometry and availability flags of a node of one CTU (the flags depend on the CTU's position in the picture)
-__device__ __forceinline__ Node make_node(const CtuGeom &g, const NodeId &id) {
+__device__ __forceinline__ Node make_node(const CtuGeom g, const NodeId &id) {
     Node n;
     n.x = 0; n.y = 0; n.w = 32; n.tree = SINGLE_TREE;
     n.bl = false;
@@ -58,19 +58,19 @@ __device__ __forceinline__ Node make_node(const CtuGeom &g, const NodeId &id) {
     return n;
 }
 
-__device__ __forceinline__ long long luma_hdr(const Ctx S, const DevTables *tab, const Node &nd, int mode, int ck) {
+__device__ __forceinline__ long long luma_hdr(const Ctx S, const DevTables *tab, const Node nd, int mode, int ck) {
     int lk = luma_kind(S, S.c->g, nd, mode, S.c->root_mode);
     return nd.tree == SINGLE_TREE ? tab->hdr_single[lk][ck] : tab->hdr_dual[lk];
 }
 
-__device__ __forceinline__ void fill_lm(const Ctx S, const Node &nd, int mode, int lane) {
+__device__ __forceinline__ void fill_lm(const Ctx S, const Node nd, int mode, int lane) {
     int cells = nd.w >> 2;
     for (int i = lane; i < cells * cells; i += 32) {
         int yy = i / cells, xx = i - yy * cells;
         S.c->lm[((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx] = (uint8_t)mode;
     }
 }
-__device__ __forceinline__ void fill_cm(const Ctx S, const Node &nd, int mode, int lane) {
+__device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, int lane) {
     int cells = nd.w >> 3;
     for (int i = lane; i < cells * cells; i += 32) {
         int yy = i / cells, xx = i - yy * cells;
@@ -415,7 +415,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
 __device__ __forceinline__ int sv_off_y(int d) { return d == 0 ? 0 : (d == 1 ? 1024 : 1280); }
 __device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 256 : 320); }
 
-__device__ __noinline__ void save_node(const Ctx S, const Node &nd, int d, int tid) {
+__device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int tid) {
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i / w, x = i - y * w;
@@ -432,7 +432,7 @@ __device__ __noinline__ void save_node(const Ctx S, const Node &nd, int d, int t
     for (int i = tid; i < 64; i += NTHREADS) S.c->svLm[d][i] = S.c->lm[i];
     for (int i = tid; i < 16; i += NTHREADS) S.c->svCm[d][i] = S.c->cm[i];
 }
-__device__ __noinline__ void restore_node(const Ctx S, const Node &nd, int d, int tid) {
+__device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int tid) {
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i / w, x = i - y * w;

@@ -181,7 +181,7 @@ __device__ __forceinline__ int rec_at(const Ctx S, int c, int x, int y) { return
 __device__ __forceinline__ int org_at(const Ctx S, int c, int x, int y) { return c == 0 ? S.c->orgY[y * 32 + x] : S.c->orgC[c - 1][y * 16 + x]; }
 
 // encoder_context.rs:918-956 derive_neighbouring_block_availability, CTU-relative luma coordinates (H9)
-__device__ __forceinline__ bool nb_avail(const CtuGeom &g, const Node &nd, int xn, int yn, bool ar, bool bl) {
+__device__ __forceinline__ bool nb_avail(const CtuGeom g, const Node nd, int xn, int yn, bool ar, bool bl) {
     int ax = g.cx + xn, ay = g.cy + yn;
     return ax >= 0 && ay >= 0 && ax < g.W && ay < g.H && (((xn >> 5) <= 0) || ((yn >> 5) < 0)) && ((yn >> 5) < 1) &&
            (xn < nd.x + nd.w || ar) && (yn < nd.y + nd.w || bl);
@@ -195,7 +195,7 @@ __device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float la
 // ---------------------------------------------------------------------------------------------------------------
 // reference samples (intra_predictor.rs:146-353), one warp per component
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void build_refs(const Ctx S, const CtuGeom &g, const Node &nd, int c, int lane) {
+__device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node nd, int c, int lane) {
     const int cs = c != 0;
     const int n = nd.w >> cs, xt = nd.x >> cs, yt = nd.y >> cs;
     const int nl = 2 * n + 1, na = 2 * n, tot = nl + na;
@@ -313,7 +313,7 @@ __device__ __forceinline__ int cclm_ds6(const Ctx S, int bx, int by, bool avail_
 }
 
 // down-sampled luma of the node (intra_predictor.rs:1854-1868), one warp
-__device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom &g, const Node &nd, int lane) {
+__device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom g, const Node nd, int lane) {
     Node tmp = nd;
     bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
     int tw = nd.w >> 1;
@@ -324,7 +324,7 @@ __device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom &g, cons
 }
 
 // derive (a,k,b) for one CCLM mode / component (intra_predictor.rs:1604-2031); uniform across the warp
-__device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, PredCtx &pc) {
+__device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, PredCtx &pc) {
     const int tw = nd.w >> 1, th = tw, tx = nd.x >> 1, ty = nd.y >> 1;
     bool avail_l = nb_avail(g, nd, nd.x - 1, nd.y, false, false);
     bool avail_t = nb_avail(g, nd, nd.x, nd.y - 1, false, false);
@@ -413,7 +413,7 @@ __device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom &g, const No
 }
 
 // per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
-__device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+__device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
     const int cs = c != 0;
     const int n = nd.w >> cs;
     pc.mode = mode; pc.c = c; pc.n = n; pc.l2 = ilog2i(n);
@@ -890,9 +890,10 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
 
 // prediction of one (mode, component) block: the only place pred_sample is instantiated in the search kernel.
 // Writes the samples to pred_out (may be null) and returns the SAD against the source block.
-__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
-    PredCtx pc;
-    pred_setup(S, g, nd, c, mode, refx, lane, pc);
+__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
+    PredCtx pc_mem;
+    pred_setup(S, g, nd, c, mode, refx, lane, pc_mem);
+    const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
 #pragma unroll 1
@@ -906,14 +907,14 @@ __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom &g, co
 }
 
 // SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
-__device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom &g, const Node &nd, int c, int mode, const WarpScratch &ws, int lane) {
+__device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, const WarpScratch ws, int lane) {
     return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane);
 }
 
 // full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
 // commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
-__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom &g, const Node &nd, int c, int mode, bool commit,
-                          const WarpScratch &ws, int lane, unsigned &ssd_out, int &rate_out) {
+__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit,
+                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out) {
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
     const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
     __syncwarp();
@@ -979,7 +980,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
 // ---------------------------------------------------------------------------------------------------------------
 // MPM derivation for the mode-bit estimate (ctu.rs:1498-1635) with the H1 neighbour semantics
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ int luma_kind(const Ctx S, const CtuGeom &g, const Node &nd, int mode, int root_mode) {
+__device__ __noinline__ int luma_kind(const Ctx S, const CtuGeom g, const Node nd, int mode, int root_mode) {
     if (mode == MODE_PLANAR) return 0;
     int left, above;
     if (nd.x == 0) left = g.cx > 0 ? S.c->leftModes[(nd.y + nd.w - 1) >> 2] : MODE_PLANAR;
