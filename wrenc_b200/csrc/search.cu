@@ -416,6 +416,7 @@ __device__ __forceinline__ int sv_off_y(int d) { return d == 0 ? 0 : (d == 1 ? 1
 __device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 256 : 320); }
 
 __device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int tid) {
+    WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i / w, x = i - y * w;
@@ -433,6 +434,7 @@ __device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int ti
     for (int i = tid; i < 16; i += NTHREADS) S.c->svCm[d][i] = S.c->cm[i];
 }
 __device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int tid) {
+    WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i / w, x = i - y * w;

@@ -154,6 +154,11 @@ struct Node {
     bool ar, bl;
 };
 
+// Every pointer the block functions receive points into shared memory; telling the compiler lets it emit LDS/STS instead of
+// generic loads/stores in the out-of-line functions.
+#define WB_SHARED_PTR(p) __builtin_assume(__isShared(p))
+#define WB_SHARED_CTX(S) do { WB_SHARED_PTR((S).c); WB_SHARED_PTR((S).tb); } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------------------------
@@ -196,6 +201,7 @@ __device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float la
 // reference samples (intra_predictor.rs:146-353), one warp per component
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node nd, int c, int lane) {
+    WB_SHARED_CTX(S);
     const int cs = c != 0;
     const int n = nd.w >> cs, xt = nd.x >> cs, yt = nd.y >> cs;
     const int nl = 2 * n + 1, na = 2 * n, tot = nl + na;
@@ -314,6 +320,7 @@ __device__ __forceinline__ int cclm_ds6(const Ctx S, int bx, int by, bool avail_
 
 // down-sampled luma of the node (intra_predictor.rs:1854-1868), one warp
 __device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom g, const Node nd, int lane) {
+    WB_SHARED_CTX(S);
     Node tmp = nd;
     bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
     int tw = nd.w >> 1;
@@ -325,6 +332,7 @@ __device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom g, const
 
 // derive (a,k,b) for one CCLM mode / component (intra_predictor.rs:1604-2031); uniform across the warp
 __device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, PredCtx &pc) {
+    WB_SHARED_CTX(S);
     const int tw = nd.w >> 1, th = tw, tx = nd.x >> 1, ty = nd.y >> 1;
     bool avail_l = nb_avail(g, nd, nd.x - 1, nd.y, false, false);
     bool avail_t = nb_avail(g, nd, nd.x, nd.y - 1, false, false);
@@ -414,6 +422,8 @@ __device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom g, const Nod
 
 // per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
 __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(refx);
     const int cs = c != 0;
     const int n = nd.w >> cs;
     pc.mode = mode; pc.c = c; pc.n = n; pc.l2 = ilog2i(n);
@@ -540,6 +550,7 @@ __device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x
 // ---------------------------------------------------------------------------------------------------------------
 // out[y][i] = (sum_x T[i][x] * in[y][x] + rnd) >> sh              (rows; lanes over i, Tt makes the T read conflict-free)
 __device__ __noinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+    WB_SHARED_PTR(Tt); WB_SHARED_PTR(in); WB_SHARED_PTR(out);
     const int nn = n * n;
 #pragma unroll 1
     for (int o = lane; o < nn; o += 32) {
@@ -555,6 +566,7 @@ __device__ __noinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int16_
 }
 // out[i][x] = (sum_y T[i][y] * in[y][x] + rnd) >> sh              (columns; lanes over x)
 __device__ __noinline__ void mm_cols(const int8_t *T, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+    WB_SHARED_PTR(T); WB_SHARED_PTR(in); WB_SHARED_PTR(out);
     const int nn = n * n;
 #pragma unroll 1
     for (int o = lane; o < nn; o += 32) {
@@ -670,6 +682,8 @@ __device__ __forceinline__ unsigned pos_map(unsigned pk, unsigned dec, bool nz) 
 // int32 relative to the running minimum; the decisions are identical to the reference's i64 comparisons.
 __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
                         int &rate_out, bool &any_out) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(coef); WB_SHARED_PTR(Wd); WB_SHARED_PTR(lev);
     const int n = 1 << l2, nn = n * n, sh = l2 + 4, off = 1 << (sh - 1);
     const int ls = tab->ls;
     const uint16_t *scan = S.tb->scan + tab_off(l2);
@@ -891,6 +905,9 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
 // prediction of one (mode, component) block: the only place pred_sample is instantiated in the search kernel.
 // Writes the samples to pred_out (may be null) and returns the SAD against the source block.
 __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(refx);
+    if (pred_out) WB_SHARED_PTR(pred_out);
     PredCtx pc_mem;
     pred_setup(S, g, nd, c, mode, refx, lane, pc_mem);
     const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
@@ -915,6 +932,8 @@ __device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const
 // commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
 __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit,
                           const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
     const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
     __syncwarp();
@@ -981,6 +1000,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
 // MPM derivation for the mode-bit estimate (ctu.rs:1498-1635) with the H1 neighbour semantics
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ int luma_kind(const Ctx S, const CtuGeom g, const Node nd, int mode, int root_mode) {
+    WB_SHARED_CTX(S);
     if (mode == MODE_PLANAR) return 0;
     int left, above;
     if (nd.x == 0) left = g.cx > 0 ? S.c->leftModes[(nd.y + nd.w - 1) >> 2] : MODE_PLANAR;
