@@ -751,9 +751,35 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         }
         Lf0 = Cs[0]; Lf1 = Cs[1]; Lf2 = Cs[2]; Lf3 = Cs[3];
     }
-    const int CS = nn >= 256 ? 16 : 4, nch = nn / CS, rounds = (nch + 31) >> 5;
+    const bool tiny = nn == 16;  // 4x4 TBs (the most numerous): one position per lane, plain sequential pass over 15 steps
+    const int CS = tiny ? 1 : (nn >= 256 ? 16 : 4), nch = nn / CS, rounds = (nch + 31) >> 5;
     int carry0 = 0, carry1 = 0, carry2 = 0, carry3 = 0;
     unsigned cmaps = 0;
+    if (tiny) {
+        LC l;
+        l.L00 = l.L01 = l.L0s0 = 0; l.L10 = l.L11 = TR_INF; l.pk = 0;
+        unsigned w = 0;
+        if (lane < 16) {
+            w = Wd[lane];
+            if (lane > 0) l = local_costs(S, tab, coef[scan[lane]], w, lane, kstar, ls, sh, off, ldq1);
+        }
+        int C0 = Lf0, C1 = Lf1, C2 = Lf2, C3 = Lf3;
+        unsigned mydec = leafdec;
+#pragma unroll 1
+        for (int j = 1; j < 16; j++) {
+            LC b;
+            b.L00 = __shfl_sync(0xffffffffu, l.L00, j); b.L10 = __shfl_sync(0xffffffffu, l.L10, j);
+            b.L01 = __shfl_sync(0xffffffffu, l.L01, j); b.L11 = __shfl_sync(0xffffffffu, l.L11, j);
+            b.L0s0 = __shfl_sync(0xffffffffu, l.L0s0, j); b.pk = __shfl_sync(0xffffffffu, l.pk, j);
+            const unsigned dec = vstep(b, ldq1, C0, C1, C2, C3);
+            if (lane == j) mydec = dec;
+        }
+        if (lane < 16) {
+            Wd[lane] = (uint16_t)(w | (mydec << 12));
+            const unsigned pk = lane == 0 ? ((w >> 1) & 1u) * 3u : l.pk;
+            cmaps = pos_map(pk, mydec, (w & 2048u) != 0);
+        }
+    } else
     for (int r = 0; r < rounds; r++) {
         const int c = r * 32 + lane;
         const bool vc = c < nch;
