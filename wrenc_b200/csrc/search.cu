@@ -109,6 +109,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const int ncomp = id.tree == DUAL_TREE_LUMA ? 1 : 3;
     const bool is_root = id.depth == 0;
     const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
+    const bool use_slots = id.depth > 0;  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
     // ---- phase 0: reference samples
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
@@ -129,8 +130,8 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
                 if (t < 2) { mode = t; c = 0; }
                 else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
                 unsigned ssd; int rate;
-                full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate);
-                if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+                full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, use_slots ? mode : -1);
+                if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
             } else {
                 int u = t - nfull;
                 int c = u / 13, mi = u - c * 13;
@@ -208,7 +209,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int dir = V.c->dir;
             int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, make_node(V.c->g, id), c, mode, false, ws, lane, ssd, rate);
+            full_task(V, tab, V.c->g, make_node(V.c->g, id), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
             if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
         }
     }
@@ -231,9 +232,9 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             }
         }
         float mn = fminf(fminf(cc[0], cc[1]), cc[2]);
-        if (cc[0] == mn) { C.dir_cost = cc[0]; }
-        else if (cc[1] == mn) { C.dir -= 1; C.dir_cost = cc[1]; }
-        else { C.dir += 1; C.dir_cost = cc[2]; }
+        if (cc[0] == mn) { C.dir_cost = cc[0]; C.dir_cand = 0; }
+        else if (cc[1] == mn) { C.dir -= 1; C.dir_cost = cc[1]; C.dir_cand = 1; }
+        else { C.dir += 1; C.dir_cost = cc[2]; C.dir_cand = 2; }
         // ---- winner among planar, DC, dir (first minimum)
         C.min_cost = fminf(fminf(C.cost_pl, C.cost_dc), C.dir_cost);
         C.mode = C.cost_pl == C.min_cost ? 0 : (C.cost_dc == C.min_cost ? 1 : C.dir);
@@ -246,9 +247,18 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = make_node(V.c->g, id);
-        unsigned ssd; int rate;
-        full_task(V, tab, V.c->g, nd, t, V.c->mode, true, ws, lane, ssd, rate);
-        if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+        if (use_slots) {  // the winner's luma and its same-mode (DM) chroma were evaluated in phase 1 or 4: copy them out
+            const int md = V.c->mode, dc = V.c->dir_cand;
+            commit_slot(V, nd, t, md <= 1 ? md : 2 + dc, lane);
+            if (lane == 0) {
+                if (md <= 1) { V.c->fin_ssd[t] = V.c->pd_ssd[md][t]; V.c->fin_rate[t] = V.c->pd_rate[md][t]; }
+                else { const int r = t == 0 ? dc : 3 + 2 * dc + (t - 1); V.c->fin_ssd[t] = V.c->r_ssd[r]; V.c->fin_rate[t] = V.c->r_rate[r]; }
+            }
+        } else {
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, nd, t, V.c->mode, true, ws, lane, ssd, rate);
+            if (lane == 0) { V.c->fin_ssd[t] = ssd; V.c->fin_rate[t] = rate; }
+        }
         if (t == 0) fill_lm(V, nd, V.c->mode, lane);
     }
     __syncthreads();
@@ -295,8 +305,8 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         Ctx V{&S.tb, &S.c[tid]};
         CtuCtx &C = *V.c;
         const Node nd = make_node(C.g, id);
-        const unsigned ssdY = C.r_ssd[0], ssdDM = C.r_ssd[1] + C.r_ssd[2];
-        const long long rateY = C.r_rate[0], rateDM = (long long)C.r_rate[1] + C.r_rate[2];
+        const unsigned ssdY = C.fin_ssd[0], ssdDM = C.fin_ssd[1] + C.fin_ssd[2];
+        const long long rateY = C.fin_rate[0], rateDM = (long long)C.fin_rate[1] + C.fin_rate[2];
         const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
         const unsigned ssdCC = C.r_ssd[8] + C.r_ssd[9];
         const long long rateCC = (long long)C.r_rate[8] + C.r_rate[9];

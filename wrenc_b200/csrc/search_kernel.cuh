@@ -125,7 +125,13 @@ struct CtuCtx {
     int restore;
     // leaf-evaluation state
     float cost_pl, cost_dc, cur_cost, dir_cost, min_cost, cost_dm;
-    int cur, dir, mode, cclm_mode, v0, v1, cclm_wins;
+    int cur, dir, mode, cclm_mode, v0, v1, cclm_wins, dir_cand;
+    // results of the planar / DC evaluations (phase 1) and of the winner (phase 5), per component
+    unsigned pd_ssd[2][3], fin_ssd[3];
+    int pd_rate[2][3], fin_rate[3];
+    // candidate slots of nodes up to 16x16: reconstruction and levels of planar, DC, dir, dir-1, dir+1 (Y at 0, Cb at 256, Cr at 320)
+    uint8_t slotRec[5][384];
+    int16_t slotLv[5][384];
 };
 
 struct Shared {
@@ -957,7 +963,7 @@ __device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const
 // full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
 // commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
 __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit,
-                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out) {
+                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out, int slot = -1) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
@@ -993,6 +999,9 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
             dst[(by + y) * stride + bx + x] = B[i];
         }
     }
+    const int soff = c == 0 ? 0 : (c == 1 ? 256 : 320);
+    if (slot >= 0)
+        for (int i = lane; i < nn; i += 32) S.c->slotLv[slot][soff + i] = B[i];
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
         for (int i = lane; i < nn; i += 32) A[i] = (int16_t)min(32767, max(-32768, ((int)B[i] * ls + off) >> sh));  // quantizer.rs:1074-1075
@@ -1016,9 +1025,28 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
             if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
             else RC(S, c, bx + x, by + y) = (uint8_t)rec;
         }
+        if (slot >= 0) S.c->slotRec[slot][soff + i] = (uint8_t)rec;
     }
     ssd_out = warp_sumu(ssd);
     rate_out = rate;
+    __syncwarp();
+}
+
+// The winner of a node up to 16x16 was already evaluated with unchanged inputs (the reference repeats that evaluation,
+// block_splitter.rs:989-1037 / 1062-1076, with identical results): copy its reconstruction and levels out of its slot.
+__device__ __noinline__ void commit_slot(const Ctx S, const Node nd, int c, int slot, int lane) {
+    WB_SHARED_CTX(S);
+    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
+    const int soff = c == 0 ? 0 : (c == 1 ? 256 : 320);
+    int16_t *dst = c == 0 ? S.c->lvY : S.c->lvC[c - 1];
+    const int stride = c == 0 ? 32 : 16;
+    for (int i = lane; i < nn; i += 32) {
+        int y = i >> l2, x = i & (n - 1);
+        dst[(by + y) * stride + bx + x] = S.c->slotLv[slot][soff + i];
+        const uint8_t r = S.c->slotRec[slot][soff + i];
+        if (c == 0) RY(S, bx + x, by + y) = r;
+        else RC(S, c, bx + x, by + y) = r;
+    }
     __syncwarp();
 }
 
