@@ -87,6 +87,15 @@ __device__ __forceinline__ int next_task(Shared &S, int &slot, bool dyn, int pre
     if (lane == 0) t = atomicAdd(&S.ticket[slot], 1);
     return __shfl_sync(0xffffffffu, t, 0);
 }
+// node geometry + availability flags of the current node, cached per CTU (x | y << 6 | w << 12 | tree << 18 | ar << 20 | bl << 21)
+__device__ __forceinline__ unsigned pack_node(const Node n) {
+    return (unsigned)n.x | ((unsigned)n.y << 6) | ((unsigned)n.w << 12) | ((unsigned)n.tree << 18) | ((unsigned)n.ar << 20) | ((unsigned)n.bl << 21);
+}
+__device__ __forceinline__ Node unpack_node(unsigned p) {
+    Node n;
+    n.x = p & 63; n.y = (p >> 6) & 63; n.w = (p >> 12) & 63; n.tree = (p >> 18) & 3; n.ar = (p >> 20) & 1; n.bl = (p >> 21) & 1;
+    return n;
+}
 #define WB_FOR_TASKS(ntask)                                                                            \
     for (int tt = next_task(S, S_slot, dyn, -1, warp, lane); tt < (ntask) * KC; tt = next_task(S, S_slot, dyn, tt, warp, lane)) \
         if (S.c[tt % KC].active)
@@ -110,11 +119,13 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const bool is_root = id.depth == 0;
     const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
     const bool use_slots = id.depth > 0;  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
+    if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
+    __syncthreads();
     // ---- phase 0: reference samples
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        build_refs(V, V.c->g, make_node(V.c->g, id), t, lane);
+        build_refs(V, V.c->g, unpack_node(V.c->node), t, lane);
     }
     __syncthreads();
     WB_NEXT_PHASE();
@@ -124,7 +135,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         WB_FOR_TASKS(ntask) {
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
-            const Node nd = make_node(V.c->g, id);
+            const Node nd = unpack_node(V.c->node);
             if (t < nfull) {
                 int mode, c;
                 if (t < 2) { mode = t; c = 0; }
@@ -145,7 +156,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
         CtuCtx &C = *V.c;
-        const Node nd = make_node(C.g, id);
+        const Node nd = unpack_node(C.node);
         unsigned ssd0 = C.r_ssd[0], ssd1 = C.r_ssd[1];
         long long r0 = C.r_rate[0], r1 = C.r_rate[1];
         if (ncomp == 3) {
@@ -176,7 +187,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             Ctx V{&S.tb, &S.c[k]};
             int cand = t / ncomp, c = t - cand * ncomp;
             if (cand == 0 ? V.c->v0 : V.c->v1) {
-                unsigned sad = sad_task(V, V.c->g, make_node(V.c->g, id), c, cand == 0 ? V.c->cur - step : V.c->cur + step, ws, lane);
+                unsigned sad = sad_task(V, V.c->g, unpack_node(V.c->node), c, cand == 0 ? V.c->cur - step : V.c->cur + step, ws, lane);
                 if (lane == 0) V.c->r_sad[t] = sad;
             }
         }
@@ -209,7 +220,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int dir = V.c->dir;
             int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, make_node(V.c->g, id), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
             if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
         }
     }
@@ -218,7 +229,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
         CtuCtx &C = *V.c;
-        const Node nd = make_node(C.g, id);
+        const Node nd = unpack_node(C.node);
         float cc[3];
         for (int cand = 0; cand < 3; cand++) {
             bool valid = cand == 0 || (cand == 1 ? C.v0 : C.v1);
@@ -246,7 +257,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = make_node(V.c->g, id);
+        const Node nd = unpack_node(V.c->node);
         if (use_slots) {  // the winner's luma and its same-mode (DM) chroma were evaluated in phase 1 or 4: copy them out
             const int md = V.c->mode, dc = V.c->dir_cand;
             commit_slot(V, nd, t, md <= 1 ? md : 2 + dc, lane);
@@ -268,7 +279,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     WB_FOR_TASKS(1) {
         const int k = tt % KC;
         Ctx V{&S.tb, &S.c[k]};
-        cclm_downsample(V, V.c->g, make_node(V.c->g, id), lane);
+        cclm_downsample(V, V.c->g, unpack_node(V.c->node), lane);
     }
     __syncthreads();
     WB_NEXT_PHASE();
@@ -278,7 +289,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         Ctx V{&S.tb, &S.c[k]};
         const int mi = t >> 1, c = 1 + (t & 1);
         const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-        unsigned sad = sad_task(V, V.c->g, make_node(V.c->g, id), c, cm, ws, lane);
+        unsigned sad = sad_task(V, V.c->g, unpack_node(V.c->node), c, cm, ws, lane);
         if (lane == 0) V.c->r_sad[t] = sad;
     }
     __syncthreads();
@@ -296,7 +307,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         unsigned ssd; int rate;
-        full_task(V, tab, V.c->g, make_node(V.c->g, id), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
+        full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
         if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
     }
     __syncthreads();
@@ -304,7 +315,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
         CtuCtx &C = *V.c;
-        const Node nd = make_node(C.g, id);
+        const Node nd = unpack_node(C.node);
         const unsigned ssdY = C.fin_ssd[0], ssdDM = C.fin_ssd[1] + C.fin_ssd[2];
         const long long rateY = C.fin_rate[0], rateDM = (long long)C.fin_rate[1] + C.fin_rate[2];
         const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
@@ -326,7 +337,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     WB_FOR_TASKS(2) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = make_node(V.c->g, id);
+        const Node nd = unpack_node(V.c->node);
         if (V.c->cclm_wins) {
             unsigned ssd; int rate;
             full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
@@ -345,10 +356,12 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
     const bool dyn = true;
     const DevTables *tab = P.tab;
     const WarpScratch ws = warp_scratch(S, warp);
+    if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
+    __syncthreads();
     WB_FOR_TASKS(3) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = make_node(V.c->g, id);
+        const Node nd = unpack_node(V.c->node);
         if (t < 2) build_refs(V, V.c->g, nd, 1 + t, lane);
         else cclm_downsample(V, V.c->g, nd, lane);
     }
@@ -357,7 +370,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
     WB_FOR_TASKS(8) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = make_node(V.c->g, id);
+        const Node nd = unpack_node(V.c->node);
         if (t < 2) {
             // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396)
             const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
@@ -386,7 +399,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         unsigned ssd; int rate;
-        full_task(V, tab, V.c->g, make_node(V.c->g, id), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
+        full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
         if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
     }
     __syncthreads();
@@ -404,7 +417,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
     WB_FOR_TASKS(2) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = make_node(V.c->g, id);
+        const Node nd = unpack_node(V.c->node);
         if (V.c->cclm_wins) {
             unsigned ssd; int rate;
             full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);

@@ -119,6 +119,7 @@ struct CtuCtx {
     // control state: written by the CTU's decision thread, read by everyone after the next barrier
     CtuGeom g;
     int active, pic, cxi, cyi;
+    unsigned node;  // packed geometry + availability flags of the node being evaluated (pack_node)
     int root_mode;
     unsigned mask, mask_sv[2];
     float cost[3], split[3], leaf_cost;
