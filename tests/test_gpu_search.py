@@ -145,3 +145,17 @@ def test_decoded_gpu_slice_data_equals_gpu_reconstruction():
             assert np.array_equal(d["rec"][c], r["rec"][c]) and np.array_equal(d["coef"][c], r["coef"][c])
         for k in ("split_mask", "luma_mode", "chroma_mode"):
             assert np.array_equal(d["records"][k], r["records"][k])
+
+
+@pytest.mark.parametrize("qp", [12, 17, 42, 51, 63])
+def test_extreme_qps_noise_and_synthetic(qp):
+    """Large levels (noise at low QP: |level| > 1000, escape codes in abs_remainder) and empty pictures (QP 63) keep
+    decisions, levels, reconstruction and slice_data identical to the oracle, and the stream decodes to the same picture."""
+    import oracle_lib
+    for f in (wrenc_b200.synth_frame(96, 64, frame=qp), wrenc_b200.random_frame(96, 64, qp)):
+        enc = wrenc_b200.SearchEncoder(96, 64, qp=qp, pictures_in_flight=1)
+        r = enc.encode_pictures([f])[0]
+        enc.close()
+        assert_same(Oracle(qp, 3).encode_picture(*f, want_slice_data=True), r, f"qp {qp}")
+        d = oracle_lib.decode_picture(qp, 96, 64, r["slice_data"])
+        assert d is not None and all(np.array_equal(d["rec"][c], r["rec"][c]) for c in range(3))
