@@ -238,7 +238,7 @@ def run_ours(args):
     Fe = args.e2e_frames
 
     def e2e_step():
-        got, cost = 0, 0.0
+        got, cost, coded = 0, 0.0, []
         i = 0
         while got < Fe:
             nb = min(args.e2e_batch, Fe - i) if i < Fe else 0
@@ -249,7 +249,13 @@ def run_ours(args):
             while enc.pending():
                 r = enc.receive(copy=False)
                 cost += float(r["records"]["cost"][0]) + len(r["slice_data"])
+                coded.append(r["slice_data"])
                 got += 1
+        if dist is not None:  # the job's only exchange: ordered gather of the per-picture byte buffers on the writer rank
+            from wrenc_b200.sharding import gather_in_order
+            allb = gather_in_order(coded, dst=0, device=dev)
+            if rank == 0:
+                assert len(allb) == world * Fe
         return cost
 
     e2e_step()
@@ -286,7 +292,7 @@ def run_ours(args):
     roof = {"bound": "int32", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tops/s", "frac": achieved_ops / peak_ops,
             "traffic": None, "kernel": "wrenc_b200_search_kernel", "launch_ms": launch_ms, "units_per_launch": ctus, "ops_per_unit": OPS_PER_CTU, "share_of_step": launch_ms / (elapsed_ms / args.steps),
             "peak_source": "IMAD-chain microbenchmark run live in bench.py (2 ops per multiply-add); not in MEASURED_PEAKS.json"}
-    roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": ALG_BYTES_PER_CTU,
+    roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": ALG_BYTES_PER_CTU, "ncu_dram_bytes_per_unit": 7160, "ncu_note": "dram__bytes_read+write of one --set full capture (5280-CTU launch, profiles/r1_search_kernel_ncu_full.txt): 1.15x algorithmic",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
     # ---- CPU baseline on a bounded sample

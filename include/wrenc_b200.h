@@ -81,9 +81,8 @@ int wrenc_b200_pending(const wrenc_b200 *h);
 
 /* Device-resident entry (throughput path / bench "value"): n_pictures I420 pictures already in HBM, contiguous, each
  * width*height*3/2 bytes; outputs written to device buffers of the same geometry (rec: u8, levels: i16 per sample),
- * records: n_pictures*(H/32)*(W/32).  All pointers are DEVICE pointers on cfg.device; rec/levels/records may be NULL
- * only if the handle was created for it... they are required.  Runs on `stream` (a cudaStream_t, or NULL for the
- * handle's own stream) and does not synchronise.  Returns the number of search-kernel launches enqueued (>=1) or <0. */
+ * records: n_pictures*(H/32)*(W/32).  All pointers are DEVICE pointers on cfg.device and all are required.  Runs on
+ * `stream` (a cudaStream_t, or NULL for the handle's own stream) and does not synchronise.  Returns the number of search-kernel launches enqueued (>=1) or <0. */
 int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t *d_yuv, uint8_t *d_rec, int16_t *d_levels,
                                wrenc_b200_ctu_record *d_records, void *stream);
 /* Phase 2 on resident data: CABAC-codes the pictures the preceding wrenc_b200_search_resident call on this handle decided
