@@ -409,6 +409,10 @@ int wrenc_b200_pending(const wrenc_b200 *h) { return h ? h->n_filled - (h->launc
 int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t *d_yuv, uint8_t *d_rec, int16_t *d_levels,
                                wrenc_b200_ctu_record *d_records, void *stream) {
     if (!h || n_pictures <= 0 || n_pictures > 65535 || !d_yuv || !d_rec || !d_levels || !d_records) return WRENC_B200_EINVAL;
+    if (((uintptr_t)d_yuv & 15) || ((uintptr_t)d_rec & 3) || ((uintptr_t)d_levels & 3)) {
+        h->err = "d_yuv must be 16-byte aligned (TMA bulk copies), d_rec / d_levels 4-byte aligned";
+        return WRENC_B200_EINVAL;
+    }
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     // workspace (re)allocation and work-list upload happen on the handle's stream and are synchronised there

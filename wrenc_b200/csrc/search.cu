@@ -626,6 +626,31 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
     }
 }
 
+// ---- TMA (bulk async copy) staging of the source blocks: global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WB_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WB_MBAR_DONE;\n"
+        "bra WB_MBAR_WAIT;\n"
+        "WB_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ int ld_relaxed(const int *p) {  // polling load: no L1 invalidation per poll (the acquire fence follows the loop)
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -638,8 +663,13 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
     Shared &S = *reinterpret_cast<Shared *>(smem_raw);
     const int tid = threadIdx.x;
     init_tables(S, P.tab, tid);
-    if (tid == 0) { S.ticket[0] = 0; S.ticket[1] = 0; }
+    if (tid == 0) {
+        S.ticket[0] = 0; S.ticket[1] = 0;
+        mbar_init(&S.tma_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     int S_slot = 0;
+    unsigned tma_phase = 0;
     __syncthreads();
     const int W = P.W, H = P.H, Wc = P.Wc;
     const size_t pic_samples = (size_t)W * H * 3 / 2;
@@ -669,7 +699,14 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
             __threadfence();  // acquire side: order the halo loads after the flag observation
         }
         __syncthreads();
-        // ---- stage the CTUs: source samples, neighbouring reconstruction, left-CTU modes
+        // ---- stage the CTUs: source samples (TMA), neighbouring reconstruction, left-CTU modes
+        if (tid == 0) {
+            int nact = 0;
+            for (int k = 0; k < KC; k++) nact += S.c[k].active;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the source buffers vs the async writes
+            mbar_arrive_expect_tx(&S.tma_bar, (unsigned)nact * 1536u);
+        }
+        __syncthreads();
         for (int k = 0; k < KC; k++) {
             CtuCtx &C = S.c[k];
             if (!C.active) continue;
@@ -678,14 +715,14 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
             const int pic = C.pic;
             const uint8_t *oY = P.orig + (size_t)pic * pic_samples, *oCb = oY + (size_t)W * H, *oCr = oCb + (size_t)cw * chh;
             const uint8_t *rY = P.rec + (size_t)pic * pic_samples, *rCb = rY + (size_t)W * H, *rCr = rCb + (size_t)cw * chh;
-            for (int i = tid; i < 256; i += NTHREADS) {  // 32 rows x 8 words
-                int y = i >> 3, x4 = (i & 7) * 4;
-                *reinterpret_cast<uint32_t *>(&C.orgY[y * 32 + x4]) = __ldg(reinterpret_cast<const uint32_t *>(oY + (size_t)(g.cy + y) * W + g.cx + x4));
-            }
-            for (int i = tid; i < 128; i += NTHREADS) {
-                int c = i >> 6, t = i & 63, yy = t >> 2, xx = (t & 3) * 4;
-                const uint8_t *src = (c ? oCr : oCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1) + xx;
-                *reinterpret_cast<uint32_t *>(&C.orgC[c][yy * 16 + xx]) = __ldg(reinterpret_cast<const uint32_t *>(src));
+            // source block: 32 luma rows of 32 bytes + 2 x 16 chroma rows of 16 bytes, one TMA bulk copy per row, all
+            // completing on S.tma_bar (armed above with the byte count of the whole batch)
+            for (int i = tid; i < 64; i += NTHREADS) {
+                if (i < 32) tma_bulk_g2s(&C.orgY[i * 32], oY + (size_t)(g.cy + i) * W + g.cx, 32, &S.tma_bar);
+                else {
+                    const int c = (i - 32) >> 4, yy = (i - 32) & 15;
+                    tma_bulk_g2s(&C.orgC[c][yy * 16], (c ? oCr : oCb) + (size_t)((g.cy >> 1) + yy) * cw + (g.cx >> 1), 16, &S.tma_bar);
+                }
             }
             // luma halo: rows -2,-1 (cols -4..63) and cols -4..-1 of rows 0..31
             for (int i = tid; i < 2 * RY_STRIDE + 32 * 4; i += NTHREADS) {
@@ -714,6 +751,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
             for (int i = tid; i < 64; i += NTHREADS) C.lm[i] = 0;
             for (int i = tid; i < 16; i += NTHREADS) C.cm[i] = 0;
         }
+        mbar_wait(&S.tma_bar, tma_phase);  // all source bytes have landed
+        tma_phase ^= 1;
         __syncthreads();
         ctu_search(S, P, S_slot);
         __syncthreads();

@@ -92,8 +92,8 @@ struct CtuGeom {
 };
 
 // Everything that belongs to ONE CTU while it is searched.  A CTA searches WB_K independent CTUs in lock step.
-struct CtuCtx {
-    uint8_t orgY[1024];
+struct alignas(16) CtuCtx {
+    uint8_t orgY[1024];       // source block; filled by TMA bulk copies (16-byte aligned rows)
     uint8_t orgC[2][256];
     uint8_t recY[RY_ROWS * RY_STRIDE];
     uint8_t recC[2][RC_ROWS * RC_STRIDE];
@@ -139,6 +139,7 @@ struct Shared {
     Tables tb;
     CtuCtx c[WB_K];
     int item0;
+    unsigned long long tma_bar;  // mbarrier the TMA bulk copies of the source blocks complete on
     int ticket[2];            // dynamic task tickets of the current / previous phase
     // per-warp scratch
     int16_t bigA[NBIG][1024], bigB[NBIG][1024];
