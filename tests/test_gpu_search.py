@@ -159,3 +159,26 @@ def test_extreme_qps_noise_and_synthetic(qp):
         assert_same(Oracle(qp, 3).encode_picture(*f, want_slice_data=True), r, f"qp {qp}")
         d = oracle_lib.decode_picture(qp, 96, 64, r["slice_data"])
         assert d is not None and all(np.array_equal(d["rec"][c], r["rec"][c]) for c in range(3))
+
+
+@pytest.mark.parametrize("W,H,qp,n", [(1280, 704, 32, 2), (3840, 2176, 27, 1)])
+def test_full_size_decode_round_trip(W, H, qp, n):
+    """BASELINE.json configs[3] (3840x2176 QP27, down to 4x4 CUs) and configs[4] (1280x704 streams) at full size through
+    the size-independent property the domain offers: encode -> decode (oracle/wrenc_decode.cpp, a standard CABAC decoder +
+    VVC intra reconstruction) must reproduce the encoder's reconstruction, levels and decisions exactly; plus determinism
+    across batch positions and a PSNR sanity bound."""
+    import oracle_lib
+    frames = [wrenc_b200.synth_frame(W, H, seed=0xB2000003 + W, frame=f) for f in range(n)]
+    enc = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=n + 1)
+    res = enc.encode_pictures(frames + [frames[0]])
+    enc.close()
+    assert_same(res[0], res[-1], "same picture at another batch position")
+    for f, r in zip(frames, res):
+        d = oracle_lib.decode_picture(qp, W, H, r["slice_data"])
+        assert d is not None, "slice_data does not parse"
+        for c in range(3):
+            assert np.array_equal(d["rec"][c], r["rec"][c]) and np.array_equal(d["coef"][c], r["coef"][c])
+        for k in ("split_mask", "luma_mode", "chroma_mode"):
+            assert np.array_equal(d["records"][k], r["records"][k])
+        mse = ((r["rec"][0].astype(float) - f[0]) ** 2).mean()
+        assert 10 * np.log10(255 ** 2 / mse) > (30 if qp <= 27 else 28)
