@@ -6,6 +6,22 @@
 
 namespace wb {
 
+// Dev-time phase timer (-DWB_PROFILE builds only, tools/phase_profile.py): thread 0 of every CTA adds the cycles between two
+// barriers to g_prof[slot]; slot = 16 * node kind (0: 32x32, 1: 16x16, 2: 8x8, 3: 4x4 luma, 4: chroma CT, 5: outside the tree) + phase.
+#ifdef WB_PROFILE
+__device__ unsigned long long g_prof[128];
+#define WB_PROF(slot)                                                              \
+    do {                                                                           \
+        if (threadIdx.x == 0) {                                                    \
+            const long long t_ = clock64();                                        \
+            atomicAdd(&g_prof[slot], (unsigned long long)(t_ - S.prof_last));      \
+            S.prof_last = t_;                                                      \
+        }                                                                          \
+    } while (0)
+#else
+#define WB_PROF(slot)
+#endif
+
 // ---------------------------------------------------------------------------------------------------------------
 // Lock-step execution of KC independent CTUs per CTA.
 //
@@ -118,9 +134,11 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const int ncomp = id.tree == DUAL_TREE_LUMA ? 1 : 3;
     const bool is_root = id.depth == 0;
     const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
-    const bool use_slots = id.depth > 0;  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
+    const bool use_slots = id.depth > 0;
+    [[maybe_unused]] const int pk_ = 16 * id.depth;  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
     __syncthreads();
+    WB_PROF(pk_ + 0);
     // ---- phase 0: reference samples
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
@@ -128,30 +146,43 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         build_refs(V, V.c->g, unpack_node(V.c->node), t, lane);
     }
     __syncthreads();
+    WB_PROF(pk_ + 1);
     WB_NEXT_PHASE();
-    // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs
+    // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs.  4x4 TBs (the luma of a 4x4 CU, the chroma of an
+    //      8x8 CU) are evaluated two per warp: planar + DC of a 4x4 luma CU, or Cb + Cr of one mode.
     {
-        const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
+        const int nfull = id.depth == 3 ? 1 : (id.depth == 2 ? 4 : 2 * ncomp), ntask = nfull + 13 * ncomp;
         WB_FOR_TASKS(ntask) {
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
             const Node nd = unpack_node(V.c->node);
             if (t < nfull) {
-                int mode, c;
-                if (t < 2) { mode = t; c = 0; }
-                else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
                 unsigned ssd; int rate;
-                full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, use_slots ? mode : -1);
-                if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
+                if (id.depth == 3 || (id.depth == 2 && t >= 2)) {
+                    const int half = lane >> 4;
+                    const int mode = id.depth == 3 ? half : t - 2, c = id.depth == 3 ? 0 : 1 + half;
+                    full_pair4(V, tab, V.c->g, nd, c, mode, false, mode, ws, lane, ssd, rate);
+                    if ((lane & 15) == 0) {
+                        const int ri = c == 0 ? mode : 2 + 2 * mode + (c - 1);
+                        V.c->r_ssd[ri] = ssd; V.c->r_rate[ri] = rate; V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate;
+                    }
+                } else {
+                    int mode, c;
+                    if (t < 2) { mode = t; c = 0; }
+                    else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
+                    full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, use_slots ? mode : -1);
+                    if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
+                }
             } else {
                 int u = t - nfull;
                 int c = u / 13, mi = u - c * 13;
                 unsigned sad = sad_task(V, V.c->g, nd, c, c_cand15[2 + mi], ws, lane);
-                if (lane == 0) V.c->r_sad[t] = sad;
+                if (lane == 0) V.c->r_sad[2 * ncomp + u] = sad;
             }
         }
     }
     __syncthreads();
+    WB_PROF(pk_ + 2);
     WB_NEXT_PHASE();
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
@@ -180,6 +211,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         C.v1 = !(C.cur + 2 > 66);
     }
     __syncthreads();
+    WB_PROF(pk_ + 3);
     // ---- phases 2,3: SAD refinement +-2, +-1 (step_search aux=true, block_splitter.rs:905-973)
     for (int step = 2; step >= 1; step >>= 1) {
         WB_FOR_TASKS(2 * ncomp) {
@@ -192,6 +224,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             }
         }
         __syncthreads();
+    WB_PROF(pk_ + 4);
         WB_NEXT_PHASE();
         if (tid < KC && S.c[tid].active) {
             CtuCtx &C = S.c[tid];
@@ -207,24 +240,48 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             else { C.dir = C.cur; C.v0 = !(C.dir < 3); C.v1 = !(C.dir + 1 > 66); }
         }
         __syncthreads();
+    WB_PROF(pk_ + 5);
     }
-    // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false)
-    WB_FOR_TASKS(3 * ncomp) {
-        const int k = tt % KC, t = tt / KC;
-        Ctx V{&S.tb, &S.c[k]};
-        int cand, c;
-        if (t < 3) { cand = t; c = 0; }
-        else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
-        bool valid = cand == 0 || (cand == 1 ? V.c->v0 : V.c->v1);
-        if (valid) {
-            const int dir = V.c->dir;
-            int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
-            unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
-            if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+    // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false); 4x4 TBs two per warp
+    if (id.depth == 3) {
+        WB_FOR_TASKS(2) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            const int cand = 2 * t + (lane >> 4);
+            const bool valid = cand == 0 || (cand == 1 ? V.c->v0 : (cand == 2 && V.c->v1));
+            if (valid) {
+                const int dir = V.c->dir;
+                unsigned ssd; int rate;
+                full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 0, cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1), false, 2 + cand, ws, lane, ssd, rate);
+                if ((lane & 15) == 0) { V.c->r_ssd[cand] = ssd; V.c->r_rate[cand] = rate; }
+            }
+        }
+    } else {
+        WB_FOR_TASKS(id.depth == 2 ? 6 : 9) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            const bool pair = id.depth == 2 && t >= 3;
+            int cand, c;
+            if (t < 3) { cand = t; c = 0; }
+            else if (pair) { cand = t - 3; c = 1 + (lane >> 4); }
+            else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
+            bool valid = cand == 0 || (cand == 1 ? V.c->v0 : V.c->v1);
+            if (valid) {
+                const int dir = V.c->dir;
+                int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
+                unsigned ssd; int rate;
+                if (pair) {
+                    full_pair4(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, 2 + cand, ws, lane, ssd, rate);
+                    if ((lane & 15) == 0) { V.c->r_ssd[3 + 2 * cand + (c - 1)] = ssd; V.c->r_rate[3 + 2 * cand + (c - 1)] = rate; }
+                } else {
+                    full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
+                    if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+                }
+            }
         }
     }
     __syncthreads();
+    WB_PROF(pk_ + 6);
     WB_NEXT_PHASE();
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
@@ -253,6 +310,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         C.leaf_cost = C.min_cost;
     }
     __syncthreads();
+    WB_PROF(pk_ + 7);
     // ---- phase 5: luma redo (commit) + chroma DM full evaluation (commit)
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
@@ -273,6 +331,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         if (t == 0) fill_lm(V, nd, V.c->mode, lane);
     }
     __syncthreads();
+    WB_PROF(pk_ + 8);
     WB_NEXT_PHASE();
     if (ncomp == 1) return;
     // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
@@ -282,6 +341,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         cclm_downsample(V, V.c->g, unpack_node(V.c->node), lane);
     }
     __syncthreads();
+    WB_PROF(pk_ + 9);
     WB_NEXT_PHASE();
     // ---- phase 6: CCLM SADs in the order LT, T, L
     WB_FOR_TASKS(6) {
@@ -293,6 +353,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         if (lane == 0) V.c->r_sad[t] = sad;
     }
     __syncthreads();
+    WB_PROF(pk_ + 10);
     WB_NEXT_PHASE();
     if (tid < KC && S.c[tid].active) {
         CtuCtx &C = S.c[tid];
@@ -302,15 +363,27 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         else C.cclm_mode = MODE_L_CCLM;
     }
     __syncthreads();
+    WB_PROF(pk_ + 11);
     // ---- phase 7: CCLM full evaluation (no commit)
-    WB_FOR_TASKS(2) {
-        const int k = tt % KC, t = tt / KC;
-        Ctx V{&S.tb, &S.c[k]};
-        unsigned ssd; int rate;
-        full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
-        if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
+    if (id.depth == 2) {
+        WB_FOR_TASKS(1) {
+            const int k = tt % KC, h = lane >> 4;
+            Ctx V{&S.tb, &S.c[k]};
+            unsigned ssd; int rate;
+            full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, -1, ws, lane, ssd, rate);
+            if ((lane & 15) == 0) { V.c->r_ssd[8 + h] = ssd; V.c->r_rate[8 + h] = rate; }
+        }
+    } else {
+        WB_FOR_TASKS(2) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
+            if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
+        }
     }
     __syncthreads();
+    WB_PROF(pk_ + 12);
     WB_NEXT_PHASE();
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
@@ -333,18 +406,33 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         }
     }
     __syncthreads();
+    WB_PROF(pk_ + 13);
     // ---- phase 8: commit the CCLM chroma where it won; publish the chroma mode
-    WB_FOR_TASKS(2) {
-        const int k = tt % KC, t = tt / KC;
-        Ctx V{&S.tb, &S.c[k]};
-        const Node nd = unpack_node(V.c->node);
-        if (V.c->cclm_wins) {
-            unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+    if (id.depth == 2) {
+        WB_FOR_TASKS(1) {
+            const int k = tt % KC;
+            Ctx V{&S.tb, &S.c[k]};
+            const Node nd = unpack_node(V.c->node);
+            if (V.c->cclm_wins) {
+                unsigned ssd; int rate;
+                full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), V.c->cclm_mode, true, -1, ws, lane, ssd, rate);
+            }
+            fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
         }
-        if (t == 0) fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
+    } else {
+        WB_FOR_TASKS(2) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            const Node nd = unpack_node(V.c->node);
+            if (V.c->cclm_wins) {
+                unsigned ssd; int rate;
+                full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+            }
+            if (t == 0) fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
+        }
     }
     __syncthreads();
+    WB_PROF(pk_ + 14);
     WB_NEXT_PHASE();
 }
 
@@ -358,6 +446,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
     const WarpScratch ws = warp_scratch(S, warp);
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
     __syncthreads();
+    WB_PROF(64 + 0);
     WB_FOR_TASKS(3) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
@@ -366,19 +455,20 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         else cclm_downsample(V, V.c->g, nd, lane);
     }
     __syncthreads();
+    WB_PROF(64 + 1);
     WB_NEXT_PHASE();
-    WB_FOR_TASKS(8) {
+    WB_FOR_TASKS(7) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = unpack_node(V.c->node);
-        if (t < 2) {
-            // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396)
-            const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
+        if (t < 1) {
+            // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396); Cb and Cr by one half-warp each
+            const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1], h = lane >> 4;
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, nd, 1 + t, dm, true, ws, lane, ssd, rate);
-            if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+            full_pair4(V, tab, V.c->g, nd, 1 + h, dm, true, -1, ws, lane, ssd, rate);
+            if ((lane & 15) == 0) { V.c->r_ssd[h] = ssd; V.c->r_rate[h] = rate; }
         } else {
-            const int u = t - 2;
+            const int u = t - 1;
             const int mi = u >> 1, c = 1 + (u & 1);
             const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
             unsigned sad = sad_task(V, V.c->g, nd, c, cm, ws, lane);
@@ -386,6 +476,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         }
     }
     __syncthreads();
+    WB_PROF(64 + 2);
     WB_NEXT_PHASE();
     if (tid < KC && S.c[tid].active) {
         CtuCtx &C = S.c[tid];
@@ -395,14 +486,16 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         else C.cclm_mode = MODE_L_CCLM;
     }
     __syncthreads();
-    WB_FOR_TASKS(2) {
-        const int k = tt % KC, t = tt / KC;
+    WB_PROF(64 + 3);
+    WB_FOR_TASKS(1) {
+        const int k = tt % KC, h = lane >> 4;
         Ctx V{&S.tb, &S.c[k]};
         unsigned ssd; int rate;
-        full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
-        if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
+        full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, -1, ws, lane, ssd, rate);
+        if ((lane & 15) == 0) { V.c->r_ssd[8 + h] = ssd; V.c->r_rate[8 + h] = rate; }
     }
     __syncthreads();
+    WB_PROF(64 + 4);
     WB_NEXT_PHASE();
     if (tid < KC && S.c[tid].active) {
         CtuCtx &C = S.c[tid];
@@ -414,20 +507,20 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         C.leaf_cost = mn;
     }
     __syncthreads();
-    WB_FOR_TASKS(2) {
-        const int k = tt % KC, t = tt / KC;
+    WB_PROF(64 + 5);
+    WB_FOR_TASKS(1) {
+        const int k = tt % KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = unpack_node(V.c->node);
         if (V.c->cclm_wins) {
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+            full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), V.c->cclm_mode, true, -1, ws, lane, ssd, rate);
         }
-        if (t == 0) {
-            const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
-            fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : dm, lane);
-        }
+        const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
+        fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : dm, lane);
     }
     __syncthreads();
+    WB_PROF(64 + 6);
     WB_NEXT_PHASE();
 }
 
@@ -670,6 +763,9 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
     }
     int S_slot = 0;
     unsigned tma_phase = 0;
+#ifdef WB_PROFILE
+    if (tid == 0) S.prof_last = clock64();
+#endif
     __syncthreads();
     const int W = P.W, H = P.H, Wc = P.Wc;
     const size_t pic_samples = (size_t)W * H * 3 / 2;
@@ -679,6 +775,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
         __syncthreads();
         const int item0 = S.item0;
         if (item0 >= P.n_items) break;
+        WB_PROF(80);
         // ---- one thread per CTU: decode the item, wait for the wavefront dependencies (left CTU and above-right CTU,
         //      above when in the last column, of the same picture must be final)
         if (tid < KC) {
@@ -699,6 +796,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
             __threadfence();  // acquire side: order the halo loads after the flag observation
         }
         __syncthreads();
+        WB_PROF(81);
         // ---- stage the CTUs: source samples (TMA), neighbouring reconstruction, left-CTU modes
         if (tid == 0) {
             int nact = 0;
@@ -754,8 +852,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
         mbar_wait(&S.tma_bar, tma_phase);  // all source bytes have landed
         tma_phase ^= 1;
         __syncthreads();
+        WB_PROF(82);
         ctu_search(S, P, S_slot);
         __syncthreads();
+        WB_PROF(83);
         // ---- write back: reconstruction, levels, modes, record
         for (int k = 0; k < KC; k++) {
             CtuCtx &C = S.c[k];
@@ -800,6 +900,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
             st_release(P.done + (size_t)C.pic * Wc * P.Hc + C.cyi * Wc + C.cxi, P.epoch);
         }
         __syncthreads();
+        WB_PROF(84);
     }
 }
 
@@ -839,7 +940,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
             else build_refs(V, g, nd, c, lane);
             __syncwarp();
             PredCtx pc;
-            pred_setup(V, g, nd, c, P.mode, ws.refx, lane, pc);
+            pred_setup(V, g, nd, c, P.mode, ws.refx, lane, 32, 0xffffffffu, pc);
             for (int i = lane; i < n * n; i += 32) P.out8[i] = (uint8_t)pred_sample(V, pc, i % n, i / n);
         }
         return;
@@ -882,6 +983,17 @@ cudaError_t launch_block(const BlockParams &P, int grid, cudaStream_t stream) {
     wrenc_b200_block_kernel<<<grid, NTHREADS, sizeof(Shared), stream>>>(P);
     return cudaGetLastError();
 }
+
+#ifdef WB_PROFILE
+extern "C" int wrenc_b200_debug_prof(unsigned long long *out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_prof, sizeof(g_prof));
+    if (e == cudaSuccess && reset) {
+        static unsigned long long zero[128];
+        e = cudaMemcpyToSymbol(g_prof, zero, sizeof(zero));
+    }
+    return e == cudaSuccess ? 0 : -1;
+}
+#endif
 
 size_t search_smem_bytes() { return sizeof(Shared); }
 int search_ctus_per_cta() { return KC; }

@@ -17,6 +17,7 @@
 // RD cost, which is IEEE f32 with explicit _rn intrinsics (no FMA contraction) in the reference's operation order.
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "search_kernel_api.h"
@@ -139,6 +140,9 @@ struct Shared {
     Tables tb;
     CtuCtx c[WB_K];
     int item0;
+#ifdef WB_PROFILE
+    long long prof_last;
+#endif
     unsigned long long tma_bar;  // mbarrier the TMA bulk copies of the source blocks complete on
     int ticket[2];            // dynamic task tickets of the current / previous phase
     // per-warp scratch
@@ -150,6 +154,10 @@ struct Shared {
     uint8_t smP[NW - NBIG + 1][256];
     int16_t refx[NW][100];
 };
+
+static_assert(offsetof(Shared, bigA) % 8 == 0 && offsetof(Shared, bigB) % 8 == 0 && offsetof(Shared, smA) % 8 == 0 && offsetof(Shared, smB) % 8 == 0 &&
+                  offsetof(Tables, Tt) % 4 == 0,
+              "full_pair4 reads these arrays as 32-bit words");
 
 struct Ctx {  // what the per-CTU device functions see
     Tables *tb;
@@ -180,6 +188,11 @@ __device__ __forceinline__ int warp_sum(int v) {
 __device__ __forceinline__ unsigned warp_sumu(unsigned v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// lane groups: the whole warp, or one of its halves (two independent 4x4 blocks per warp); collectives take the group's mask
+__device__ __forceinline__ int group_sum(int v, int gsz, unsigned mask) {
+    for (int o = gsz >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
 __device__ __forceinline__ int warp_max(int v) {
@@ -429,7 +442,7 @@ __device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom g, const Nod
 }
 
 // per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
-__device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+__device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int gl, int gsz, unsigned gmask, PredCtx &pc) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(refx);
     const int cs = c != 0;
@@ -453,8 +466,8 @@ __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node
     if (mode == MODE_DC) {
         pc.kind = 1; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
         int s = 0;
-        for (int i = lane; i < n; i += 32) s += pc.ab[i] + pc.lf[1 + i];
-        s = warp_sum(s) + n;
+        for (int i = gl; i < n; i += gsz) s += pc.ab[i] + pc.lf[1 + i];
+        s = group_sum(s, gsz, gmask) + n;
         pc.dc = (s >> (pc.l2 + 1)) & 255;
         return;
     }
@@ -478,7 +491,7 @@ __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node
     // projection array r[idx], idx in [-n, 2n+2]  (intra_predictor.rs:1398-1414 / 1480-1495)
     int16_t *r = refx + n;
     const int lo = ang < 0 ? -n : 0, hi = ang < 0 ? n + 1 : 2 * n + 2;
-    for (int idx = lo + lane; idx <= hi; idx += 32) {
+    for (int idx = lo + gl; idx <= hi; idx += gsz) {
         int v;
         if (pc.vertical) {
             if (idx < 0) v = pc.lf[min((idx * pc.inv_angle + 256) >> 9, n)];
@@ -492,7 +505,7 @@ __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node
         }
         r[idx] = (int16_t)v;
     }
-    __syncwarp();
+    __syncwarp(gmask);
 }
 
 __device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x, int y) {
@@ -938,28 +951,29 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
 
 // prediction of one (mode, component) block: the only place pred_sample is instantiated in the search kernel.
 // Writes the samples to pred_out (may be null) and returns the SAD against the source block.
-__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
+__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int gl, int gsz,
+                                               unsigned gmask) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(refx);
     if (pred_out) WB_SHARED_PTR(pred_out);
     PredCtx pc_mem;
-    pred_setup(S, g, nd, c, mode, refx, lane, pc_mem);
+    pred_setup(S, g, nd, c, mode, refx, gl, gsz, gmask, pc_mem);
     const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
 #pragma unroll 1
-    for (int i = lane; i < n * n; i += 32) {
+    for (int i = gl; i < n * n; i += gsz) {
         int y = i >> l2, x = i & (n - 1);
         int p = pred_sample(S, pc, x, y);
         if (pred_out) pred_out[i] = (uint8_t)p;
         sad += abs(p - org_at(S, c, bx + x, by + y));
     }
-    return warp_sumu(sad);
+    return (unsigned)group_sum((int)sad, gsz, gmask);
 }
 
 // SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
 __device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, const WarpScratch ws, int lane) {
-    return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane);
+    return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane, 32, 0xffffffffu);
 }
 
 // full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
@@ -969,7 +983,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
-    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
+    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane, 32, 0xffffffffu) != 0;
     __syncwarp();
     int16_t *A = ws.A, *B = ws.B;
     bool anyres = anysad;
@@ -1032,6 +1046,172 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     ssd_out = warp_sumu(ssd);
     rate_out = rate;
     __syncwarp();
+}
+
+// Full evaluation of a 4x4 TB by HALF a warp (lanes 0-15 and 16-31 evaluate two independent TBs of the same node: two modes
+// of a 4x4 luma CU, or the Cb and Cr blocks of one chroma mode).  Same arithmetic as full_task, but the block lives in
+// registers (lane gl = raster sample 4y + x), the 4-point transforms exchange operands by shuffles, and the dependent
+// quantisation runs one trellis STATE per lane (lanes 0-3 of the half) over the 15 sequential steps, reading the local costs
+// that the position lanes tabulated in shared memory.  c, mode, commit and slot may differ between the halves; every
+// collective uses the half's mask, so a half whose TB is not evaluated simply does not call.
+constexpr unsigned long long INV_SCAN4 = 0xFDA6EB73C8419520ull;  // nibble r = scan position of raster offset r (inverse of the 4x4 diagonal scan)
+__device__ __forceinline__ int dot4_s8(int packed, int a0, int a1, int a2, int a3) {
+    return (int)(int8_t)(packed & 255) * a0 + (int)(int8_t)((packed >> 8) & 255) * a1 + (int)(int8_t)((packed >> 16) & 255) * a2 + (packed >> 24) * a3;
+}
+__device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit, int slot,
+                                        const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
+    const int hb = lane & 16, gl = lane & 15, half = hb >> 4;
+    const unsigned hm = half ? 0xffff0000u : 0x0000ffffu;
+    const int cs = c != 0, bx = nd.x >> cs, by = nd.y >> cs;
+    const int x = gl & 3, y = gl >> 2;
+    uint8_t *pbuf = ws.pred + 16 * half;
+    predict_block(S, g, nd, c, mode, ws.refx + 50 * half, pbuf, gl, 16, hm);
+    __syncwarp(hm);
+    const int p = pbuf[gl];
+    const int org = org_at(S, c, bx + x, by + y);
+    const int res = org - p;
+    // ---- forward DCT (transformer.rs:2040-2378 with n = 4: shifts 1 and 8)
+    const int rowq = 4 * y, colq = x;
+    const int Trow_x = *reinterpret_cast<const int *>(S.tb->T + 4 * x);    // T[x][0..3]
+    const int Trow_y = *reinterpret_cast<const int *>(S.tb->T + 4 * y);    // T[y][0..3]
+    const int Tcol_x = *reinterpret_cast<const int *>(S.tb->Tt + 4 * x);   // T[0..3][x]
+    const int Tcol_y = *reinterpret_cast<const int *>(S.tb->Tt + 4 * y);   // T[0..3][y]
+    int a0 = __shfl_sync(hm, res, hb + rowq), a1 = __shfl_sync(hm, res, hb + rowq + 1), a2 = __shfl_sync(hm, res, hb + rowq + 2), a3 = __shfl_sync(hm, res, hb + rowq + 3);
+    const int b1 = (int)(int16_t)((dot4_s8(Trow_x, a0, a1, a2, a3) + 1) >> 1);           // B[y][i = x]
+    a0 = __shfl_sync(hm, b1, hb + colq); a1 = __shfl_sync(hm, b1, hb + colq + 4); a2 = __shfl_sync(hm, b1, hb + colq + 8); a3 = __shfl_sync(hm, b1, hb + colq + 12);
+    const int coef = (int)(int16_t)((dot4_s8(Trow_y, a0, a1, a2, a3) + 128) >> 8);       // coef[i = y][x]
+    // ---- dependent quantisation: the 4x4 case of trellis() (quantizer.rs:338-517, 686-721; rate block_splitter.rs:415-460)
+    const int sh = 6, off = 32, ls = tab->ls, ldq1 = S.tb->ldq[1];
+    const int k = gl;  // scan position owned by this lane
+    const int tc = __shfl_sync(hm, coef, hb + S.tb->scan[k]);
+    unsigned xq = 0;
+    const unsigned nz = tc != 0;
+    if (nz) {
+        const unsigned sc = tc > 0 ? ((unsigned)tc << sh) - (unsigned)off : ((unsigned)(-tc) << sh) + (unsigned)off;
+        xq = min(sc / (unsigned)ls, 2047u);
+    }
+    const unsigned w = xq | (nz << 11);
+    const unsigned bstar = (__ballot_sync(hm, xq >= 2) >> hb) & 0xffffu;
+    const int kstar = bstar ? 31 - __clz(bstar) : -1;
+    const bool anytc = ((__ballot_sync(hm, nz) >> hb) & 0xffffu) != 0;
+    int q = 0, rate = 0;
+    bool anylev = false;
+    if (anytc) {
+        LC l;
+        l.L00 = l.L01 = l.L0s0 = 0; l.L10 = l.L11 = TR_INF; l.pk = 0;
+        if (k > 0) l = local_costs(S, tab, tc, w, k, kstar, ls, sh, off, ldq1);  // (k & 15) != 0: no sub-block-start adjustment inside a 4x4 TB
+        int *tbl = reinterpret_cast<int *>(half ? ws.B : ws.A);  // [position][state] -> (cost of candidate a0, cost of candidate a1)
+        tbl[8 * k + 0] = l.L0s0; tbl[8 * k + 1] = l.L10;
+        tbl[8 * k + 2] = l.L00;  tbl[8 * k + 3] = l.L10;
+        tbl[8 * k + 4] = l.L01;  tbl[8 * k + 5] = l.L11;
+        tbl[8 * k + 6] = l.L01;  tbl[8 * k + 7] = l.L11;
+        const unsigned m1 = (__ballot_sync(hm, l.pk & 1u) >> hb) & 0xffffu, m2 = (__ballot_sync(hm, l.pk & 2u) >> hb) & 0xffffu;
+        const int tc0 = __shfl_sync(hm, tc, hb);
+        const unsigned x0 = __shfl_sync(hm, xq, hb);
+        __syncwarp(hm);
+        unsigned dec = 0;
+        if (gl < 4) {
+            const int s = gl;
+            const unsigned m4 = 0xFu << hb;
+            // DC leaf (quantizer.rs:367-409) for this lane's state
+            int C;
+            {
+                const bool itz = (s == 0) && (kstar < 0);
+                if (tc0 == 0) {
+                    C = itz ? -ldq1 : ldq1;
+                } else {
+                    const int delta = s > 1;
+                    const int A0 = (int)(x0 >> 1);
+                    int q0 = (int)(int16_t)(2 * A0 - delta);  // H3: usize wrap gives -1 for a0 == 0, delta == 1
+                    if (tc0 < 0) q0 = -q0;
+                    const int d0 = abs(tc0 - ((q0 * ls + off) >> sh));
+                    const int bits0 = (A0 != 0 || !itz) ? A0 + 1 : 0;
+                    const int cost0 = 128 * d0 + WB_LDQ(bits0);
+                    const int A1 = A0 + 1;
+                    int q1 = 2 * A1 - delta;
+                    if (tc0 < 0) q1 = -q1;
+                    const int d1 = abs(tc0 - ((q1 * ls + off) >> sh));
+                    const int cost1 = 128 * d1 + WB_LDQ(A1 + 1);
+                    if (cost0 <= cost1) {
+                        C = cost0;
+                        if (itz && A0 == 0) C -= ldq1;
+                    } else {
+                        C = cost1;
+                        dec = 1u;
+                    }
+                }
+            }
+            // states 0,1 continue from {0,2}, states 2,3 from {1,3}; which of the two feeds candidate a0 depends on the parity of a0
+            const int srcP = hb + (s >> 1), srcQ = srcP + 2;
+            const unsigned msw = (s < 2 ? m1 : m2) ^ ((s & 1) ? 0xffffu : 0u);
+            const int *tp = tbl + 2 * s;
+#pragma unroll 5
+            for (int j = 1; j < 16; j++) {
+                const int La = tp[8 * j], Lb = tp[8 * j + 1];
+                const int P = __shfl_sync(m4, C, srcP), Q = __shfl_sync(m4, C, srcQ);
+                const bool sw = (msw >> j) & 1u;
+                const int c0 = La + (sw ? Q : P), c1 = Lb + (sw ? P : Q);
+                const bool d = c1 < c0;  // ties keep a0 (quantizer.rs:505)
+                C = d ? c1 : c0;
+                dec |= (unsigned)d << j;
+            }
+        }
+        __syncwarp(hm);
+        unsigned mydec = 0;
+#pragma unroll
+        for (int s = 0; s < 4; s++) mydec |= ((__shfl_sync(hm, dec, hb + s) >> k) & 1u) << s;
+        const unsigned pk = k == 0 ? ((w >> 1) & 1u) * 3u : l.pk;
+        unsigned inc = pos_map(pk, mydec, nz != 0);
+        // walk from the last scan position with state 0
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const unsigned t = __shfl_down_sync(hm, inc, d, 16);
+            if (gl + d < 16) inc = map_compose(t, inc);
+        }
+        const unsigned exc = __shfl_down_sync(hm, inc, 1, 16);
+        const unsigned s = gl == 15 ? 0u : (exc & 3u);
+        const int delta = s > 1;
+        if (nz) {
+            const unsigned a = ((k == 0) ? (xq >> 1) : ((xq + delta) >> 1)) + ((mydec >> s) & 1u);
+            if (k == 0) q = (int)(int16_t)(2 * (int)a - delta);
+            else q = a > 0 ? 2 * (int)a - delta : 0;
+            if (tc < 0) q = -q;
+        }
+        const bool has = q != 0;
+        const unsigned bal = (__ballot_sync(hm, has) >> hb) & 0xffffu;
+        if (has) rate = WB_LV((abs(q) + delta) >> 1);
+        else if ((bal >> (gl + 1)) != 0) rate = S.tb->lv[0];
+        rate = group_sum(rate, 16, hm);
+        anylev = bal != 0;
+    }
+    // levels back to raster order
+    const int lev = __shfl_sync(hm, q, hb + (int)((INV_SCAN4 >> (4 * gl)) & 15ull));
+    const int soff = (c == 0 ? 0 : (c == 1 ? 256 : 320)) + gl;
+    if (commit) {
+        if (c == 0) S.c->lvY[(by + y) * 32 + bx + x] = (int16_t)lev;
+        else S.c->lvC[c - 1][(by + y) * 16 + bx + x] = (int16_t)lev;
+    }
+    if (slot >= 0) S.c->slotLv[slot][soff] = (int16_t)lev;
+    int r = 0;
+    if (anylev) {  // dequantise (quantizer.rs:1074-1075), inverse DCT (transformer.rs:2380-2737 with n = 4)
+        const int dq = min(32767, max(-32768, (lev * ls + off) >> sh));
+        a0 = __shfl_sync(hm, dq, hb + colq); a1 = __shfl_sync(hm, dq, hb + colq + 4); a2 = __shfl_sync(hm, dq, hb + colq + 8); a3 = __shfl_sync(hm, dq, hb + colq + 12);
+        const int v = min(32767, max(-32768, (dot4_s8(Tcol_y, a0, a1, a2, a3) + 64) >> 7));   // V[y][x] = sum_i T[i][y] D[i][x]
+        a0 = __shfl_sync(hm, v, hb + rowq); a1 = __shfl_sync(hm, v, hb + rowq + 1); a2 = __shfl_sync(hm, v, hb + rowq + 2); a3 = __shfl_sync(hm, v, hb + rowq + 3);
+        r = (int)(int16_t)((dot4_s8(Tcol_x, a0, a1, a2, a3) + 2048) >> 12);                    // R[y][x] = sum_i T[i][x] V[y][i]
+    }
+    const int rec = clip8((int)(int16_t)(p + r));
+    const int d = rec - org;
+    if (commit) {
+        if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
+        else RC(S, c, bx + x, by + y) = (uint8_t)rec;
+    }
+    if (slot >= 0) S.c->slotRec[slot][soff] = (uint8_t)rec;
+    ssd_out = (unsigned)group_sum(d * d, 16, hm);
+    rate_out = rate;
+    __syncwarp(hm);
 }
 
 // The winner of a node up to 16x16 was already evaluated with unchanged inputs (the reference repeats that evaluation,
