@@ -135,7 +135,8 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const bool is_root = id.depth == 0;
     const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
     const bool use_slots = id.depth > 0;
-    [[maybe_unused]] const int pk_ = 16 * id.depth;  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
+    [[maybe_unused]] const int pk_ = 16 * id.depth;
+    const bool small = id.depth >= 2;  // CUs up to 8x8  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
     __syncthreads();
     WB_PROF(pk_ + 0);
@@ -149,98 +150,105 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     WB_PROF(pk_ + 1);
     WB_NEXT_PHASE();
     // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs.  4x4 TBs (the luma of a 4x4 CU, the chroma of an
-    //      8x8 CU) are evaluated two per warp: planar + DC of a 4x4 luma CU, or Cb + Cr of one mode.
-    {
-        const int nfull = id.depth == 3 ? 1 : (id.depth == 2 ? 4 : 2 * ncomp), ntask = nfull + 13 * ncomp;
+    //      8x8 CU) are evaluated two per warp: planar + DC of a 4x4 luma CU, or Cb + Cr of one mode.  For CUs up to 8x8 the
+    //      whole SAD-driven direction search (coarse modes and both refinement steps) is one task of one warp (dir_search).
+    if (small) {
+        const int ntask = id.depth == 3 ? 2 : 5;
         WB_FOR_TASKS(ntask) {
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
             const Node nd = unpack_node(V.c->node);
-            if (t < nfull) {
+            if (t == 0) {
+                dir_search(V, nd, lane);
+            } else if (id.depth == 3 || t >= 3) {
+                const int half = lane >> 4;
+                const int mode = id.depth == 3 ? half : t - 3, c = id.depth == 3 ? 0 : 1 + half;
                 unsigned ssd; int rate;
-                if (id.depth == 3 || (id.depth == 2 && t >= 2)) {
-                    const int half = lane >> 4;
-                    const int mode = id.depth == 3 ? half : t - 2, c = id.depth == 3 ? 0 : 1 + half;
-                    full_pair4(V, tab, V.c->g, nd, c, mode, false, mode, ws, lane, ssd, rate);
-                    if ((lane & 15) == 0) {
-                        const int ri = c == 0 ? mode : 2 + 2 * mode + (c - 1);
-                        V.c->r_ssd[ri] = ssd; V.c->r_rate[ri] = rate; V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate;
-                    }
-                } else {
+                full_pair4(V, tab, V.c->g, nd, c, mode, false, mode, ws, lane, ssd, rate);
+                if ((lane & 15) == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
+            } else {
+                const int mode = t - 1;
+                unsigned ssd; int rate;
+                full_task(V, tab, V.c->g, nd, 0, mode, false, ws, lane, ssd, rate, mode);
+                if (lane == 0) { V.c->pd_ssd[mode][0] = ssd; V.c->pd_rate[mode][0] = rate; }
+            }
+        }
+        __syncthreads();
+        WB_PROF(pk_ + 2);
+        WB_NEXT_PHASE();
+    } else {
+        {
+            const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
+            WB_FOR_TASKS(ntask) {
+                const int k = tt % KC, t = tt / KC;
+                Ctx V{&S.tb, &S.c[k]};
+                const Node nd = unpack_node(V.c->node);
+                if (t < nfull) {
                     int mode, c;
                     if (t < 2) { mode = t; c = 0; }
                     else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
+                    unsigned ssd; int rate;
                     full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, use_slots ? mode : -1);
-                    if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
+                    if (lane == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
+                } else {
+                    int u = t - nfull;
+                    int c = u / 13, mi = u - c * 13;
+                    unsigned sad = sad_task(V, V.c->g, nd, c, c_cand15[2 + mi], ws, lane);
+                    if (lane == 0) V.c->r_sad[t] = sad;
                 }
-            } else {
-                int u = t - nfull;
-                int c = u / 13, mi = u - c * 13;
-                unsigned sad = sad_task(V, V.c->g, nd, c, c_cand15[2 + mi], ws, lane);
-                if (lane == 0) V.c->r_sad[2 * ncomp + u] = sad;
-            }
-        }
-    }
-    __syncthreads();
-    WB_PROF(pk_ + 2);
-    WB_NEXT_PHASE();
-    if (tid < KC && S.c[tid].active) {
-        Ctx V{&S.tb, &S.c[tid]};
-        CtuCtx &C = *V.c;
-        const Node nd = unpack_node(C.node);
-        unsigned ssd0 = C.r_ssd[0], ssd1 = C.r_ssd[1];
-        long long r0 = C.r_rate[0], r1 = C.r_rate[1];
-        if (ncomp == 3) {
-            ssd0 += C.r_ssd[2] + C.r_ssd[3]; r0 += (long long)C.r_rate[2] + C.r_rate[3];
-            ssd1 += C.r_ssd[4] + C.r_ssd[5]; r1 += (long long)C.r_rate[4] + C.r_rate[5];
-        }
-        C.cost_pl = rd_cost(ssd0, r0 + luma_hdr(V, tab, nd, 0, 0), tab->lambda_rd);
-        C.cost_dc = rd_cost(ssd1, r1 + luma_hdr(V, tab, nd, 1, 0), tab->lambda_rd);
-        const int nfull = 2 * ncomp;
-        int best = 0;
-        float bc = 0.f;
-        for (int i = 0; i < 13; i++) {
-            unsigned s = C.r_sad[nfull + i];
-            if (ncomp == 3) s += C.r_sad[nfull + 13 + i] + C.r_sad[nfull + 26 + i];
-            float c = __uint2float_rn(s);
-            if (i == 0 || c < bc) { bc = c; best = i; }
-        }
-        C.cur = c_cand15[2 + best];
-        C.cur_cost = bc;
-        C.v0 = !(C.cur < 2 + 2);
-        C.v1 = !(C.cur + 2 > 66);
-    }
-    __syncthreads();
-    WB_PROF(pk_ + 3);
-    // ---- phases 2,3: SAD refinement +-2, +-1 (step_search aux=true, block_splitter.rs:905-973)
-    for (int step = 2; step >= 1; step >>= 1) {
-        WB_FOR_TASKS(2 * ncomp) {
-            const int k = tt % KC, t = tt / KC;
-            Ctx V{&S.tb, &S.c[k]};
-            int cand = t / ncomp, c = t - cand * ncomp;
-            if (cand == 0 ? V.c->v0 : V.c->v1) {
-                unsigned sad = sad_task(V, V.c->g, unpack_node(V.c->node), c, cand == 0 ? V.c->cur - step : V.c->cur + step, ws, lane);
-                if (lane == 0) V.c->r_sad[t] = sad;
             }
         }
         __syncthreads();
-    WB_PROF(pk_ + 4);
+        WB_PROF(pk_ + 2);
         WB_NEXT_PHASE();
         if (tid < KC && S.c[tid].active) {
             CtuCtx &C = S.c[tid];
-            float c0 = FLT_MAX, c1 = FLT_MAX;
-            if (C.v0) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += C.r_sad[c]; c0 = __uint2float_rn(s); }
-            if (C.v1) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += C.r_sad[ncomp + c]; c1 = __uint2float_rn(s); }
-            float mn = fminf(fminf(C.cur_cost, c0), c1);
-            if (C.cur_cost == mn) {
-            } else if (c0 == mn) { C.cur -= step; C.cur_cost = c0; }
-            else { C.cur += step; C.cur_cost = c1; }
-            const int ns = step >> 1;
-            if (ns > 0) { C.v0 = !(C.cur < 2 + ns); C.v1 = !(C.cur + ns > 66); }
-            else { C.dir = C.cur; C.v0 = !(C.dir < 3); C.v1 = !(C.dir + 1 > 66); }
+            const int nfull = 2 * ncomp;
+            int best = 0;
+            float bc = 0.f;
+            for (int i = 0; i < 13; i++) {
+                unsigned s = C.r_sad[nfull + i];
+                if (ncomp == 3) s += C.r_sad[nfull + 13 + i] + C.r_sad[nfull + 26 + i];
+                float c = __uint2float_rn(s);
+                if (i == 0 || c < bc) { bc = c; best = i; }
+            }
+            C.cur = c_cand15[2 + best];
+            C.cur_cost = bc;
+            C.v0 = !(C.cur < 2 + 2);
+            C.v1 = !(C.cur + 2 > 66);
         }
         __syncthreads();
-    WB_PROF(pk_ + 5);
+        WB_PROF(pk_ + 3);
+        // ---- phases 2,3: SAD refinement +-2, +-1 (step_search aux=true, block_splitter.rs:905-973)
+        for (int step = 2; step >= 1; step >>= 1) {
+            WB_FOR_TASKS(2 * ncomp) {
+                const int k = tt % KC, t = tt / KC;
+                Ctx V{&S.tb, &S.c[k]};
+                int cand = t / ncomp, c = t - cand * ncomp;
+                if (cand == 0 ? V.c->v0 : V.c->v1) {
+                    unsigned sad = sad_task(V, V.c->g, unpack_node(V.c->node), c, cand == 0 ? V.c->cur - step : V.c->cur + step, ws, lane);
+                    if (lane == 0) V.c->r_sad[t] = sad;
+                }
+            }
+            __syncthreads();
+            WB_PROF(pk_ + 4);
+            WB_NEXT_PHASE();
+            if (tid < KC && S.c[tid].active) {
+                CtuCtx &C = S.c[tid];
+                float c0 = FLT_MAX, c1 = FLT_MAX;
+                if (C.v0) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += C.r_sad[c]; c0 = __uint2float_rn(s); }
+                if (C.v1) { unsigned s = 0; for (int c = 0; c < ncomp; c++) s += C.r_sad[ncomp + c]; c1 = __uint2float_rn(s); }
+                float mn = fminf(fminf(C.cur_cost, c0), c1);
+                if (C.cur_cost == mn) {
+                } else if (c0 == mn) { C.cur -= step; C.cur_cost = c0; }
+                else { C.cur += step; C.cur_cost = c1; }
+                const int ns = step >> 1;
+                if (ns > 0) { C.v0 = !(C.cur < 2 + ns); C.v1 = !(C.cur + ns > 66); }
+                else { C.dir = C.cur; C.v0 = !(C.dir < 3); C.v1 = !(C.dir + 1 > 66); }
+            }
+            __syncthreads();
+            WB_PROF(pk_ + 5);
+        }
     }
     // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false); 4x4 TBs two per warp
     if (id.depth == 3) {
@@ -298,6 +306,16 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
                 int mode = cand == 0 ? C.dir : (cand == 1 ? C.dir - 1 : C.dir + 1);
                 cc[cand] = rd_cost(ssd, r + luma_hdr(V, tab, nd, mode, 0), tab->lambda_rd);
             }
+        }
+        {   // planar and DC (evaluated in phase 1)
+            unsigned ssd0 = C.pd_ssd[0][0], ssd1 = C.pd_ssd[1][0];
+            long long r0 = C.pd_rate[0][0], r1 = C.pd_rate[1][0];
+            if (ncomp == 3) {
+                ssd0 += C.pd_ssd[0][1] + C.pd_ssd[0][2]; r0 += (long long)C.pd_rate[0][1] + C.pd_rate[0][2];
+                ssd1 += C.pd_ssd[1][1] + C.pd_ssd[1][2]; r1 += (long long)C.pd_rate[1][1] + C.pd_rate[1][2];
+            }
+            C.cost_pl = rd_cost(ssd0, r0 + luma_hdr(V, tab, nd, 0, 0), tab->lambda_rd);
+            C.cost_dc = rd_cost(ssd1, r1 + luma_hdr(V, tab, nd, 1, 0), tab->lambda_rd);
         }
         float mn = fminf(fminf(cc[0], cc[1]), cc[2]);
         if (cc[0] == mn) { C.dir_cost = cc[0]; C.dir_cand = 0; }
@@ -716,6 +734,11 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
         unsigned pk = 0;
         for (int i = 0; i < 4; i++) pk |= ((unsigned)(uint8_t)c_fC[tid][i]) << (8 * i);
         S.tb.fc[tid] = (int)pk;
+    }
+    for (int m = tid; m < 68; m += NTHREADS) {
+        const int ang = m < 67 ? c_angle[m] : 0;
+        S.tb.ang[m] = (int8_t)ang;
+        S.tb.invang[m] = (int16_t)(ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0));
     }
 }
 

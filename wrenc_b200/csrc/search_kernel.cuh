@@ -76,6 +76,8 @@ struct Tables {
     int32_t ldq[64];
     int32_t lv[64];
     int32_t fc[32];            // fC taps packed as 4 x int8
+    int16_t invang[68];        // inverse angle per mode (sign of the angle kept; intra_predictor.rs:1330-1341)
+    int8_t ang[68];            // intraPredAngle per mode
 };
 
 struct WarpScratch {  // pointers into the scratch pool
@@ -108,7 +110,8 @@ struct alignas(16) CtuCtx {
     int16_t svLvC[2][256 + 64 + 16];
     uint8_t svLm[3][64], svCm[3][16];
     // reference samples of the current node: [comp][raw|filtered]
-    int16_t seq[3][132];
+    int16_t seq[3][132];      // after build_refs: the substituted samples in one line, left[2n] ... left[1], corner, above[0] ... above[2n-1]
+    int16_t seqF[132];        // the same line of the [1 2 1] filtered luma references
     int16_t refL[3][2][68];
     int16_t refA[3][2][64];
     uint8_t pds[256];         // CCLM down-sampled luma of the current node
@@ -285,6 +288,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             if (j < tot) {
                 if (j < nl) L[nl - 1 - j] = (int16_t)vals[r];
                 else A[j - nl] = (int16_t)vals[r];
+                seq[j] = (int16_t)vals[r];
             }
         }
     }
@@ -297,6 +301,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             else if (i == nl - 1) v = L[i];
             else v = (L[i + 1] + 2 * L[i] + L[i - 1] + 2) >> 2;
             LF[i] = (int16_t)v;
+            S.c->seqF[nl - 1 - i] = (int16_t)v;
         }
         for (int i = lane; i < na; i += 32) {
             int v;
@@ -304,6 +309,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             else if (i == na - 1) v = A[i];
             else v = (A[i - 1] + 2 * A[i] + A[i + 1] + 2) >> 2;
             AF[i] = (int16_t)v;
+            S.c->seqF[nl + i] = (int16_t)v;
         }
     }
     __syncwarp();
@@ -564,6 +570,144 @@ __device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x
         p = clip8(v >> 6);
     }
     return p;
+}
+
+// Angular prediction of one sample straight from the reference line (no per-task projection array): with
+// E[j] = above[j-1] (j > 0), corner (j = 0), left[-j] (j < 0), the projected reference of intra_predictor.rs:1398-1414 /
+// 1480-1495 is ref[idx] = E[+-f(idx)], f(idx) = min(idx, 2n) for idx >= 0 and -min((idx * invAngle + 256) >> 9, n) below
+// (+ for the vertical modes, - for the horizontal ones).  mode, c, n may differ from lane to lane.
+__device__ __forceinline__ int ang_sample_direct(const Ctx S, int c, int n, int l2, int mode, int x, int y) {
+    const int ang = S.tb->ang[mode], inv = S.tb->invang[mode];
+    const bool vertical = mode >= 34;
+    const int filt = (c == 0 && n >= 8 && (mode == 2 || mode == 34 || mode == 66)) ? 1 : 0;
+    const int16_t *lf = S.c->refL[c][filt], *ab = S.c->refA[c][filt];
+    const int16_t *e0 = (filt ? S.c->seqF : S.c->seq[c]) + 2 * n;
+    const int t = vertical ? y : x, u = vertical ? x : y;
+    const int prod = (t + 1) * ang;
+    const int ifact = prod & 31, base = u + (prod >> 5);
+    auto tap = [&](int idx) -> int {
+        const int f = idx >= 0 ? min(idx, 2 * n) : -min((idx * inv + 256) >> 9, n);
+        return e0[vertical ? f : -f];
+    };
+    int p;
+    if (c == 0) {
+        int f0, f1, f2, f3;
+        bool use_fg = false;
+        if (!(mode == 2 || mode == 34 || mode == 66)) {
+            const int md = min(abs(mode - 50), abs(mode - 18));
+            const int thr = l2 == 2 ? 24 : (l2 == 3 ? 14 : (l2 == 4 ? 2 : 0));
+            use_fg = md > thr;
+        }
+        if (use_fg) {
+            const int h = ifact >> 1;
+            f0 = 16 - h; f1 = 32 - h; f2 = 16 + h; f3 = h;
+        } else {
+            const int pk = S.tb->fc[ifact];
+            f0 = (int8_t)(pk & 255); f1 = (int8_t)((pk >> 8) & 255); f2 = (int8_t)((pk >> 16) & 255); f3 = pk >> 24;
+        }
+        p = clip8((f0 * tap(base) + f1 * tap(base + 1) + f2 * tap(base + 2) + f3 * tap(base + 3) + 32) >> 6);
+    } else if (ifact != 0) {
+        p = (((32 - ifact) * tap(base + 1) + ifact * tap(base + 2) + 16) >> 5) & 255;
+    } else {
+        p = tap(base + 1) & 255;
+    }
+    if (mode <= 18 || mode >= 50) {  // PDPC (intra_predictor.rs:355-757)
+        int ns;
+        if (mode == 18 || mode == 50) ns = (2 * l2 - 2) >> 2;
+        else ns = min(l2 - ilog2i(3 * inv - 2) + 8, 2);
+        if (ns >= 0) {
+            const int16_t *lrs = lf + 1, *ars = ab;
+            int refl = 0, reft = 0, wl = 0, wt = 0;
+            if (mode == 18 || mode == 50) {
+                const int corner = lf[0];
+                refl = lrs[y] - corner + p; reft = ars[x] - corner + p;
+                if (mode == 50) wl = pdpc_w(ns, x); else wt = pdpc_w(ns, y);
+            } else if (mode < 18) {
+                if (y < (3 << ns)) reft = ars[x + (((y + 1) * inv + 256) >> 9)];
+                wt = pdpc_w(ns, y);
+            } else {
+                if (x < (3 << ns)) refl = lrs[y + (((x + 1) * inv + 256) >> 9)];
+                wl = pdpc_w(ns, x);
+            }
+            const int v = (int16_t)(refl * wl + reft * wt + (64 - wt - wl) * p + 32);
+            p = clip8(v >> 6);
+        }
+    }
+    return p;
+}
+
+// SAD of one warp-iteration of the direction search: the lanes cover the samples of one angular mode over the node's
+// components (8x8 CU: luma rows in two iterations, then Cb | Cr by the two half-warps; 4x4 luma CU: one mode per half-warp).
+__device__ __forceinline__ unsigned dir_sad_item(const Ctx S, const Node nd, int c, int mode, int idx) {
+    const int cs = c != 0, n = nd.w >> cs, l2 = ilog2i(n), bx = nd.x >> cs, by = nd.y >> cs;
+    const int x = idx & (n - 1), y = idx >> l2;
+    const int p = ang_sample_direct(S, c, n, l2, mode, x, y);
+    return (unsigned)abs(p - org_at(S, c, bx + x, by + y));
+}
+// summed-over-components SAD of `mode` for an 8x8 SINGLE_TREE CU (uniform result)
+__device__ __forceinline__ unsigned dir_sad8(const Ctx S, const Node nd, int mode, int lane) {
+    unsigned s = dir_sad_item(S, nd, 0, mode, lane) + dir_sad_item(S, nd, 0, mode, 32 + lane) + dir_sad_item(S, nd, 1 + (lane >> 4), mode, lane & 15);
+    return warp_sumu(s);
+}
+// SADs of two modes of a 4x4 luma CU, one per half-warp; returns this half's sum (uniform within the half)
+__device__ __forceinline__ unsigned dir_sad4(const Ctx S, const Node nd, int mode, int lane) {
+    unsigned s = dir_sad_item(S, nd, 0, mode, lane & 15);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// The whole SAD-driven direction search of one CU up to 8x8 by ONE warp (block_splitter.rs:887-973: 13 coarse angular
+// modes, then step_search +-2 and +-1 on the summed SAD, first-minimum rules H6).  The SADs are integers below 2^24, so the
+// reference's f32 comparisons are integer comparisons.  Leaves dir, v0 (dir-1 valid), v1 (dir+1 valid) in the CTU context.
+__device__ __noinline__ void dir_search(const Ctx S, const Node nd, int lane) {
+    WB_SHARED_CTX(S);
+    const bool luma_only = nd.tree == DUAL_TREE_LUMA;  // 4x4 CU
+    unsigned bs = 0;
+    int best = 0;
+    if (luma_only) {
+#pragma unroll 1
+        for (int i = 0; i < 14; i += 2) {
+            const int mi = min(i + (lane >> 4), 12);
+            const unsigned s = dir_sad4(S, nd, c_cand15[2 + mi], lane);
+            const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
+            if (i == 0 || s0 < bs) { bs = s0; best = i; }
+            if (i + 1 < 13 && s1 < bs) { bs = s1; best = i + 1; }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < 13; i++) {
+            const unsigned s = dir_sad8(S, nd, c_cand15[2 + i], lane);
+            if (i == 0 || s < bs) { bs = s; best = i; }
+        }
+    }
+    int cur = c_cand15[2 + best];
+    unsigned cur_cost = bs;
+#pragma unroll 1
+    for (int step = 2; step >= 1; step >>= 1) {
+        const bool v0 = !(cur < 2 + step), v1 = !(cur + step > 66);
+        unsigned c0 = 0xffffffffu, c1 = 0xffffffffu;
+        if (luma_only) {
+            const int m = (lane >> 4) ? (v1 ? cur + step : 66) : (v0 ? cur - step : 2);
+            const unsigned s = dir_sad4(S, nd, m, lane);
+            const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
+            if (v0) c0 = s0;
+            if (v1) c1 = s1;
+        } else {
+            if (v0) c0 = dir_sad8(S, nd, cur - step, lane);
+            if (v1) c1 = dir_sad8(S, nd, cur + step, lane);
+        }
+        const unsigned mn = min(min(cur_cost, c0), c1);
+        if (cur_cost == mn) {
+        } else if (c0 == mn) { cur -= step; cur_cost = c0; }
+        else { cur += step; cur_cost = c1; }
+    }
+    if (lane == 0) {
+        S.c->dir = cur;
+        S.c->v0 = !(cur < 3);
+        S.c->v1 = !(cur + 1 > 66);
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
