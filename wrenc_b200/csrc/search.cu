@@ -963,7 +963,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
             else build_refs(V, g, nd, c, lane);
             __syncwarp();
             PredCtx pc;
-            pred_setup(V, g, nd, c, P.mode, ws.refx, lane, 32, 0xffffffffu, pc);
+            pred_setup(V, g, nd, c, P.mode, ws.refx, lane, pc);
             for (int i = lane; i < n * n; i += 32) P.out8[i] = (uint8_t)pred_sample(V, pc, i % n, i / n);
         }
         return;

@@ -193,9 +193,10 @@ __device__ __forceinline__ unsigned warp_sumu(unsigned v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// lane groups: the whole warp, or one of its halves (two independent 4x4 blocks per warp); collectives take the group's mask
-__device__ __forceinline__ int group_sum(int v, int gsz, unsigned mask) {
-    for (int o = gsz >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
+// sum over one half of the warp (two independent 4x4 blocks per warp); mask = the half's lanes
+__device__ __forceinline__ int half_sum(int v, unsigned mask) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o);
     return v;
 }
 __device__ __forceinline__ int warp_max(int v) {
@@ -218,7 +219,8 @@ __device__ __forceinline__ bool nb_avail(const CtuGeom g, const Node nd, int xn,
 
 __device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float lambda) {
     // block_splitter.rs:472-473 / 779: ssd as f32 + lambda * (level as f32 / 16384.0)
-    return __fadd_rn(__uint2float_rn(ssd), __fmul_rn(lambda, __fdiv_rn(__ll2float_rn(level), 16384.0f)));
+    // (the division by 2^14 is an exact scaling, so it is done as a multiplication by 2^-14: bit-identical, no division sequence)
+    return __fadd_rn(__uint2float_rn(ssd), __fmul_rn(lambda, __fmul_rn(__ll2float_rn(level), 6.103515625e-05f)));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -311,6 +313,36 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             AF[i] = (int16_t)v;
             S.c->seqF[nl + i] = (int16_t)v;
         }
+    }
+    __syncwarp();
+}
+
+// The same for a 4x4 block (any component): 9 left + 8 above samples, one per lane, substitution by shuffles.
+__device__ __noinline__ void build_refs4(const Ctx S, const CtuGeom g, const Node nd, int c, int lane) {
+    WB_SHARED_CTX(S);
+    const int cs = c != 0, xt = nd.x >> cs, yt = nd.y >> cs;
+    constexpr int nl = 9, tot = 17;
+    const int j = lane;
+    int v = -1;
+    if (j < tot) {
+        if (j < nl) {
+            const int y = (nl - 1 - j) - 1;
+            const int yr = (y == -1) ? -1 : (y & ~3);
+            if (nb_avail(g, nd, (xt - 1) << cs, (yt + yr) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt - 1, yt + y);
+        } else {
+            const int x = j - nl;
+            if (nb_avail(g, nd, (xt + (x & ~3)) << cs, (yt - 1) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt + x, yt - 1);
+        }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, v >= 0);
+    const unsigned mm = mask & (0xffffffffu >> (31 - lane));
+    const int src = mm ? 31 - __clz(mm) : (mask ? __ffs(mask) - 1 : 0);
+    int val = __shfl_sync(0xffffffffu, v, src);
+    if (!mask) val = 128;
+    if (j < tot) {
+        if (j < nl) S.c->refL[c][0][nl - 1 - j] = (int16_t)val;
+        else S.c->refA[c][0][j - nl] = (int16_t)val;
+        S.c->seq[c][j] = (int16_t)val;
     }
     __syncwarp();
 }
@@ -448,7 +480,7 @@ __device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom g, const Nod
 }
 
 // per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
-__device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int gl, int gsz, unsigned gmask, PredCtx &pc) {
+__device__ __forceinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(refx);
     const int cs = c != 0;
@@ -472,15 +504,15 @@ __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node
     if (mode == MODE_DC) {
         pc.kind = 1; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
         int s = 0;
-        for (int i = gl; i < n; i += gsz) s += pc.ab[i] + pc.lf[1 + i];
-        s = group_sum(s, gsz, gmask) + n;
+        for (int i = lane; i < n; i += 32) s += pc.ab[i] + pc.lf[1 + i];
+        s = warp_sum(s) + n;
         pc.dc = (s >> (pc.l2 + 1)) & 255;
         return;
     }
     pc.kind = 2;
-    const int ang = c_angle[mode];
+    const int ang = S.tb->ang[mode];
     pc.ang = ang;
-    pc.inv_angle = ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0);
+    pc.inv_angle = S.tb->invang[mode];
     pc.vertical = mode >= 34;
     if (mode == 2 || mode == 34 || mode == 66) pc.use_fg = 0;
     else {
@@ -497,7 +529,7 @@ __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node
     // projection array r[idx], idx in [-n, 2n+2]  (intra_predictor.rs:1398-1414 / 1480-1495)
     int16_t *r = refx + n;
     const int lo = ang < 0 ? -n : 0, hi = ang < 0 ? n + 1 : 2 * n + 2;
-    for (int idx = lo + gl; idx <= hi; idx += gsz) {
+    for (int idx = lo + lane; idx <= hi; idx += 32) {
         int v;
         if (pc.vertical) {
             if (idx < 0) v = pc.lf[min((idx * pc.inv_angle + 256) >> 9, n)];
@@ -511,7 +543,7 @@ __device__ __noinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node
         }
         r[idx] = (int16_t)v;
     }
-    __syncwarp(gmask);
+    __syncwarp();
 }
 
 __device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x, int y) {
@@ -636,24 +668,27 @@ __device__ __forceinline__ int ang_sample_direct(const Ctx S, int c, int n, int 
     return p;
 }
 
-// SAD of one warp-iteration of the direction search: the lanes cover the samples of one angular mode over the node's
-// components (8x8 CU: luma rows in two iterations, then Cb | Cr by the two half-warps; 4x4 luma CU: one mode per half-warp).
-__device__ __forceinline__ unsigned dir_sad_item(const Ctx S, const Node nd, int c, int mode, int idx) {
-    const int cs = c != 0, n = nd.w >> cs, l2 = ilog2i(n), bx = nd.x >> cs, by = nd.y >> cs;
-    const int x = idx & (n - 1), y = idx >> l2;
-    const int p = ang_sample_direct(S, c, n, l2, mode, x, y);
-    return (unsigned)abs(p - org_at(S, c, bx + x, by + y));
-}
-// summed-over-components SAD of `mode` for an 8x8 SINGLE_TREE CU (uniform result)
-__device__ __forceinline__ unsigned dir_sad8(const Ctx S, const Node nd, int mode, int lane) {
-    unsigned s = dir_sad_item(S, nd, 0, mode, lane) + dir_sad_item(S, nd, 0, mode, 32 + lane) + dir_sad_item(S, nd, 1 + (lane >> 4), mode, lane & 15);
-    return warp_sumu(s);
-}
-// SADs of two modes of a 4x4 luma CU, one per half-warp; returns this half's sum (uniform within the half)
-__device__ __forceinline__ unsigned dir_sad4(const Ctx S, const Node nd, int mode, int lane) {
-    unsigned s = dir_sad_item(S, nd, 0, mode, lane & 15);
+// SAD of one angular mode for the direction search, summed over the CU's components.  8x8 SINGLE_TREE CU: the warp covers
+// the 64 luma samples in two iterations, then Cb | Cr by the two half-warps (result uniform over the warp).  4x4 luma CU:
+// one iteration, and the two half-warps evaluate two different modes (`mode` is per half; result uniform within a half).
+__device__ __noinline__ unsigned dir_sad(const Ctx S, const Node nd, int mode, int lane) {
+    WB_SHARED_CTX(S);
+    const bool luma_only = nd.tree == DUAL_TREE_LUMA;
+    const int nit = luma_only ? 1 : 3;
+    unsigned s = 0;
+#pragma unroll 1
+    for (int j = 0; j < nit; j++) {
+        const bool last = j == nit - 1;
+        const int c = (last && !luma_only) ? 1 + (lane >> 4) : 0;
+        const int idx = last ? (lane & 15) : 32 * j + lane;
+        const int cs = c != 0, n = nd.w >> cs, l2 = ilog2i(n), bx = nd.x >> cs, by = nd.y >> cs;
+        const int x = idx & (n - 1), y = idx >> l2;
+        const int p = ang_sample_direct(S, c, n, l2, mode, x, y);
+        s += (unsigned)abs(p - org_at(S, c, bx + x, by + y));
+    }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (!luma_only) s += __shfl_xor_sync(0xffffffffu, s, 16);
     return s;
 }
 
@@ -662,24 +697,17 @@ __device__ __forceinline__ unsigned dir_sad4(const Ctx S, const Node nd, int mod
 // reference's f32 comparisons are integer comparisons.  Leaves dir, v0 (dir-1 valid), v1 (dir+1 valid) in the CTU context.
 __device__ __noinline__ void dir_search(const Ctx S, const Node nd, int lane) {
     WB_SHARED_CTX(S);
-    const bool luma_only = nd.tree == DUAL_TREE_LUMA;  // 4x4 CU
+    const bool luma_only = nd.tree == DUAL_TREE_LUMA;  // 4x4 CU: two modes per call
+    const int half = lane >> 4;
     unsigned bs = 0;
     int best = 0;
-    if (luma_only) {
 #pragma unroll 1
-        for (int i = 0; i < 14; i += 2) {
-            const int mi = min(i + (lane >> 4), 12);
-            const unsigned s = dir_sad4(S, nd, c_cand15[2 + mi], lane);
-            const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
-            if (i == 0 || s0 < bs) { bs = s0; best = i; }
-            if (i + 1 < 13 && s1 < bs) { bs = s1; best = i + 1; }
-        }
-    } else {
-#pragma unroll 1
-        for (int i = 0; i < 13; i++) {
-            const unsigned s = dir_sad8(S, nd, c_cand15[2 + i], lane);
-            if (i == 0 || s < bs) { bs = s; best = i; }
-        }
+    for (int i = 0; i < 13; i += luma_only ? 2 : 1) {
+        const int mi = luma_only ? min(i + half, 12) : i;
+        const unsigned s = dir_sad(S, nd, c_cand15[2 + mi], lane);
+        const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
+        if (i == 0 || s0 < bs) { bs = s0; best = i; }
+        if (luma_only && i + 1 < 13 && s1 < bs) { bs = s1; best = i + 1; }
     }
     int cur = c_cand15[2 + best];
     unsigned cur_cost = bs;
@@ -687,15 +715,15 @@ __device__ __noinline__ void dir_search(const Ctx S, const Node nd, int lane) {
     for (int step = 2; step >= 1; step >>= 1) {
         const bool v0 = !(cur < 2 + step), v1 = !(cur + step > 66);
         unsigned c0 = 0xffffffffu, c1 = 0xffffffffu;
-        if (luma_only) {
-            const int m = (lane >> 4) ? (v1 ? cur + step : 66) : (v0 ? cur - step : 2);
-            const unsigned s = dir_sad4(S, nd, m, lane);
+#pragma unroll 1
+        for (int cand = 0; cand < (luma_only ? 1 : 2); cand++) {
+            const int side = luma_only ? half : cand;  // 0: cur - step, 1: cur + step
+            const int m = side ? (v1 ? cur + step : 66) : (v0 ? cur - step : 2);
+            const unsigned s = dir_sad(S, nd, m, lane);
             const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
-            if (v0) c0 = s0;
-            if (v1) c1 = s1;
-        } else {
-            if (v0) c0 = dir_sad8(S, nd, cur - step, lane);
-            if (v1) c1 = dir_sad8(S, nd, cur + step, lane);
+            if (luma_only) { if (v0) c0 = s0; if (v1) c1 = s1; }
+            else if (cand == 0) { if (v0) c0 = s0; }
+            else if (v1) c1 = s0;
         }
         const unsigned mn = min(min(cur_cost, c0), c1);
         if (cur_cost == mn) {
@@ -1095,29 +1123,27 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
 
 // prediction of one (mode, component) block: the only place pred_sample is instantiated in the search kernel.
 // Writes the samples to pred_out (may be null) and returns the SAD against the source block.
-__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int gl, int gsz,
-                                               unsigned gmask) {
+__device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(refx);
     if (pred_out) WB_SHARED_PTR(pred_out);
-    PredCtx pc_mem;
-    pred_setup(S, g, nd, c, mode, refx, gl, gsz, gmask, pc_mem);
-    const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
+    PredCtx pc;
+    pred_setup(S, g, nd, c, mode, refx, lane, pc);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
 #pragma unroll 1
-    for (int i = gl; i < n * n; i += gsz) {
+    for (int i = lane; i < n * n; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int p = pred_sample(S, pc, x, y);
         if (pred_out) pred_out[i] = (uint8_t)p;
         sad += abs(p - org_at(S, c, bx + x, by + y));
     }
-    return (unsigned)group_sum((int)sad, gsz, gmask);
+    return warp_sumu(sad);
 }
 
 // SAD of one (mode, component) (block_splitter.rs:64-108 / 476-522)
 __device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, const WarpScratch ws, int lane) {
-    return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane, 32, 0xffffffffu);
+    return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane);
 }
 
 // full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
@@ -1127,7 +1153,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
-    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane, 32, 0xffffffffu) != 0;
+    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
     __syncwarp();
     int16_t *A = ws.A, *B = ws.B;
     bool anyres = anysad;
@@ -1205,15 +1231,28 @@ __device__ __forceinline__ int dot4_s8(int packed, int a0, int a1, int a2, int a
 __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit, int slot,
                                         const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out) {
     WB_SHARED_CTX(S);
-    WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
+    WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B);
     const int hb = lane & 16, gl = lane & 15, half = hb >> 4;
     const unsigned hm = half ? 0xffff0000u : 0x0000ffffu;
     const int cs = c != 0, bx = nd.x >> cs, by = nd.y >> cs;
     const int x = gl & 3, y = gl >> 2;
-    uint8_t *pbuf = ws.pred + 16 * half;
-    predict_block(S, g, nd, c, mode, ws.refx + 50 * half, pbuf, gl, 16, hm);
-    __syncwarp(hm);
-    const int p = pbuf[gl];
+    int p;  // prediction sample, straight from the reference samples (no projection array, no per-task setup pass)
+    if (mode >= 2 && mode <= 66) {
+        p = ang_sample_direct(S, c, 4, 2, mode, x, y);
+    } else if (mode > 66) {
+        PredCtx pc;
+        cclm_params(S, g, nd, c, mode, pc);
+        p = pc.cclm128 ? 128 : clip8(((S.c->pds[gl] * pc.a) >> pc.k) + pc.b);
+    } else {  // planar / DC with PDPC, n = 4 (nScale 0, unfiltered references)
+        const int16_t *lrs = S.c->refL[c][0] + 1, *ars = S.c->refA[c][0];
+        if (mode == MODE_PLANAR) {
+            p = (((3 - y) * ars[x] + (y + 1) * lrs[4] + (3 - x) * lrs[y] + (x + 1) * ars[4] + 4) >> 3) & 255;
+        } else {
+            p = ((ars[0] + ars[1] + ars[2] + ars[3] + lrs[0] + lrs[1] + lrs[2] + lrs[3] + 4) >> 3) & 255;
+        }
+        const int wl = pdpc_w(0, x), wt = pdpc_w(0, y);
+        p = clip8((int)(int16_t)(lrs[y] * wl + ars[x] * wt + (64 - wt - wl) * p + 32) >> 6);
+    }
     const int org = org_at(S, c, bx + x, by + y);
     const int res = org - p;
     // ---- forward DCT (transformer.rs:2040-2378 with n = 4: shifts 1 and 8)
@@ -1327,7 +1366,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
         const unsigned bal = (__ballot_sync(hm, has) >> hb) & 0xffffu;
         if (has) rate = WB_LV((abs(q) + delta) >> 1);
         else if ((bal >> (gl + 1)) != 0) rate = S.tb->lv[0];
-        rate = group_sum(rate, 16, hm);
+        rate = half_sum(rate, hm);
         anylev = bal != 0;
     }
     // levels back to raster order
@@ -1353,9 +1392,29 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
         else RC(S, c, bx + x, by + y) = (uint8_t)rec;
     }
     if (slot >= 0) S.c->slotRec[slot][soff] = (uint8_t)rec;
-    ssd_out = (unsigned)group_sum(d * d, 16, hm);
+    ssd_out = (unsigned)half_sum(d * d, hm);
     rate_out = rate;
     __syncwarp(hm);
+}
+
+// SAD-driven choice among the three CCLM modes for 4x4 chroma blocks (block_splitter.rs:1041-1054 / 812-850), one warp:
+// lanes 0-15 predict Cb, 16-31 Cr; order LT, T, L with the reference's tie rules (LT unless strictly worse, then T).
+__device__ __noinline__ int cclm_search4(const Ctx S, const CtuGeom g, const Node nd, int lane) {
+    WB_SHARED_CTX(S);
+    const int c = 1 + (lane >> 4), gl = lane & 15, bx = nd.x >> 1, by = nd.y >> 1;
+    const int org = org_at(S, c, bx + (gl & 3), by + (gl >> 2)), ds = S.c->pds[gl];
+    unsigned s_lt = 0, s_t = 0, s_l = 0;
+#pragma unroll 1
+    for (int mi = 0; mi < 3; mi++) {
+        const int mode = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
+        PredCtx pc;
+        cclm_params(S, g, nd, c, mode, pc);
+        const int p = pc.cclm128 ? 128 : clip8(((ds * pc.a) >> pc.k) + pc.b);
+        const unsigned s = warp_sumu((unsigned)abs(p - org));
+        if (mi == 0) s_lt = s; else if (mi == 1) s_t = s; else s_l = s;
+    }
+    if (s_lt <= s_t && s_lt <= s_l) return MODE_LT_CCLM;
+    return s_t <= s_l ? MODE_T_CCLM : MODE_L_CCLM;
 }
 
 // The winner of a node up to 16x16 was already evaluated with unchanged inputs (the reference repeats that evaluation,
