@@ -131,12 +131,11 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const DevTables *tab = P.tab;
     const WarpScratch ws = warp_scratch(S, warp);
-    const int ncomp = id.tree == DUAL_TREE_LUMA ? 1 : 3;
+    constexpr int ncomp = 3;  // SINGLE_TREE 32x32 / 16x16 CUs (smaller CUs: small_eval)
     const bool is_root = id.depth == 0;
     const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
-    const bool use_slots = id.depth > 0;
+    const bool use_slots = id.depth > 0;  // 16x16 CUs keep every full evaluation's outcome; the root re-evaluates its winner
     [[maybe_unused]] const int pk_ = 16 * id.depth;
-    const bool small = id.depth >= 2;  // CUs up to 8x8  // nodes up to 16x16 keep every full evaluation's outcome; the root re-evaluates its winner
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
     __syncthreads();
     WB_PROF(pk_ + 0);
@@ -149,34 +148,8 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 1);
     WB_NEXT_PHASE();
-    // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs.  4x4 TBs (the luma of a 4x4 CU, the chroma of an
-    //      8x8 CU) are evaluated two per warp: planar + DC of a 4x4 luma CU, or Cb + Cr of one mode.  For CUs up to 8x8 the
-    //      whole SAD-driven direction search (coarse modes and both refinement steps) is one task of one warp (dir_search).
-    if (small) {
-        const int ntask = id.depth == 3 ? 2 : 5;
-        WB_FOR_TASKS(ntask) {
-            const int k = tt % KC, t = tt / KC;
-            Ctx V{&S.tb, &S.c[k]};
-            const Node nd = unpack_node(V.c->node);
-            if (t == 0) {
-                dir_search(V, nd, lane);
-            } else if (id.depth == 3 || t >= 3) {
-                const int half = lane >> 4;
-                const int mode = id.depth == 3 ? half : t - 3, c = id.depth == 3 ? 0 : 1 + half;
-                unsigned ssd; int rate;
-                full_pair4(V, tab, V.c->g, nd, c, mode, false, mode, ws, lane, ssd, rate);
-                if ((lane & 15) == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
-            } else {
-                const int mode = t - 1;
-                unsigned ssd; int rate;
-                full_task(V, tab, V.c->g, nd, 0, mode, false, ws, lane, ssd, rate, mode);
-                if (lane == 0) { V.c->pd_ssd[mode][0] = ssd; V.c->pd_rate[mode][0] = rate; }
-            }
-        }
-        __syncthreads();
-        WB_PROF(pk_ + 2);
-        WB_NEXT_PHASE();
-    } else {
+    // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs
+    {
         {
             const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
             WB_FOR_TASKS(ntask) {
@@ -250,42 +223,20 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             WB_PROF(pk_ + 5);
         }
     }
-    // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false); 4x4 TBs two per warp
-    if (id.depth == 3) {
-        WB_FOR_TASKS(2) {
-            const int k = tt % KC, t = tt / KC;
-            Ctx V{&S.tb, &S.c[k]};
-            const int cand = 2 * t + (lane >> 4);
-            const bool valid = cand == 0 || (cand == 1 ? V.c->v0 : (cand == 2 && V.c->v1));
-            if (valid) {
-                const int dir = V.c->dir;
-                unsigned ssd; int rate;
-                full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 0, cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1), false, 2 + cand, ws, lane, ssd, rate);
-                if ((lane & 15) == 0) { V.c->r_ssd[cand] = ssd; V.c->r_rate[cand] = rate; }
-            }
-        }
-    } else {
-        WB_FOR_TASKS(id.depth == 2 ? 6 : 9) {
-            const int k = tt % KC, t = tt / KC;
-            Ctx V{&S.tb, &S.c[k]};
-            const bool pair = id.depth == 2 && t >= 3;
-            int cand, c;
-            if (t < 3) { cand = t; c = 0; }
-            else if (pair) { cand = t - 3; c = 1 + (lane >> 4); }
-            else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
-            bool valid = cand == 0 || (cand == 1 ? V.c->v0 : V.c->v1);
-            if (valid) {
-                const int dir = V.c->dir;
-                int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
-                unsigned ssd; int rate;
-                if (pair) {
-                    full_pair4(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, 2 + cand, ws, lane, ssd, rate);
-                    if ((lane & 15) == 0) { V.c->r_ssd[3 + 2 * cand + (c - 1)] = ssd; V.c->r_rate[3 + 2 * cand + (c - 1)] = rate; }
-                } else {
-                    full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
-                    if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
-                }
-            }
+    // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false)
+    WB_FOR_TASKS(9) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        int cand, c;
+        if (t < 3) { cand = t; c = 0; }
+        else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
+        bool valid = cand == 0 || (cand == 1 ? V.c->v0 : V.c->v1);
+        if (valid) {
+            const int dir = V.c->dir;
+            int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
+            if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
         }
     }
     __syncthreads();
@@ -351,7 +302,6 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 8);
     WB_NEXT_PHASE();
-    if (ncomp == 1) return;
     // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
     WB_FOR_TASKS(1) {
         const int k = tt % KC;
@@ -383,15 +333,6 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 11);
     // ---- phase 7: CCLM full evaluation (no commit)
-    if (id.depth == 2) {
-        WB_FOR_TASKS(1) {
-            const int k = tt % KC, h = lane >> 4;
-            Ctx V{&S.tb, &S.c[k]};
-            unsigned ssd; int rate;
-            full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, -1, ws, lane, ssd, rate);
-            if ((lane & 15) == 0) { V.c->r_ssd[8 + h] = ssd; V.c->r_rate[8 + h] = rate; }
-        }
-    } else {
         WB_FOR_TASKS(2) {
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
@@ -399,7 +340,6 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
             if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
         }
-    }
     __syncthreads();
     WB_PROF(pk_ + 12);
     WB_NEXT_PHASE();
@@ -426,18 +366,6 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 13);
     // ---- phase 8: commit the CCLM chroma where it won; publish the chroma mode
-    if (id.depth == 2) {
-        WB_FOR_TASKS(1) {
-            const int k = tt % KC;
-            Ctx V{&S.tb, &S.c[k]};
-            const Node nd = unpack_node(V.c->node);
-            if (V.c->cclm_wins) {
-                unsigned ssd; int rate;
-                full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), V.c->cclm_mode, true, -1, ws, lane, ssd, rate);
-            }
-            fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
-        }
-    } else {
         WB_FOR_TASKS(2) {
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
@@ -448,6 +376,195 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             }
             if (t == 0) fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
         }
+    __syncthreads();
+    WB_PROF(pk_ + 14);
+    WB_NEXT_PHASE();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CUs up to 8x8: the 8x8 SINGLE_TREE CU, the 4x4 DUAL_TREE_LUMA CU and the 8x8 DUAL_TREE_CHROMA coding tree.  These are the
+// most numerous nodes and their blocks are too small to fill a phase with work, so the evaluation is cut into few, fat
+// phases: whatever depends only on one CTU's previous result (decision -> commit -> CCLM down-sampling -> CCLM mode search)
+// runs back to back in ONE warp per CTU instead of being separated by block-wide barriers.
+//   A  node geometry + reference samples                                    (one warp per component)
+//   B  coarse direction search in parts + refinement by the last arriver || planar / DC full evaluations
+//   C  dir, dir-1, dir+1 full evaluations
+//   D  one warp per CTU: RD decision among planar, DC, dir (costs of the 5 candidates on 5 lanes), commit of the winner from
+//      its slot, mode map; 4x4 CU: cost to the parent, done.  8x8 CU: CCLM down-sampled luma, CCLM mode by SAD
+//   E  8x8 CU: CCLM full evaluation (Cb | Cr by the two half-warps)
+//   F  8x8 CU, one warp per CTU: DM vs CCLM, commit, chroma mode
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const NodeId id, int &S_slot) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const DevTables *tab = P.tab;
+    const WarpScratch ws = warp_scratch(S, warp);
+    const bool cu4 = id.depth == 3;  // 4x4 luma CU (else the 8x8 SINGLE_TREE CU)
+    const int ncomp = cu4 ? 1 : 3;
+    const int nparts = cu4 ? 3 : 4;
+    const bool dyn = true;
+    [[maybe_unused]] const int pk_ = 16 * id.depth;
+    // ---- A
+    WB_FOR_TASKS(ncomp) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = make_node(V.c->g, id);
+        if (t == 0 && lane == 0) V.c->node = pack_node(nd);
+        if (t == 0 && !cu4) build_refs(V, V.c->g, nd, 0, lane);
+        else build_refs4(V, V.c->g, nd, t, lane);
+    }
+    __syncthreads();
+    WB_PROF(pk_ + 1);
+    WB_NEXT_PHASE();
+    // ---- B
+    WB_FOR_TASKS(cu4 ? nparts + 1 : nparts + 4) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = unpack_node(V.c->node);
+        if (!cu4 && t < 2) {  // 8x8 luma planar, DC
+            unsigned ssd; int rate;
+            full_task(V, tab, V.c->g, nd, 0, t, false, ws, lane, ssd, rate, t);
+            if (lane == 0) { V.c->pd_ssd[t][0] = ssd; V.c->pd_rate[t][0] = rate; }
+        } else if (t < (cu4 ? 0 : 2) + nparts) {
+            dir_search_part(V, nd, t - (cu4 ? 0 : 2), nparts, lane);
+        } else {  // 4x4 TBs: planar | DC of the luma CU, or Cb | Cr of one mode
+            const int half = lane >> 4;
+            const int mode = cu4 ? half : t - (2 + nparts), c = cu4 ? 0 : 1 + half;
+            unsigned ssd; int rate;
+            full_pair4(V, tab, V.c->g, nd, c, mode, false, mode, ws, lane, ssd, rate);
+            if ((lane & 15) == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
+        }
+    }
+    __syncthreads();
+    WB_PROF(pk_ + 2);
+    WB_NEXT_PHASE();
+    // ---- C
+    WB_FOR_TASKS(cu4 ? 2 : 6) {
+        const int k = tt % KC, t = tt / KC;
+        Ctx V{&S.tb, &S.c[k]};
+        const Node nd = unpack_node(V.c->node);
+        const int dir = V.c->dir;
+        if (!cu4 && t < 3) {
+            const bool valid = t == 0 || (t == 1 ? V.c->v0 : V.c->v1);
+            if (valid) {
+                unsigned ssd; int rate;
+                full_task(V, tab, V.c->g, nd, 0, t == 0 ? dir : (t == 1 ? dir - 1 : dir + 1), false, ws, lane, ssd, rate, 2 + t);
+                if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+            }
+        } else {
+            const int half = lane >> 4;
+            const int cand = cu4 ? 2 * t + half : t - 3, c = cu4 ? 0 : 1 + half;
+            const bool valid = cand == 0 || (cand == 1 ? V.c->v0 : (cand == 2 && V.c->v1));
+            if (valid) {
+                unsigned ssd; int rate;
+                full_pair4(V, tab, V.c->g, nd, c, cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1), false, 2 + cand, ws, lane, ssd, rate);
+                const int ri = c == 0 ? cand : 3 + 2 * cand + (c - 1);
+                if ((lane & 15) == 0) { V.c->r_ssd[ri] = ssd; V.c->r_rate[ri] = rate; }
+            }
+        }
+    }
+    __syncthreads();
+    WB_PROF(pk_ + 6);
+    WB_NEXT_PHASE();
+    // ---- D
+    WB_FOR_TASKS(1) {
+        const int k = tt % KC;
+        Ctx V{&S.tb, &S.c[k]};
+        CtuCtx &C = *V.c;
+        const Node nd = unpack_node(C.node);
+        int dir = C.dir;
+        // lane j < 5 prices candidate j: planar, DC, dir, dir-1, dir+1 (block_splitter.rs:472-473)
+        float cost = FLT_MAX;
+        if (lane < 5) {
+            const int cand = lane - 2;
+            const bool valid = lane < 3 || (cand == 1 ? C.v0 : C.v1);
+            if (valid) {
+                unsigned ssd;
+                long long r;
+                if (lane < 2) {
+                    ssd = C.pd_ssd[lane][0]; r = C.pd_rate[lane][0];
+                    if (ncomp == 3) { ssd += C.pd_ssd[lane][1] + C.pd_ssd[lane][2]; r += (long long)C.pd_rate[lane][1] + C.pd_rate[lane][2]; }
+                } else {
+                    ssd = C.r_ssd[cand]; r = C.r_rate[cand];
+                    if (ncomp == 3) { ssd += C.r_ssd[3 + 2 * cand] + C.r_ssd[4 + 2 * cand]; r += (long long)C.r_rate[3 + 2 * cand] + C.r_rate[4 + 2 * cand]; }
+                }
+                const int mode = lane < 2 ? lane : (cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1));
+                cost = rd_cost(ssd, r + luma_hdr(V, tab, nd, mode, 0), tab->lambda_rd);
+            }
+        }
+        const float cost_pl = __shfl_sync(0xffffffffu, cost, 0), cost_dc = __shfl_sync(0xffffffffu, cost, 1);
+        const float cc0 = __shfl_sync(0xffffffffu, cost, 2), cc1 = __shfl_sync(0xffffffffu, cost, 3), cc2 = __shfl_sync(0xffffffffu, cost, 4);
+        const float mn = fminf(fminf(cc0, cc1), cc2);
+        float dir_cost;
+        int dir_cand;
+        if (cc0 == mn) { dir_cost = cc0; dir_cand = 0; }
+        else if (cc1 == mn) { dir -= 1; dir_cost = cc1; dir_cand = 1; }
+        else { dir += 1; dir_cost = cc2; dir_cand = 2; }
+        // winner among planar, DC, dir (first minimum)
+        const float min_cost = fminf(fminf(cost_pl, cost_dc), dir_cost);
+        const int mode = cost_pl == min_cost ? 0 : (cost_dc == min_cost ? 1 : dir);
+        if (lane == 0) {
+            C.mode = mode;
+            C.leaf_cost = min_cost;
+            if (cu4) C.split[2] = __fadd_rn(C.split[2], min_cost);  // the 4x4 CU is final: its cost goes to the 8x8 parent's split cost
+        }
+        // the winner's luma and same-mode (DM) chroma were evaluated in phase B or C: copy them out of the slot
+        const int slot = mode <= 1 ? mode : 2 + dir_cand;
+        for (int t = 0; t < ncomp; t++) commit_slot(V, nd, t, slot, lane);
+        if (!cu4 && lane < 3) {
+            const int t = lane;
+            if (mode <= 1) { C.fin_ssd[t] = C.pd_ssd[mode][t]; C.fin_rate[t] = C.pd_rate[mode][t]; }
+            else { const int r = t == 0 ? dir_cand : 3 + 2 * dir_cand + (t - 1); C.fin_ssd[t] = C.r_ssd[r]; C.fin_rate[t] = C.r_rate[r]; }
+        }
+        fill_lm(V, nd, mode, lane);
+        if (!cu4) {
+            __syncwarp();
+            cclm_downsample(V, C.g, nd, lane);
+            __syncwarp();
+            const int cm = cclm_search4(V, C.g, nd, lane);
+            if (lane == 0) C.cclm_mode = cm;
+        }
+    }
+    __syncthreads();
+    WB_PROF(pk_ + 7);
+    WB_NEXT_PHASE();
+    if (cu4) return;
+    // ---- E
+    WB_FOR_TASKS(1) {
+        const int k = tt % KC, h = lane >> 4;
+        Ctx V{&S.tb, &S.c[k]};
+        unsigned ssd; int rate;
+        full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, -1, ws, lane, ssd, rate);
+        if ((lane & 15) == 0) { V.c->r_ssd[8 + h] = ssd; V.c->r_rate[8 + h] = rate; }
+    }
+    __syncthreads();
+    WB_PROF(pk_ + 12);
+    WB_NEXT_PHASE();
+    // ---- F
+    WB_FOR_TASKS(1) {
+        const int k = tt % KC;
+        Ctx V{&S.tb, &S.c[k]};
+        CtuCtx &C = *V.c;
+        const Node nd = unpack_node(C.node);
+        const unsigned ssdY = C.fin_ssd[0], ssdDM = C.fin_ssd[1] + C.fin_ssd[2];
+        const long long rateY = C.fin_rate[0], rateDM = (long long)C.fin_rate[1] + C.fin_rate[2];
+        const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
+        const unsigned ssdCC = C.r_ssd[8] + C.r_ssd[9];
+        const long long rateCC = (long long)C.r_rate[8] + C.r_rate[9];
+        const int cclm_mode = C.cclm_mode, mode = C.mode;
+        const int ck = 1 + (cclm_mode - MODE_LT_CCLM);
+        const float cost_cclm = rd_cost(ssdCC, rateCC + tab->hdr_chroma[ck], tab->lambda_rd_c);
+        const bool cclm_wins = !(cost_dm == fminf(cost_dm, cost_cclm));  // tie -> DM
+        __syncwarp();
+        if (lane == 0) {
+            C.cclm_wins = cclm_wins;
+            C.leaf_cost = cclm_wins ? rd_cost(ssdY + ssdCC, rateY + rateCC + luma_hdr(V, tab, nd, mode, ck), tab->lambda_rd)
+                                    : rd_cost(ssdY + ssdDM, rateY + rateDM + luma_hdr(V, tab, nd, mode, 0), tab->lambda_rd);
+        }
+        if (cclm_wins) {
+            unsigned ssd; int rate;
+            full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), cclm_mode, true, -1, ws, lane, ssd, rate);
+        }
+        fill_cm(V, nd, cclm_wins ? cclm_mode : mode, lane);
     }
     __syncthreads();
     WB_PROF(pk_ + 14);
@@ -455,56 +572,45 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// the 8x8 DUAL_TREE_CHROMA coding tree that follows four 4x4 luma CUs (block_splitter.rs:794-885)
+// the 8x8 DUAL_TREE_CHROMA coding tree that follows four 4x4 luma CUs (block_splitter.rs:794-885): DM (the mode of the
+// luma CU covering the centre, ctu.rs:2372-2396 = the bottom-right 4x4) against the best-SAD CCLM mode
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, const NodeId id, int &S_slot) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const bool dyn = true;
     const DevTables *tab = P.tab;
     const WarpScratch ws = warp_scratch(S, warp);
-    if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
-    __syncthreads();
-    WB_PROF(64 + 0);
+    // ---- A: reference samples of Cb, Cr; CCLM down-sampled luma
     WB_FOR_TASKS(3) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = unpack_node(V.c->node);
-        if (t < 2) build_refs(V, V.c->g, nd, 1 + t, lane);
+        const Node nd = make_node(V.c->g, id);
+        if (t == 0 && lane == 0) V.c->node = pack_node(nd);
+        if (t < 2) build_refs4(V, V.c->g, nd, 1 + t, lane);
         else cclm_downsample(V, V.c->g, nd, lane);
     }
     __syncthreads();
     WB_PROF(64 + 1);
     WB_NEXT_PHASE();
-    WB_FOR_TASKS(7) {
+    // ---- B: DM full evaluation (committed) || CCLM mode by SAD
+    WB_FOR_TASKS(2) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = unpack_node(V.c->node);
-        if (t < 1) {
-            // luma CU covering the parent's centre sample = the bottom-right 4x4 (ctu.rs:2372-2396); Cb and Cr by one half-warp each
+        if (t == 0) {
             const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1], h = lane >> 4;
             unsigned ssd; int rate;
             full_pair4(V, tab, V.c->g, nd, 1 + h, dm, true, -1, ws, lane, ssd, rate);
             if ((lane & 15) == 0) { V.c->r_ssd[h] = ssd; V.c->r_rate[h] = rate; }
         } else {
-            const int u = t - 1;
-            const int mi = u >> 1, c = 1 + (u & 1);
-            const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-            unsigned sad = sad_task(V, V.c->g, nd, c, cm, ws, lane);
-            if (lane == 0) V.c->r_sad[u] = sad;
+            const int cm = cclm_search4(V, V.c->g, nd, lane);
+            if (lane == 0) V.c->cclm_mode = cm;
         }
     }
     __syncthreads();
     WB_PROF(64 + 2);
     WB_NEXT_PHASE();
-    if (tid < KC && S.c[tid].active) {
-        CtuCtx &C = S.c[tid];
-        float lt = __uint2float_rn(C.r_sad[0] + C.r_sad[1]), t = __uint2float_rn(C.r_sad[2] + C.r_sad[3]), l = __uint2float_rn(C.r_sad[4] + C.r_sad[5]);
-        if (lt <= t && lt <= l) C.cclm_mode = MODE_LT_CCLM;
-        else if (t <= l) C.cclm_mode = MODE_T_CCLM;
-        else C.cclm_mode = MODE_L_CCLM;
-    }
-    __syncthreads();
-    WB_PROF(64 + 3);
+    // ---- C: CCLM full evaluation (not committed)
     WB_FOR_TASKS(1) {
         const int k = tt % KC, h = lane >> 4;
         Ctx V{&S.tb, &S.c[k]};
@@ -515,27 +621,30 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
     __syncthreads();
     WB_PROF(64 + 4);
     WB_NEXT_PHASE();
-    if (tid < KC && S.c[tid].active) {
-        CtuCtx &C = S.c[tid];
-        const float cost_dm = rd_cost(C.r_ssd[0] + C.r_ssd[1], (long long)C.r_rate[0] + C.r_rate[1] + tab->hdr_chroma[0], tab->lambda_rd_c);
-        const int ck = 1 + (C.cclm_mode - MODE_LT_CCLM);
-        const float cost_cclm = rd_cost(C.r_ssd[8] + C.r_ssd[9], (long long)C.r_rate[8] + C.r_rate[9] + tab->hdr_chroma[ck], tab->lambda_rd_c);
-        const float mn = fminf(cost_dm, cost_cclm);
-        C.cclm_wins = !(cost_dm == mn);
-        C.leaf_cost = mn;
-    }
-    __syncthreads();
-    WB_PROF(64 + 5);
+    // ---- D: one warp per CTU: decision (tie -> DM), commit of the CCLM chroma if it won, chroma mode, cost to the 8x8 parent
     WB_FOR_TASKS(1) {
         const int k = tt % KC;
         Ctx V{&S.tb, &S.c[k]};
-        const Node nd = unpack_node(V.c->node);
-        if (V.c->cclm_wins) {
-            unsigned ssd; int rate;
-            full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), V.c->cclm_mode, true, -1, ws, lane, ssd, rate);
+        CtuCtx &C = *V.c;
+        const Node nd = unpack_node(C.node);
+        const int cclm_mode = C.cclm_mode;
+        const float cost_dm = rd_cost(C.r_ssd[0] + C.r_ssd[1], (long long)C.r_rate[0] + C.r_rate[1] + tab->hdr_chroma[0], tab->lambda_rd_c);
+        const int ck = 1 + (cclm_mode - MODE_LT_CCLM);
+        const float cost_cclm = rd_cost(C.r_ssd[8] + C.r_ssd[9], (long long)C.r_rate[8] + C.r_rate[9] + tab->hdr_chroma[ck], tab->lambda_rd_c);
+        const float mn = fminf(cost_dm, cost_cclm);
+        const bool cclm_wins = !(cost_dm == mn);
+        const int dm = C.lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
+        __syncwarp();
+        if (lane == 0) {
+            C.cclm_wins = cclm_wins;
+            C.leaf_cost = mn;
+            C.split[2] = __fadd_rn(C.split[2], mn);
         }
-        const int dm = V.c->lm[((nd.y >> 2) + 1) * 8 + (nd.x >> 2) + 1];
-        fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : dm, lane);
+        if (cclm_wins) {
+            unsigned ssd; int rate;
+            full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), cclm_mode, true, -1, ws, lane, ssd, rate);
+        }
+        fill_cm(V, nd, cclm_wins ? cclm_mode : dm, lane);
     }
     __syncthreads();
     WB_PROF(64 + 6);
@@ -658,17 +767,15 @@ __device__ void ctu_search(Shared &S, const SearchParams &P, int &S_slot) {
                 begin_split(S, n16, 1);
                 for (int b = 0; b < 4; b++) {
                     NodeId n8{2, a, b, 0, SINGLE_TREE};
-                    leaf_eval(S, P, n8, S_slot);
+                    small_eval(S, P, n8, S_slot);
                     if (md >= 3) {
                         begin_split(S, n8, 2);
-                        for (int c = 0; c < 4; c++) {
+                        for (int c = 0; c < 4; c++) {  // the 4x4 CUs and the chroma CT add their cost to split[2] themselves
                             NodeId n4{3, a, b, c, DUAL_TREE_LUMA};
-                            leaf_eval(S, P, n4, S_slot);
-                            add_to_parent(S, 2);
+                            small_eval(S, P, n4, S_slot);
                         }
                         NodeId nc{2, a, b, 0, DUAL_TREE_CHROMA};
                         chroma_ct_eval(S, P, nc, S_slot);
-                        add_to_parent(S, 2);
                         end_split(S, n8, 2, 5 + a * 4 + b);
                     }
                     add_to_parent(S, 1);
@@ -808,7 +915,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
             if (C.active) {
                 C.pic = it >> 16; C.cyi = (it >> 8) & 255; C.cxi = it & 255;
                 C.g.cx = C.cxi * 32; C.g.cy = C.cyi * 32; C.g.W = W; C.g.H = H;
-                C.mask = 0; C.root_mode = 0;
+                C.mask = 0; C.root_mode = 0; C.dir_cnt = 0;
                 int *done = P.done + (size_t)C.pic * Wc * P.Hc;
                 if (C.cxi > 0) while (ld_relaxed(&done[C.cyi * Wc + C.cxi - 1]) != P.epoch) __nanosleep(1000);
                 if (C.cyi > 0) {

@@ -131,6 +131,8 @@ struct alignas(16) CtuCtx {
     // leaf-evaluation state
     float cost_pl, cost_dc, cur_cost, dir_cost, min_cost, cost_dm;
     int cur, dir, mode, cclm_mode, v0, v1, cclm_wins, dir_cand;
+    unsigned dir_part[4];     // direction search of CUs up to 8x8: first minimum of each part of the coarse modes, and the arrival counter
+    int dir_cnt;
     // results of the planar / DC evaluations (phase 1) and of the winner (phase 5), per component
     unsigned pd_ssd[2][3], fin_ssd[3];
     int pd_rate[2][3], fin_rate[3];
@@ -692,25 +694,38 @@ __device__ __noinline__ unsigned dir_sad(const Ctx S, const Node nd, int mode, i
     return s;
 }
 
-// The whole SAD-driven direction search of one CU up to 8x8 by ONE warp (block_splitter.rs:887-973: 13 coarse angular
-// modes, then step_search +-2 and +-1 on the summed SAD, first-minimum rules H6).  The SADs are integers below 2^24, so the
-// reference's f32 comparisons are integer comparisons.  Leaves dir, v0 (dir-1 valid), v1 (dir+1 valid) in the CTU context.
-__device__ __noinline__ void dir_search(const Ctx S, const Node nd, int lane) {
+// The SAD-driven direction search of one CU up to 8x8 (block_splitter.rs:887-973: 13 coarse angular modes, then
+// step_search +-2 and +-1 on the summed SAD, first-minimum rules H6).  The coarse modes are split over `nparts` warp tasks;
+// each leaves its first minimum as (sad << 4 | index), and the warp that finishes last (shared-memory counter) takes the
+// overall first minimum and runs the two refinement steps.  The SADs are integers below 2^24, so the reference's f32
+// comparisons are integer comparisons.  Leaves dir, v0 (dir-1 valid), v1 (dir+1 valid) in the CTU context.
+__device__ __noinline__ void dir_search_part(const Ctx S, const Node nd, int part, int nparts, int lane) {
     WB_SHARED_CTX(S);
     const bool luma_only = nd.tree == DUAL_TREE_LUMA;  // 4x4 CU: two modes per call
     const int half = lane >> 4;
-    unsigned bs = 0;
-    int best = 0;
+    const int lo = part * 13 / nparts, hi = (part + 1) * 13 / nparts;
+    unsigned bp = 0xffffffffu;
 #pragma unroll 1
-    for (int i = 0; i < 13; i += luma_only ? 2 : 1) {
-        const int mi = luma_only ? min(i + half, 12) : i;
+    for (int i = lo; i < hi; i += luma_only ? 2 : 1) {
+        const int mi = luma_only ? min(i + half, hi - 1) : i;
         const unsigned s = dir_sad(S, nd, c_cand15[2 + mi], lane);
         const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
-        if (i == 0 || s0 < bs) { bs = s0; best = i; }
-        if (luma_only && i + 1 < 13 && s1 < bs) { bs = s1; best = i + 1; }
+        bp = min(bp, (s0 << 4) | (unsigned)i);
+        if (luma_only && i + 1 < hi) bp = min(bp, (s1 << 4) | (unsigned)(i + 1));
     }
-    int cur = c_cand15[2 + best];
-    unsigned cur_cost = bs;
+    int last = 0;
+    if (lane == 0) {
+        S.c->dir_part[part] = bp;
+        __threadfence_block();
+        last = atomicAdd(&S.c->dir_cnt, 1) == nparts - 1;
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence_block();
+    for (int q = 0; q < nparts; q++) bp = min(bp, *(volatile unsigned *)&S.c->dir_part[q]);
+    if (lane == 0) S.c->dir_cnt = 0;
+    int cur = c_cand15[2 + (bp & 15u)];
+    unsigned cur_cost = bp >> 4;
 #pragma unroll 1
     for (int step = 2; step >= 1; step >>= 1) {
         const bool v0 = !(cur < 2 + step), v1 = !(cur + step > 66);
