@@ -95,13 +95,14 @@ __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, in
 }
 
 // Tasks of a phase are handed out in list order (the large luma tasks first) to whichever warp is free: a shared-memory
-// ticket per phase (S.ticket[phase parity], reset two phases later).  32x32 luma tasks need the large scratch buffers that
-// only the first NBIG warps own, so nodes of that size keep the static round-robin assignment.
-__device__ __forceinline__ int next_task(Shared &S, int &slot, bool dyn, int prev, int warp, int lane) {
-    if (!dyn) return prev < 0 ? warp : prev + NW;
+// ticket per phase (S.ticket[phase parity], reset two phases later).  32x32 luma pipelines need the large scratch buffers
+// that only the first NBIG warps own: those tasks lead the list and the first `nst` of them are taken statically by warps
+// 0..nst-1 as their first task; everything else is dynamic.
+__device__ __forceinline__ int next_task(Shared &S, int &slot, int nst, int prev, int warp, int lane) {
+    if (prev < 0 && warp < nst) return warp;
     int t = 0;
     if (lane == 0) t = atomicAdd(&S.ticket[slot], 1);
-    return __shfl_sync(0xffffffffu, t, 0);
+    return nst + __shfl_sync(0xffffffffu, t, 0);
 }
 // node geometry + availability flags of the current node, cached per CTU (x | y << 6 | w << 12 | tree << 18 | ar << 20 | bl << 21)
 __device__ __forceinline__ unsigned pack_node(const Node n) {
@@ -113,7 +114,7 @@ __device__ __forceinline__ Node unpack_node(unsigned p) {
     return n;
 }
 #define WB_FOR_TASKS(ntask)                                                                            \
-    for (int tt = next_task(S, S_slot, dyn, -1, warp, lane); tt < (ntask) * KC; tt = next_task(S, S_slot, dyn, tt, warp, lane)) \
+    for (int tt = next_task(S, S_slot, nst, -1, warp, lane); tt < (ntask) * KC; tt = next_task(S, S_slot, nst, tt, warp, lane)) \
         if (S.c[tt % KC].active)
 // called by every thread between two phases (after the barrier that ends a phase): switch to the other ticket and
 // clear the one used two phases ago
@@ -133,7 +134,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const WarpScratch ws = warp_scratch(S, warp);
     constexpr int ncomp = 3;  // SINGLE_TREE 32x32 / 16x16 CUs (smaller CUs: small_eval)
     const bool is_root = id.depth == 0;
-    const bool dyn = id.depth > 0;  // 32x32 luma tasks must stay on the warps that own large scratch
+    int nst = 0;  // leading tasks that need the large scratch (32x32 luma pipelines of the root), see next_task
     const bool use_slots = id.depth > 0;  // 16x16 CUs keep every full evaluation's outcome; the root re-evaluates its winner
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
@@ -152,6 +153,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     {
         {
             const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
+            nst = is_root ? 2 * KC : 0;
             WB_FOR_TASKS(ntask) {
                 const int k = tt % KC, t = tt / KC;
                 Ctx V{&S.tb, &S.c[k]};
@@ -174,6 +176,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         __syncthreads();
         WB_PROF(pk_ + 2);
         WB_NEXT_PHASE();
+        nst = 0;
         if (tid < KC && S.c[tid].active) {
             CtuCtx &C = S.c[tid];
             const int nfull = 2 * ncomp;
@@ -224,6 +227,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         }
     }
     // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false)
+    nst = is_root ? 3 * KC : 0;
     WB_FOR_TASKS(9) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
@@ -281,6 +285,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 7);
     // ---- phase 5: luma redo (commit) + chroma DM full evaluation (commit)
+    nst = is_root ? KC : 0;
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
@@ -303,6 +308,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     WB_PROF(pk_ + 8);
     WB_NEXT_PHASE();
     // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
+    nst = 0;
     WB_FOR_TASKS(1) {
         const int k = tt % KC;
         Ctx V{&S.tb, &S.c[k]};
@@ -401,7 +407,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
     const bool cu4 = id.depth == 3;  // 4x4 luma CU (else the 8x8 SINGLE_TREE CU)
     const int ncomp = cu4 ? 1 : 3;
     const int nparts = cu4 ? 3 : 4;
-    const bool dyn = true;
+    constexpr int nst = 0;
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     // ---- A
     WB_FOR_TASKS(ncomp) {
@@ -577,7 +583,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, const NodeId id, int &S_slot) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool dyn = true;
+    constexpr int nst = 0;
     const DevTables *tab = P.tab;
     const WarpScratch ws = warp_scratch(S, warp);
     // ---- A: reference samples of Cb, Cr; CCLM down-sampled luma
@@ -792,21 +798,31 @@ __device__ void ctu_search(Shared &S, const SearchParams &P, int &S_slot) {
 // kernel
 // ---------------------------------------------------------------------------------------------------------------
 __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
+    auto dct = [](int i, int x, int n) -> int {  // DCT-II matrix entry T[i][x] of size n (transformer.rs:934-1234)
+        if (i == 0) return 64;
+        int m = (i * (2 * x + 1) * (32 / n)) % 128;  // angle in units of pi/64
+        int sg = 1;
+        if (m > 64) m = 128 - m;
+        if (m > 32) { m = 64 - m; sg = -1; }
+        return sg * c_cos32[m];
+    };
     for (int l2 = 2; l2 <= 5; l2++) {
         const int n = 1 << l2, o = tab_off(l2);
         for (int e = tid; e < n * n; e += NTHREADS) {
-            int i = e >> l2, x = e & (n - 1);
-            int v;
-            if (i == 0) v = 64;
-            else {
-                int m = (i * (2 * x + 1) * (32 / n)) % 128;  // angle in units of pi/64
-                int s = 1;
-                if (m > 64) m = 128 - m;
-                if (m > 32) { m = 64 - m; s = -1; }
-                v = s * c_cos32[m];
-            }
+            const int i = e >> l2, x = e & (n - 1);
+            const int v = dct(i, x, n);
             S.tb.T[o + i * n + x] = (int8_t)v;
             S.tb.Tt[o + x * n + i] = (int8_t)v;
+        }
+        for (int e = tid; e < n * n / 4; e += NTHREADS) {
+            const int q4 = e >> l2, j = e & (n - 1);
+            unsigned qr = 0, qc = 0;
+            for (int b = 0; b < 4; b++) {
+                qr |= (unsigned)(uint8_t)(int8_t)dct(j, 4 * q4 + b, n) << (8 * b);
+                qc |= (unsigned)(uint8_t)(int8_t)dct(4 * q4 + b, j, n) << (8 * b);
+            }
+            S.tb.Qr[o / 4 + e] = (int32_t)qr;
+            S.tb.Qc[o / 4 + e] = (int32_t)qc;
         }
     }
     // scan tables: sub-block order and in-sub-block order are both up-right diagonal scans (ctu.rs:53-77)
@@ -1083,15 +1099,22 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
         for (int i = lane; i < nn; i += 32) ws.A[i] = in[i];
         __syncwarp();
         if (P.op == 1) {
-            mm_rows(S.tb.Tt + to, ws.A, ws.B, n, l2, 1 << (l2 - 2), l2 - 1, false, lane);
+            mm_rows_q<true>(S.tb.Qr + to / 4, ws.A, ws.B, n, l2, 1 << (l2 - 2), l2 - 1, lane);
             __syncwarp();
-            mm_cols(S.tb.T + to, ws.B, ws.A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
+            mm_cols_q(S.tb.T + to, reinterpret_cast<const int32_t *>(ws.B), ws.A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
             __syncwarp();
             for (int i = lane; i < nn; i += 32) out[i] = ws.A[i];
         } else if (P.op == 2) {
-            mm_cols(S.tb.Tt + to, ws.A, ws.B, n, l2, 64, 7, true, lane);  // Tt rows are T columns: V[y][x] = sum_i T[i][y] D[i][x]
+            for (int o = lane; o < nn / 2; o += 32) {  // pair-packed layout of the column pass
+                const int ip = o >> l2, x = o & (n - 1);
+                reinterpret_cast<int32_t *>(ws.B)[o] = ((int)ws.A[(2 * ip) * n + x] & 0xffff) | ((int)ws.A[(2 * ip + 1) * n + x] << 16);
+            }
             __syncwarp();
-            mm_rows(S.tb.T + to, ws.B, ws.A, n, l2, 2048, 12, false, lane);  // R[y][x] = sum_i T[i][x] V[y][i]
+            mm_cols_q(S.tb.Tt + to, reinterpret_cast<const int32_t *>(ws.B), ws.A, n, l2, 64, 7, true, lane);  // V[y][x] = sum_i T[i][y] D[i][x]
+            __syncwarp();
+            for (int i = lane; i < nn; i += 32) ws.B[i] = ws.A[i];
+            __syncwarp();
+            mm_rows_q<false>(S.tb.Qc + to / 4, ws.B, ws.A, n, l2, 2048, 12, lane);  // R[y][x] = sum_i T[i][x] V[y][i]
             __syncwarp();
             for (int i = lane; i < nn; i += 32) out[i] = ws.A[i];
         } else if (P.op == 3) {

@@ -72,6 +72,8 @@ constexpr int RC_STRIDE = 36, RC_X0 = 4, RC_Y0 = 1, RC_ROWS = 17;  // chroma win
 struct Tables {
     int8_t T[TAB_TOTAL];       // DCT matrix per size, row-major  T[i*n + x]
     int8_t Tt[TAB_TOTAL];      // transposed                      Tt[x*n + i]
+    int32_t Qr[TAB_TOTAL / 4]; // packed for the row passes: Qr[x4*n + i] = bytes T[i][4*x4 + 0..3]   (forward horizontal pass)
+    int32_t Qc[TAB_TOTAL / 4]; //                            Qc[i4*n + x] = bytes T[4*i4 + 0..3][x]   (inverse horizontal pass)
     uint16_t scan[TAB_TOTAL];  // forward scan index k (sub-block diagonal, then 4x4 diagonal; ctu.rs:14-81) -> raster offset
     int32_t ldq[64];
     int32_t lv[64];
@@ -756,36 +758,59 @@ __device__ __noinline__ void dir_search_part(const Ctx S, const Node nd, int par
 // ---------------------------------------------------------------------------------------------------------------
 // transforms (transformer.rs:2040-2378 forward, 2380-2737 inverse), one warp per TB, direct matrix multiply
 // ---------------------------------------------------------------------------------------------------------------
-// out[y][i] = (sum_x T[i][x] * in[y][x] + rnd) >> sh              (rows; lanes over i, Tt makes the T read conflict-free)
-__device__ __noinline__ void mm_rows(const int8_t *Tt, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
-    WB_SHARED_PTR(Tt); WB_SHARED_PTR(in); WB_SHARED_PTR(out);
-    const int nn = n * n;
+// Both passes multiply 16-bit samples by 8-bit matrix entries and run on the packed dot-product instruction (dp2a: two
+// 16x8-bit products per instruction, exact 32-bit accumulation): every item produces two outputs, loads four samples and
+// four coefficients per 32/64-bit shared-memory access, and so spends about one instruction per multiply-add.
+//
+// Row pass: out[y][i] = (sum_x M[x][i] * in[y][x] + rnd) >> sh for the row pair (2yp, 2yp+1); Q[x4*n + i] = bytes M[4*x4+0..3][i].
+// PACK: the two results are stored as one word P[yp*n + i] = (row 2yp | row 2yp+1 << 16), the layout the column pass reads.
+template <bool PACK>
+__device__ __noinline__ void mm_rows_q(const int32_t *Q, const int16_t *in, void *out, int n, int l2, int rnd, int sh, int lane) {
+    WB_SHARED_PTR(Q); WB_SHARED_PTR(in); WB_SHARED_PTR(out);
+    const int items = (n >> 1) << l2, nq = n >> 2;
 #pragma unroll 1
-    for (int o = lane; o < nn; o += 32) {
-        int y = o >> l2, i = o & (n - 1);
-        const int16_t *row = in + y * n;
-        int s = 0;
-#pragma unroll 4
-        for (int x = 0; x < n; x++) s += (int)Tt[x * n + i] * (int)row[x];
-        s = (s + rnd) >> sh;
-        if (clamp16) s = min(32767, max(-32768, s));
-        out[o] = (int16_t)s;
+    for (int o = lane; o < items; o += 32) {
+        const int yp = o >> l2, i = o & (n - 1);
+        const int2 *r0 = reinterpret_cast<const int2 *>(in + (2 * yp) * n), *r1 = reinterpret_cast<const int2 *>(in + (2 * yp + 1) * n);
+        const int32_t *q = Q + i;
+        int s0 = 0, s1 = 0;
+#pragma unroll 2
+        for (int x4 = 0; x4 < nq; x4++) {
+            const int w = q[x4 * n];
+            const int2 a = r0[x4], b = r1[x4];
+            s0 = __dp2a_lo(a.x, w, s0); s0 = __dp2a_hi(a.y, w, s0);
+            s1 = __dp2a_lo(b.x, w, s1); s1 = __dp2a_hi(b.y, w, s1);
+        }
+        s0 = (s0 + rnd) >> sh; s1 = (s1 + rnd) >> sh;
+        if (PACK) reinterpret_cast<int32_t *>(out)[yp * n + i] = (s0 & 0xffff) | (s1 << 16);
+        else {
+            reinterpret_cast<int16_t *>(out)[(2 * yp) * n + i] = (int16_t)s0;
+            reinterpret_cast<int16_t *>(out)[(2 * yp + 1) * n + i] = (int16_t)s1;
+        }
     }
 }
-// out[i][x] = (sum_y T[i][y] * in[y][x] + rnd) >> sh              (columns; lanes over x)
-__device__ __noinline__ void mm_cols(const int8_t *T, const int16_t *in, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
-    WB_SHARED_PTR(T); WB_SHARED_PTR(in); WB_SHARED_PTR(out);
-    const int nn = n * n;
+// Column pass: out[i][x] = (sum_y M[i][y] * in[y][x] + rnd) >> sh for the output row pair (2ip, 2ip+1); M row-major int8,
+// in pair-packed P[(y/2)*n + x] = (in[y][x] | in[y+1][x] << 16).
+__device__ __noinline__ void mm_cols_q(const int8_t *M, const int32_t *P, int16_t *out, int n, int l2, int rnd, int sh, bool clamp16, int lane) {
+    WB_SHARED_PTR(M); WB_SHARED_PTR(P); WB_SHARED_PTR(out);
+    const int items = (n >> 1) << l2, nq = n >> 2;
 #pragma unroll 1
-    for (int o = lane; o < nn; o += 32) {
-        int i = o >> l2, x = o & (n - 1);
-        const int8_t *trow = T + i * n;
-        int s = 0;
-#pragma unroll 4
-        for (int y = 0; y < n; y++) s += (int)trow[y] * (int)in[y * n + x];
-        s = (s + rnd) >> sh;
-        if (clamp16) s = min(32767, max(-32768, s));
-        out[o] = (int16_t)s;
+    for (int o = lane; o < items; o += 32) {
+        const int ip = o >> l2, x = o & (n - 1);
+        const int32_t *m0 = reinterpret_cast<const int32_t *>(M + (2 * ip) * n), *m1 = reinterpret_cast<const int32_t *>(M + (2 * ip + 1) * n);
+        const int32_t *pp = P + x;
+        int s0 = 0, s1 = 0;
+#pragma unroll 2
+        for (int y4 = 0; y4 < nq; y4++) {
+            const int w0 = m0[y4], w1 = m1[y4];
+            const int p0 = pp[(2 * y4) * n], p1 = pp[(2 * y4 + 1) * n];
+            s0 = __dp2a_lo(p0, w0, s0); s0 = __dp2a_hi(p1, w0, s0);
+            s1 = __dp2a_lo(p0, w1, s1); s1 = __dp2a_hi(p1, w1, s1);
+        }
+        s0 = (s0 + rnd) >> sh; s1 = (s1 + rnd) >> sh;
+        if (clamp16) { s0 = min(32767, max(-32768, s0)); s1 = min(32767, max(-32768, s1)); }
+        out[(2 * ip) * n + x] = (int16_t)s0;
+        out[(2 * ip + 1) * n + x] = (int16_t)s1;
     }
 }
 
@@ -1183,9 +1208,9 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     bool anylev = false;
     int rate = 0;
     if (anyres) {
-        mm_rows(S.tb->Tt + to, A, B, n, l2, 1 << (l2 - 2), l2 - 1, false, lane);
+        mm_rows_q<true>(S.tb->Qr + to / 4, A, B, n, l2, 1 << (l2 - 2), l2 - 1, lane);
         __syncwarp();
-        mm_cols(S.tb->T + to, B, A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
+        mm_cols_q(S.tb->T + to, reinterpret_cast<const int32_t *>(B), A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
         __syncwarp();
         trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
     } else {
@@ -1205,13 +1230,19 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         for (int i = lane; i < nn; i += 32) S.c->slotLv[slot][soff + i] = B[i];
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
-        for (int i = lane; i < nn; i += 32) A[i] = (int16_t)min(32767, max(-32768, ((int)B[i] * ls + off) >> sh));  // quantizer.rs:1074-1075
+        // dequantise (quantizer.rs:1074-1075) into the pair-packed layout of the column pass
+        for (int o = lane; o < nn / 2; o += 32) {
+            const int ip = o >> l2, x = o & (n - 1);
+            const int d0 = min(32767, max(-32768, ((int)B[(2 * ip) * n + x] * ls + off) >> sh));
+            const int d1 = min(32767, max(-32768, ((int)B[(2 * ip + 1) * n + x] * ls + off) >> sh));
+            reinterpret_cast<int32_t *>(A)[o] = (d0 & 0xffff) | (d1 << 16);
+        }
         __syncwarp();
         // vertical: V[y][x] = clamp16((sum_i T[i][y] * D[i][x] + 64) >> 7)   (Tt's rows are T's columns)
-        mm_cols(S.tb->Tt + to, A, B, n, l2, 64, 7, true, lane);
+        mm_cols_q(S.tb->Tt + to, reinterpret_cast<const int32_t *>(A), B, n, l2, 64, 7, true, lane);
         __syncwarp();
         // horizontal: R[y][x] = (sum_i T[i][x] * V[y][i] + 2048) >> 12
-        mm_rows(S.tb->T + to, B, A, n, l2, 2048, 12, false, lane);
+        mm_rows_q<false>(S.tb->Qc + to / 4, B, A, n, l2, 2048, 12, lane);
         __syncwarp();
     }
     unsigned ssd = 0;
