@@ -98,7 +98,8 @@ __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, in
 // ticket per phase (S.ticket[phase parity], reset two phases later).  32x32 luma pipelines need the large scratch buffers
 // that only the first NBIG warps own: those tasks lead the list and the first `nst` of them are taken statically by warps
 // 0..nst-1 as their first task; everything else is dynamic.
-__device__ __forceinline__ int next_task(Shared &S, int &slot, int nst, int prev, int warp, int lane) {
+__device__ __forceinline__ int next_task(Shared &S, int &slot, int nst, int ntot, int prev, int warp, int lane) {
+    if (ntot <= NW) return prev < 0 ? warp : ntot;  // at most one task per warp: no ticket needed
     if (prev < 0 && warp < nst) return warp;
     int t = 0;
     if (lane == 0) t = atomicAdd(&S.ticket[slot], 1);
@@ -114,7 +115,7 @@ __device__ __forceinline__ Node unpack_node(unsigned p) {
     return n;
 }
 #define WB_FOR_TASKS(ntask)                                                                            \
-    for (int tt = next_task(S, S_slot, nst, -1, warp, lane); tt < (ntask) * KC; tt = next_task(S, S_slot, nst, tt, warp, lane)) \
+    for (int tt = next_task(S, S_slot, nst, (ntask) * KC, -1, warp, lane); tt < (ntask) * KC; tt = next_task(S, S_slot, nst, (ntask) * KC, tt, warp, lane)) \
         if (S.c[tt % KC].active)
 // called by every thread between two phases (after the barrier that ends a phase): switch to the other ticket and
 // clear the one used two phases ago

@@ -1443,24 +1443,31 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
     __syncwarp(hm);
 }
 
-// SAD-driven choice among the three CCLM modes for 4x4 chroma blocks (block_splitter.rs:1041-1054 / 812-850), one warp:
-// lanes 0-15 predict Cb, 16-31 Cr; order LT, T, L with the reference's tie rules (LT unless strictly worse, then T).
+// SAD-driven choice among the three CCLM modes for 4x4 chroma blocks (block_splitter.rs:1041-1054 / 812-850), one warp.
+// The (a, k, b) derivation is scalar work, so the six (mode, component) combinations are derived at once, one per lane
+// (lanes 0-5; the other lanes repeat them), and handed to the sample lanes (0-15 Cb, 16-31 Cr) by shuffles.
+// Order LT, T, L with the reference's tie rules (LT unless strictly worse, then T).
 __device__ __noinline__ int cclm_search4(const Ctx S, const CtuGeom g, const Node nd, int lane) {
     WB_SHARED_CTX(S);
-    const int c = 1 + (lane >> 4), gl = lane & 15, bx = nd.x >> 1, by = nd.y >> 1;
-    const int org = org_at(S, c, bx + (gl & 3), by + (gl >> 2)), ds = S.c->pds[gl];
-    unsigned s_lt = 0, s_t = 0, s_l = 0;
-#pragma unroll 1
-    for (int mi = 0; mi < 3; mi++) {
-        const int mode = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-        PredCtx pc;
-        cclm_params(S, g, nd, c, mode, pc);
-        const int p = pc.cclm128 ? 128 : clip8(((ds * pc.a) >> pc.k) + pc.b);
-        const unsigned s = warp_sumu((unsigned)abs(p - org));
-        if (mi == 0) s_lt = s; else if (mi == 1) s_t = s; else s_l = s;
+    const int combo = min(lane & 7, 5);  // mode index * 2 + component - 1
+    PredCtx pc;
+    {
+        const int mi = combo >> 1;
+        cclm_params(S, g, nd, 1 + (combo & 1), mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM), pc);
     }
-    if (s_lt <= s_t && s_lt <= s_l) return MODE_LT_CCLM;
-    return s_t <= s_l ? MODE_T_CCLM : MODE_L_CCLM;
+    const int pa = pc.cclm128 ? 0 : pc.a, pk = pc.cclm128 ? 0 : pc.k, pb = pc.cclm128 ? 128 : pc.b;  // a = 0: the prediction is b
+    const int cidx = lane >> 4, gl = lane & 15, bx = nd.x >> 1, by = nd.y >> 1;
+    const int org = org_at(S, 1 + cidx, bx + (gl & 3), by + (gl >> 2)), ds = S.c->pds[gl];
+    unsigned s[3];
+#pragma unroll
+    for (int mi = 0; mi < 3; mi++) {
+        const int src = 2 * mi + cidx;
+        const int a = __shfl_sync(0xffffffffu, pa, src), k = __shfl_sync(0xffffffffu, pk, src), b = __shfl_sync(0xffffffffu, pb, src);
+        const int p = clip8(((ds * a) >> k) + b);
+        s[mi] = warp_sumu((unsigned)abs(p - org));
+    }
+    if (s[0] <= s[1] && s[0] <= s[2]) return MODE_LT_CCLM;
+    return s[1] <= s[2] ? MODE_T_CCLM : MODE_L_CCLM;
 }
 
 // The winner of a node up to 16x16 was already evaluated with unchanged inputs (the reference repeats that evaluation,
