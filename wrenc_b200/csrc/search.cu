@@ -82,14 +82,14 @@ __device__ __forceinline__ long long luma_hdr(const Ctx S, const DevTables *tab,
 __device__ __forceinline__ void fill_lm(const Ctx S, const Node nd, int mode, int lane) {
     int cells = nd.w >> 2;
     for (int i = lane; i < cells * cells; i += 32) {
-        int yy = i / cells, xx = i - yy * cells;
+        int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         S.c->lm[((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx] = (uint8_t)mode;
     }
 }
 __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, int lane) {
     int cells = nd.w >> 3;
     for (int i = lane; i < cells * cells; i += 32) {
-        int yy = i / cells, xx = i - yy * cells;
+        int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         S.c->cm[((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx] = (uint8_t)mode;
     }
 }
@@ -669,14 +669,14 @@ __device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int ti
     WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
-        int y = i / w, x = i - y * w;
+        int y = i >> ilog2i(w), x = i & (w - 1);
         S.c->svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
         S.c->svLvY[oy + i] = S.c->lvY[(nd.y + y) * 32 + nd.x + x];
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
     for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
-        int c = i >= cw * cw, j = i - c * cw * cw;
-        int y = j / cw, x = j - y * cw;
+        int c = i >= cw * cw, j = i & (cw * cw - 1);
+        int y = j >> ilog2i(cw), x = j & (cw - 1);
         S.c->svRecC[c][oc + j] = RC(S, 1 + c, bx + x, by + y);
         S.c->svLvC[c][oc + j] = S.c->lvC[c][(by + y) * 16 + bx + x];
     }
@@ -687,26 +687,26 @@ __device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int
     WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     for (int i = tid; i < w * w; i += NTHREADS) {
-        int y = i / w, x = i - y * w;
+        int y = i >> ilog2i(w), x = i & (w - 1);
         RY(S, nd.x + x, nd.y + y) = S.c->svRecY[oy + i];
         S.c->lvY[(nd.y + y) * 32 + nd.x + x] = S.c->svLvY[oy + i];
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
     for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
-        int c = i >= cw * cw, j = i - c * cw * cw;
-        int y = j / cw, x = j - y * cw;
+        int c = i >= cw * cw, j = i & (cw * cw - 1);
+        int y = j >> ilog2i(cw), x = j & (cw - 1);
         RC(S, 1 + c, bx + x, by + y) = S.c->svRecC[c][oc + j];
         S.c->lvC[c][(by + y) * 16 + bx + x] = S.c->svLvC[c][oc + j];
     }
     const int cells = w >> 2;
     for (int i = tid; i < cells * cells; i += NTHREADS) {
-        int yy = i / cells, xx = i - yy * cells;
+        int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         int idx = ((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx;
         S.c->lm[idx] = S.c->svLm[d][idx];
     }
     const int cc = w >> 3;
     for (int i = tid; i < cc * cc; i += NTHREADS) {
-        int yy = i / cc, xx = i - yy * cc;
+        int yy = i >> ilog2i(cc), xx = i & (cc - 1);
         int idx = ((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx;
         S.c->cm[idx] = S.c->svCm[d][idx];
     }

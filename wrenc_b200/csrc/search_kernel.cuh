@@ -388,7 +388,7 @@ __device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom g, const
     bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
     int tw = nd.w >> 1;
     for (int i = lane; i < tw * tw; i += 32) {
-        int y = i / tw, x = i - y * tw;
+        int y = i >> ilog2i(tw), x = i & (tw - 1);
         S.c->pds[i] = (uint8_t)cclm_ds6(S, nd.x, nd.y, avail_l, 2 * y, 2 * x);
     }
 }
@@ -985,7 +985,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         Lf0 = Cs[0]; Lf1 = Cs[1]; Lf2 = Cs[2]; Lf3 = Cs[3];
     }
     const bool tiny = nn == 16;  // 4x4 TBs (the most numerous): one position per lane, plain sequential pass over 15 steps
-    const int CS = tiny ? 1 : (nn >= 256 ? 16 : 4), nch = nn / CS, rounds = (nch + 31) >> 5;
+    const int CS = tiny ? 1 : (nn >= 1024 ? 16 : (nn >= 256 ? 8 : 4)), nch = nn / CS, rounds = (nch + 31) >> 5;
     int carry0 = 0, carry1 = 0, carry2 = 0, carry3 = 0;
     unsigned cmaps = 0;
     if (tiny) {
