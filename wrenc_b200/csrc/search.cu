@@ -344,7 +344,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate);
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate, use_slots ? 5 : -1);
             if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
         }
     __syncthreads();
@@ -378,8 +378,11 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             Ctx V{&S.tb, &S.c[k]};
             const Node nd = unpack_node(V.c->node);
             if (V.c->cclm_wins) {
-                unsigned ssd; int rate;
-                full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+                if (use_slots) commit_slot(V, nd, 1 + t, 5, lane);  // evaluated in phase 7 with unchanged inputs
+                else {
+                    unsigned ssd; int rate;
+                    full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
+                }
             }
             if (t == 0) fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
         }
@@ -540,7 +543,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
         const int k = tt % KC, h = lane >> 4;
         Ctx V{&S.tb, &S.c[k]};
         unsigned ssd; int rate;
-        full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, -1, ws, lane, ssd, rate);
+        full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, 5, ws, lane, ssd, rate);
         if ((lane & 15) == 0) { V.c->r_ssd[8 + h] = ssd; V.c->r_rate[8 + h] = rate; }
     }
     __syncthreads();
@@ -567,9 +570,9 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
             C.leaf_cost = cclm_wins ? rd_cost(ssdY + ssdCC, rateY + rateCC + luma_hdr(V, tab, nd, mode, ck), tab->lambda_rd)
                                     : rd_cost(ssdY + ssdDM, rateY + rateDM + luma_hdr(V, tab, nd, mode, 0), tab->lambda_rd);
         }
-        if (cclm_wins) {
-            unsigned ssd; int rate;
-            full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), cclm_mode, true, -1, ws, lane, ssd, rate);
+        if (cclm_wins) {  // evaluated in phase E with unchanged inputs: copy it out of its slot
+            commit_slot(V, nd, 1, 5, lane);
+            commit_slot(V, nd, 2, 5, lane);
         }
         fill_cm(V, nd, cclm_wins ? cclm_mode : mode, lane);
     }
@@ -622,7 +625,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         const int k = tt % KC, h = lane >> 4;
         Ctx V{&S.tb, &S.c[k]};
         unsigned ssd; int rate;
-        full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, -1, ws, lane, ssd, rate);
+        full_pair4(V, tab, V.c->g, unpack_node(V.c->node), 1 + h, V.c->cclm_mode, false, 5, ws, lane, ssd, rate);
         if ((lane & 15) == 0) { V.c->r_ssd[8 + h] = ssd; V.c->r_rate[8 + h] = rate; }
     }
     __syncthreads();
@@ -647,9 +650,9 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
             C.leaf_cost = mn;
             C.split[2] = __fadd_rn(C.split[2], mn);
         }
-        if (cclm_wins) {
-            unsigned ssd; int rate;
-            full_pair4(V, tab, V.c->g, nd, 1 + (lane >> 4), cclm_mode, true, -1, ws, lane, ssd, rate);
+        if (cclm_wins) {  // evaluated in phase C with unchanged inputs (CCLM reads the luma and the neighbours outside the block)
+            commit_slot(V, nd, 1, 5, lane);
+            commit_slot(V, nd, 2, 5, lane);
         }
         fill_cm(V, nd, cclm_wins ? cclm_mode : dm, lane);
     }

@@ -138,9 +138,9 @@ struct alignas(16) CtuCtx {
     // results of the planar / DC evaluations (phase 1) and of the winner (phase 5), per component
     unsigned pd_ssd[2][3], fin_ssd[3];
     int pd_rate[2][3], fin_rate[3];
-    // candidate slots of nodes up to 16x16: reconstruction and levels of planar, DC, dir, dir-1, dir+1 (Y at 0, Cb at 256, Cr at 320)
-    uint8_t slotRec[5][384];
-    int16_t slotLv[5][384];
+    // candidate slots of nodes up to 16x16: reconstruction and levels of planar, DC, dir, dir-1, dir+1, CCLM (Y at 0, Cb at 256, Cr at 320)
+    uint8_t slotRec[6][384];  // slot 5: the CCLM evaluation (chroma part only)
+    int16_t slotLv[6][384];
 };
 
 struct Shared {
@@ -1167,8 +1167,9 @@ __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, con
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(refx);
     if (pred_out) WB_SHARED_PTR(pred_out);
-    PredCtx pc;
-    pred_setup(S, g, nd, c, mode, refx, lane, pc);
+    PredCtx pc_mem;  // cclm_params takes its address
+    pred_setup(S, g, nd, c, mode, refx, lane, pc_mem);
+    const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
 #pragma unroll 1
