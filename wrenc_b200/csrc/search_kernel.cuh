@@ -1025,12 +1025,19 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         for (int s = 0; s < 4; s++)
 #pragma unroll
             for (int t = 0; t < 4; t++) M[s][t] = s == t ? 0 : TR_INF;
+        bool sep_head = false;
         if (vc) {
 #pragma unroll 1
             for (int i = 0; i < CS; i++) {
                 const int k = k0 + i;
                 const LC l = local_costs(S, tab, coef[scan[k]], Wd[k], k, kstar, ls, sh, off, ldq1);
-                if (i == 0) { head = l; continue; }
+                if (i == 0) {
+                    head = l;
+                    // the chunk's first step stays separate only where it is not (min,+)-linear: the DC leaf and the
+                    // sub-block starts that carry the post-comparison adjustment; everywhere else it is folded into M
+                    sep_head = k == 0 || (l.pk & 4u);
+                    if (sep_head) continue;
+                }
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     int X = (l.pk & 1) ? M[2][t] : M[0][t], Y = (l.pk & 1) ? M[0][t] : M[2][t];
@@ -1044,6 +1051,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         // ---- C: apply head + matrix chunk by chunk; lane j owns chunk r*32 + j
         int O0 = 0, O1 = 0, O2 = 0, O3 = 0, my0 = 0, my1 = 0, my2 = 0, my3 = 0;
         const int cnt = min(32, nch - r * 32);
+        const unsigned sepmask = __ballot_sync(0xffffffffu, sep_head);
 #pragma unroll 1
         for (int j = 0; j < cnt; j++) {
             int I0, I1, I2, I3;
@@ -1053,8 +1061,10 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
                 I2 = __shfl_sync(0xffffffffu, O2, j - 1); I3 = __shfl_sync(0xffffffffu, O3, j - 1);
             }
             int H0 = I0, H1 = I1, H2 = I2, H3 = I3;
-            if (r == 0 && j == 0) { H0 = Lf0; H1 = Lf1; H2 = Lf2; H3 = Lf3; }
-            else vstep(head, ldq1, H0, H1, H2, H3);
+            if ((sepmask >> j) & 1u) {  // uniform: chunk j has a separate head (every lane applies its own, only lane j's result is used)
+                if (r == 0 && j == 0) { H0 = Lf0; H1 = Lf1; H2 = Lf2; H3 = Lf3; }
+                else vstep(head, ldq1, H0, H1, H2, H3);
+            }
             int T0 = min(min(M[0][0] + H0, M[0][1] + H1), min(M[0][2] + H2, M[0][3] + H3));
             int T1 = min(min(M[1][0] + H0, M[1][1] + H1), min(M[1][2] + H2, M[1][3] + H3));
             int T2 = min(min(M[2][0] + H0, M[2][1] + H1), min(M[2][2] + H2, M[2][3] + H3));
