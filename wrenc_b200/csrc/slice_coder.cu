@@ -463,7 +463,7 @@ struct BitOut {
     __device__ __forceinline__ void bit(int b) {
         acc = (acc << 1) | (unsigned)(b & 1);
         if (++nb == 8) {
-            if (n < cap) p[n] = (uint8_t)acc;
+            if (p && n < cap) p[n] = (uint8_t)acc;
             n++;
             nb = 0;
             acc = 0;
@@ -491,13 +491,17 @@ struct Engine {
     }
 };
 
+// One WARP per picture.  The coder itself is sequential, so every lane runs it redundantly on identical state (context
+// states in shared memory, engine state in registers; lane 0 alone stores the output bytes); what the warp buys is the
+// memory side: the bin strings are fetched 32 entries at a time with one coalesced load, double-buffered, and handed to the
+// coder by shuffles, instead of one dependent 2-byte global load per bin.
 extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxParams Q) {
-    const int pic = blockIdx.x;
-    if (threadIdx.x != 0 || pic >= Q.n_pics) return;
+    const int pic = blockIdx.x, lane = threadIdx.x;
+    if (pic >= Q.n_pics) return;
     const int nctu = Q.Wc * Q.Hc;
-    uint16_t p0[CTX_TOTAL], p1[CTX_TOTAL];
-    uint8_t sh0[CTX_TOTAL], sh1[CTX_TOTAL];
-    for (int i = 0; i < CTX_TOTAL; i++) {  // init_ctx_table (bool_coder.rs:1073-1093)
+    __shared__ uint16_t p0[CTX_TOTAL], p1[CTX_TOTAL];
+    __shared__ uint8_t sh0[CTX_TOTAL], sh1[CTX_TOTAL];
+    for (int i = lane; i < CTX_TOTAL; i += 32) {  // init_ctx_table (bool_coder.rs:1073-1093)
         const int iv = kCabacInitValue[i];
         const int m = (iv >> 3) - 4, nn = (iv & 7) * 18 + 1;
         const int pre = min(127, max(1, ((m * (min(63, max(0, Q.qp)) - 16)) >> 1) + nn));
@@ -507,17 +511,26 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
         sh0[i] = (uint8_t)((si >> 2) + 2);
         sh1[i] = (uint8_t)((si & 3) + 3 + (si >> 2) + 2);
     }
+    __syncwarp();
     Engine E;
     E.low = 0; E.range = 510; E.outstanding = 0; E.first = true;
-    E.out.p = Q.out + (size_t)pic * Q.out_cap;
+    E.out.p = lane == 0 ? Q.out + (size_t)pic * Q.out_cap : nullptr;  // lanes other than 0 only count
     E.out.n = 0; E.out.cap = Q.out_cap; E.out.acc = 0; E.out.nb = 0;
     int overflow = 0;
-    for (int c = 0; c < nctu; c++) {
-        const size_t gid = (size_t)pic * nctu + c;
-        const uint16_t *b = Q.bins + Q.bin_offset[gid];
-        const int lim = Q.bin_count[gid];
-        for (int i = 0; i < lim; i++) {
-            const unsigned e = b[i];
+    // the CTUs' bin strings lie back to back in the arena (exclusive scan of the counts), in raster order
+    const size_t g0 = (size_t)pic * nctu;
+    const unsigned long long beg = Q.bin_offset[g0];
+    const unsigned long long end = Q.bin_offset[g0 + nctu - 1] + (unsigned long long)Q.bin_count[g0 + nctu - 1];
+    const uint16_t *b = Q.bins + beg;
+    const long long total = (long long)(end - beg);
+    unsigned nxt = lane < total ? b[lane] : 0u;
+    for (long long base = 0; base < total; base += 32) {
+        const unsigned cur = nxt;
+        const long long pf = base + 32 + lane;
+        nxt = pf < total ? b[pf] : 0u;  // prefetch the next 32 entries while this batch is coded
+        const int cnt = (int)min(32ll, total - base);
+        for (int i = 0; i < cnt; i++) {
+            const unsigned e = __shfl_sync(0xffffffffu, cur, i);
             const int bin = (e >> 9) & 1;
             if (e & 1024u) {  // bypass (bool_coder.rs:202-216)
                 E.low <<= 1;
@@ -527,14 +540,17 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
                 else { E.low -= 512; E.outstanding++; }
             } else {  // context coded (bool_coder.rs:254-296)
                 const int ci = e & 511;
-                const unsigned ps = (unsigned)p1[ci] + 16u * p0[ci];
+                const unsigned q0 = p0[ci], q1 = p1[ci], s0 = sh0[ci], s1 = sh1[ci];
+                const unsigned ps = q1 + 16u * q0;
                 const unsigned mps = ps >> 14;
                 const unsigned lps = ((((E.range >> 5) * ((mps ? 32767u - ps : ps) >> 9)) >> 1) + 4);
                 if ((unsigned)bin == mps) E.range -= lps;
                 else { E.low += E.range - lps; E.range = lps; }
                 E.renorm();
-                p0[ci] = (uint16_t)(p0[ci] - (p0[ci] >> sh0[ci]) + ((1023 * bin) >> sh0[ci]));
-                p1[ci] = (uint16_t)(p1[ci] - (p1[ci] >> sh1[ci]) + ((16383 * bin) >> sh1[ci]));
+                __syncwarp();  // every lane has read the old state before anyone stores the (identical) new one
+                p0[ci] = (uint16_t)(q0 - (q0 >> s0) + ((1023 * bin) >> s0));
+                p1[ci] = (uint16_t)(q1 - (q1 >> s1) + ((16383 * bin) >> s1));
+                __syncwarp();
             }
         }
     }
@@ -554,7 +570,7 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
     }
     while (E.out.nb != 0) E.out.bit(0);
     if (E.out.n > E.out.cap) overflow = 1;
-    Q.out_len[pic] = overflow ? -1 : (int)E.out.n;
+    if (lane == 0) Q.out_len[pic] = overflow ? -1 : (int)E.out.n;
 }
 
 cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream) {  // Q.bins == nullptr: counting pass
