@@ -331,8 +331,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames", type=int, default=240, help="frames per GPU per step")
     ap.add_argument("--unique", type=int, default=12, help="unique synthetic frames generated on the host (repeated on device)")
-    ap.add_argument("--e2e-frames", type=int, default=120)
-    ap.add_argument("--e2e-batch", type=int, default=120)
+    ap.add_argument("--e2e-frames", type=int, default=240)
+    ap.add_argument("--e2e-batch", type=int, default=240)
     ap.add_argument("--e2e-steps", type=int, default=1)
     ap.add_argument("--cpu-rows", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")

@@ -27,6 +27,7 @@ struct wrenc_b200 {
     // workspace shared by both entry points (sized for ws_pics pictures)
     int ws_pics = 0;
     uint8_t *d_mode_map = nullptr;
+    uint8_t *d_root_slots = nullptr;  // per CTA x lock-step CTU: candidate slots of the 32x32 root CU
     int *d_done = nullptr;
     uint32_t *d_items = nullptr;
     size_t items_cap = 0;
@@ -79,6 +80,7 @@ static int ensure_workspace(wrenc_b200 *h, int n_pics) {
     CK(cudaMalloc(&h->d_done, nctu * sizeof(int)));
     CK(cudaMemsetAsync(h->d_done, 0, nctu * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_mode_map, 0, (size_t)(h->W / 4) * (h->H / 4) * n_pics, h->stream));
+    if (!h->d_root_slots) CK(cudaMalloc(&h->d_root_slots, (size_t)h->grid * search_ctus_per_cta() * ROOT_SLOT_BYTES));
     h->ws_pics = n_pics;
     h->items_for = -1;
     h->epoch = 0;
@@ -146,6 +148,7 @@ static int enqueue_search(wrenc_b200 *h, int n_pics, const uint8_t *d_yuv, uint8
     P.epoch = ++h->epoch;
     P.orig = d_yuv; P.rec = d_rec; P.lev = d_lev; P.mode_map = h->d_mode_map; P.records = d_records;
     P.done = h->d_done; P.items = h->d_items; P.counter = h->d_counter; P.tab = h->d_tab;
+    P.root_slots = h->d_root_slots;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     int grid = std::min(h->grid, h->n_items / search_ctus_per_cta());
     CK(launch_search(P, grid, st));
@@ -270,7 +273,7 @@ void wrenc_b200_destroy(wrenc_b200 *h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_tab); cudaFree(h->d_mode_map); cudaFree(h->d_done); cudaFree(h->d_items); cudaFree(h->d_counter);
+    cudaFree(h->d_tab); cudaFree(h->d_root_slots); cudaFree(h->d_mode_map); cudaFree(h->d_done); cudaFree(h->d_items); cudaFree(h->d_counter);
     cudaFree(h->d_orig); cudaFree(h->d_rec); cudaFree(h->d_lev); cudaFree(h->d_rec_ctu);
     cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_bin_total); cudaFree(h->d_out); cudaFree(h->d_out_len);
     cudaFreeHost(h->h_out); cudaFreeHost(h->h_out_len);

@@ -136,7 +136,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     constexpr int ncomp = 3;  // SINGLE_TREE 32x32 / 16x16 CUs (smaller CUs: small_eval)
     const bool is_root = id.depth == 0;
     int nst = 0;  // leading tasks that need the large scratch (32x32 luma pipelines of the root), see next_task
-    const bool use_slots = id.depth > 0;  // 16x16 CUs keep every full evaluation's outcome; the root re-evaluates its winner
+    const int sb = is_root ? 16 : 0;  // every full evaluation's outcome is kept in a slot: shared memory (16x16 CU) or global scratch (root)
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
     __syncthreads();
@@ -164,7 +164,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
                     if (t < 2) { mode = t; c = 0; }
                     else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
                     unsigned ssd; int rate;
-                    full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, use_slots ? mode : -1);
+                    full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, sb + mode);
                     if (lane == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
                 } else {
                     int u = t - nfull;
@@ -240,7 +240,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int dir = V.c->dir;
             int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, use_slots ? 2 + cand : -1);
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, sb + 2 + cand);
             if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
         }
     }
@@ -286,22 +286,19 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 7);
     // ---- phase 5: luma redo (commit) + chroma DM full evaluation (commit)
-    nst = is_root ? KC : 0;
+    nst = 0;
     WB_FOR_TASKS(ncomp) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = unpack_node(V.c->node);
-        if (use_slots) {  // the winner's luma and its same-mode (DM) chroma were evaluated in phase 1 or 4: copy them out
+        {   // the winner's luma and its same-mode (DM) chroma were evaluated in phase 1 or 4: copy them out of their slot
             const int md = V.c->mode, dc = V.c->dir_cand;
-            commit_slot(V, nd, t, md <= 1 ? md : 2 + dc, lane);
+            if (is_root) commit_root_slot(V, t, md <= 1 ? md : 2 + dc, lane);
+            else commit_slot(V, nd, t, md <= 1 ? md : 2 + dc, lane);
             if (lane == 0) {
                 if (md <= 1) { V.c->fin_ssd[t] = V.c->pd_ssd[md][t]; V.c->fin_rate[t] = V.c->pd_rate[md][t]; }
                 else { const int r = t == 0 ? dc : 3 + 2 * dc + (t - 1); V.c->fin_ssd[t] = V.c->r_ssd[r]; V.c->fin_rate[t] = V.c->r_rate[r]; }
             }
-        } else {
-            unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, nd, t, V.c->mode, true, ws, lane, ssd, rate);
-            if (lane == 0) { V.c->fin_ssd[t] = ssd; V.c->fin_rate[t] = rate; }
         }
         if (t == 0) fill_lm(V, nd, V.c->mode, lane);
     }
@@ -344,7 +341,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate, use_slots ? 5 : -1);
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate, sb + 5);
             if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
         }
     __syncthreads();
@@ -377,12 +374,9 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
             const Node nd = unpack_node(V.c->node);
-            if (V.c->cclm_wins) {
-                if (use_slots) commit_slot(V, nd, 1 + t, 5, lane);  // evaluated in phase 7 with unchanged inputs
-                else {
-                    unsigned ssd; int rate;
-                    full_task(V, tab, V.c->g, nd, 1 + t, V.c->cclm_mode, true, ws, lane, ssd, rate);
-                }
+            if (V.c->cclm_wins) {  // evaluated in phase 7 with unchanged inputs
+                if (is_root) commit_root_slot(V, 1 + t, 5, lane);
+                else commit_slot(V, nd, 1 + t, 5, lane);
             }
             if (t == 0) fill_cm(V, nd, V.c->cclm_wins ? V.c->cclm_mode : V.c->mode, lane);
         }
@@ -936,6 +930,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
                 C.pic = it >> 16; C.cyi = (it >> 8) & 255; C.cxi = it & 255;
                 C.g.cx = C.cxi * 32; C.g.cy = C.cyi * 32; C.g.W = W; C.g.H = H;
                 C.mask = 0; C.root_mode = 0; C.dir_cnt = 0;
+                C.groot = P.root_slots + ((size_t)blockIdx.x * KC + tid) * ROOT_SLOT_BYTES;
                 int *done = P.done + (size_t)C.pic * Wc * P.Hc;
                 if (C.cxi > 0) while (ld_relaxed(&done[C.cyi * Wc + C.cxi - 1]) != P.epoch) __nanosleep(1000);
                 if (C.cyi > 0) {

@@ -133,6 +133,7 @@ struct alignas(16) CtuCtx {
     // leaf-evaluation state
     float cost_pl, cost_dc, cur_cost, dir_cost, min_cost, cost_dm;
     int cur, dir, mode, cclm_mode, v0, v1, cclm_wins, dir_cand;
+    uint8_t *groot;           // this CTU's root-CU slots in global memory (SearchParams::root_slots)
     unsigned dir_part[4];     // direction search of CUs up to 8x8: first minimum of each part of the coarse modes, and the arrival counter
     int dir_cnt;
     // results of the planar / DC evaluations (phase 1) and of the winner (phase 5), per component
@@ -162,6 +163,7 @@ struct Shared {
     int16_t refx[NW][100];
 };
 
+static_assert(offsetof(CtuCtx, lvY) % 8 == 0 && offsetof(CtuCtx, lvC) % 8 == 0 && sizeof(CtuCtx) % 8 == 0, "commit_root_slot stores the levels as 64-bit words");
 static_assert(offsetof(Shared, bigA) % 8 == 0 && offsetof(Shared, bigB) % 8 == 0 && offsetof(Shared, smA) % 8 == 0 && offsetof(Shared, smB) % 8 == 0 &&
                   offsetof(Tables, Tt) % 4 == 0,
               "full_pair4 reads these arrays as 32-bit words");
@@ -1236,8 +1238,16 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
             dst[(by + y) * stride + bx + x] = B[i];
         }
     }
-    const int soff = c == 0 ? 0 : (c == 1 ? 256 : 320);
-    if (slot >= 0)
+    // slot 0..5: shared-memory slots of CUs up to 16x16; slot 16..21: the root CU's slots in global memory
+    const bool gslot = slot >= 16;
+    const int soff = gslot ? (c == 0 ? 0 : (c == 1 ? 1024 : 1280)) : (c == 0 ? 0 : (c == 1 ? 256 : 320));
+    uint8_t *gRec = nullptr;
+    int16_t *gLv = nullptr;
+    if (gslot) {
+        gRec = S.c->groot + (slot - 16) * ROOT_SLOT_SAMPLES + soff;
+        gLv = reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + (slot - 16) * ROOT_SLOT_SAMPLES + soff;
+        for (int i = lane; i < nn; i += 32) gLv[i] = B[i];
+    } else if (slot >= 0)
         for (int i = lane; i < nn; i += 32) S.c->slotLv[slot][soff + i] = B[i];
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
@@ -1268,7 +1278,8 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
             if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
             else RC(S, c, bx + x, by + y) = (uint8_t)rec;
         }
-        if (slot >= 0) S.c->slotRec[slot][soff + i] = (uint8_t)rec;
+        if (gslot) gRec[i] = (uint8_t)rec;
+        else if (slot >= 0) S.c->slotRec[slot][soff + i] = (uint8_t)rec;
     }
     ssd_out = warp_sumu(ssd);
     rate_out = rate;
@@ -1495,6 +1506,30 @@ __device__ __noinline__ void commit_slot(const Ctx S, const Node nd, int c, int 
         const uint8_t r = S.c->slotRec[slot][soff + i];
         if (c == 0) RY(S, bx + x, by + y) = r;
         else RC(S, c, bx + x, by + y) = r;
+    }
+    __syncwarp();
+}
+
+// The same for the 32x32 root CU, whose slots live in global memory (written by other warps of this CTA before the last
+// block barrier; read around L1).
+__device__ __noinline__ void commit_root_slot(const Ctx S, int c, int slot, int lane) {
+    WB_SHARED_CTX(S);
+    const int n = c == 0 ? 32 : 16, l2 = c == 0 ? 5 : 4, nn = n * n;
+    const int soff = c == 0 ? 0 : (c == 1 ? 1024 : 1280);
+    const uint8_t *gRec = S.c->groot + slot * ROOT_SLOT_SAMPLES + soff;
+    const int16_t *gLv = reinterpret_cast<const int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + slot * ROOT_SLOT_SAMPLES + soff;
+    int16_t *dst = c == 0 ? S.c->lvY : S.c->lvC[c - 1];
+    for (int i = lane; i < nn / 4; i += 32) {  // 4 samples per lane and iteration
+        const unsigned r4 = __ldcg(reinterpret_cast<const unsigned *>(gRec) + i);
+        const uint2 l4 = __ldcg(reinterpret_cast<const uint2 *>(gLv) + i);
+        const int y = (4 * i) >> l2, x = (4 * i) & (n - 1);
+        *reinterpret_cast<uint2 *>(dst + y * n + x) = l4;  // the CTU level arrays have the block's own stride at the root
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint8_t r = (uint8_t)(r4 >> (8 * j));
+            if (c == 0) RY(S, x + j, y) = r;
+            else RC(S, c, x + j, y) = r;
+        }
     }
     __syncwarp();
 }
