@@ -80,7 +80,7 @@ static int ensure_workspace(wrenc_b200 *h, int n_pics) {
     CK(cudaMalloc(&h->d_done, nctu * sizeof(int)));
     CK(cudaMemsetAsync(h->d_done, 0, nctu * sizeof(int), h->stream));
     CK(cudaMemsetAsync(h->d_mode_map, 0, (size_t)(h->W / 4) * (h->H / 4) * n_pics, h->stream));
-    if (!h->d_root_slots) CK(cudaMalloc(&h->d_root_slots, (size_t)h->grid * search_ctus_per_cta() * ROOT_SLOT_BYTES));
+    if (!h->d_root_slots) CK(cudaMalloc(&h->d_root_slots, (size_t)h->grid * search_ctus_per_cta() * CTU_SCRATCH_BYTES));
     h->ws_pics = n_pics;
     h->items_for = -1;
     h->epoch = 0;

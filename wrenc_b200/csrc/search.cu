@@ -136,7 +136,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     constexpr int ncomp = 3;  // SINGLE_TREE 32x32 / 16x16 CUs (smaller CUs: small_eval)
     const bool is_root = id.depth == 0;
     int nst = 0;  // leading tasks that need the large scratch (32x32 luma pipelines of the root), see next_task
-    const int sb = is_root ? 16 : 0;  // every full evaluation's outcome is kept in a slot: shared memory (16x16 CU) or global scratch (root)
+    constexpr int sb = 0;  // every full evaluation's outcome is kept in a candidate slot of the CTU's global scratch
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
     __syncthreads();
@@ -662,20 +662,24 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
 __device__ __forceinline__ int sv_off_y(int d) { return d == 0 ? 0 : (d == 1 ? 1024 : 1280); }
 __device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 256 : 320); }
 
+// The saved samples and levels live in the CTU's global scratch (gsave: recY | recCb | recCr | lvY | lvCb | lvCr): written
+// once per node that may split, read back only where the no-split state wins.
 __device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int tid) {
     WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
+    uint8_t *svRecY = S.c->gsave;
+    int16_t *svLvY = reinterpret_cast<int16_t *>(S.c->gsave + SAVE_SAMPLES);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i >> ilog2i(w), x = i & (w - 1);
-        S.c->svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
-        S.c->svLvY[oy + i] = S.c->lvY[(nd.y + y) * 32 + nd.x + x];
+        svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
+        svLvY[oy + i] = S.c->lvY[(nd.y + y) * 32 + nd.x + x];
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
     for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
         int c = i >= cw * cw, j = i & (cw * cw - 1);
         int y = j >> ilog2i(cw), x = j & (cw - 1);
-        S.c->svRecC[c][oc + j] = RC(S, 1 + c, bx + x, by + y);
-        S.c->svLvC[c][oc + j] = S.c->lvC[c][(by + y) * 16 + bx + x];
+        svRecY[SAVE_Y + c * SAVE_C + oc + j] = RC(S, 1 + c, bx + x, by + y);
+        svLvY[SAVE_Y + c * SAVE_C + oc + j] = S.c->lvC[c][(by + y) * 16 + bx + x];
     }
     for (int i = tid; i < 64; i += NTHREADS) S.c->svLm[d][i] = S.c->lm[i];
     for (int i = tid; i < 16; i += NTHREADS) S.c->svCm[d][i] = S.c->cm[i];
@@ -683,17 +687,19 @@ __device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int ti
 __device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int tid) {
     WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
+    const uint8_t *svRecY = S.c->gsave;
+    const int16_t *svLvY = reinterpret_cast<const int16_t *>(S.c->gsave + SAVE_SAMPLES);
     for (int i = tid; i < w * w; i += NTHREADS) {
         int y = i >> ilog2i(w), x = i & (w - 1);
-        RY(S, nd.x + x, nd.y + y) = S.c->svRecY[oy + i];
-        S.c->lvY[(nd.y + y) * 32 + nd.x + x] = S.c->svLvY[oy + i];
+        RY(S, nd.x + x, nd.y + y) = __ldcg(svRecY + oy + i);
+        S.c->lvY[(nd.y + y) * 32 + nd.x + x] = __ldcg(svLvY + oy + i);
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
     for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
         int c = i >= cw * cw, j = i & (cw * cw - 1);
         int y = j >> ilog2i(cw), x = j & (cw - 1);
-        RC(S, 1 + c, bx + x, by + y) = S.c->svRecC[c][oc + j];
-        S.c->lvC[c][(by + y) * 16 + bx + x] = S.c->svLvC[c][oc + j];
+        RC(S, 1 + c, bx + x, by + y) = __ldcg(svRecY + SAVE_Y + c * SAVE_C + oc + j);
+        S.c->lvC[c][(by + y) * 16 + bx + x] = __ldcg(svLvY + SAVE_Y + c * SAVE_C + oc + j);
     }
     const int cells = w >> 2;
     for (int i = tid; i < cells * cells; i += NTHREADS) {
@@ -930,7 +936,8 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
                 C.pic = it >> 16; C.cyi = (it >> 8) & 255; C.cxi = it & 255;
                 C.g.cx = C.cxi * 32; C.g.cy = C.cyi * 32; C.g.W = W; C.g.H = H;
                 C.mask = 0; C.root_mode = 0; C.dir_cnt = 0;
-                C.groot = P.root_slots + ((size_t)blockIdx.x * KC + tid) * ROOT_SLOT_BYTES;
+                C.groot = P.root_slots + ((size_t)blockIdx.x * KC + tid) * CTU_SCRATCH_BYTES;
+                C.gsave = C.groot + ROOT_SLOT_BYTES;
                 int *done = P.done + (size_t)C.pic * Wc * P.Hc;
                 if (C.cxi > 0) while (ld_relaxed(&done[C.cyi * Wc + C.cxi - 1]) != P.epoch) __nanosleep(1000);
                 if (C.cyi > 0) {

@@ -105,12 +105,7 @@ struct alignas(16) CtuCtx {
     int16_t lvY[1024];
     int16_t lvC[2][256];
     uint8_t lm[64], cm[16];
-    // no-split state saved per depth (0: 32x32, 1: 16x16, 2: 8x8)
-    uint8_t svRecY[1024 + 256 + 64];
-    uint8_t svRecC[2][256 + 64 + 16];
-    int16_t svLvY[1024 + 256 + 64];
-    int16_t svLvC[2][256 + 64 + 16];
-    uint8_t svLm[3][64], svCm[3][16];
+    uint8_t svLm[3][64], svCm[3][16];  // modes of the no-split state saved per depth (0: 32x32, 1: 16x16, 2: 8x8); samples and levels: gsave
     // reference samples of the current node: [comp][raw|filtered]
     int16_t seq[3][132];      // after build_refs: the substituted samples in one line, left[2n] ... left[1], corner, above[0] ... above[2n-1]
     int16_t seqF[132];        // the same line of the [1 2 1] filtered luma references
@@ -133,15 +128,13 @@ struct alignas(16) CtuCtx {
     // leaf-evaluation state
     float cost_pl, cost_dc, cur_cost, dir_cost, min_cost, cost_dm;
     int cur, dir, mode, cclm_mode, v0, v1, cclm_wins, dir_cand;
-    uint8_t *groot;           // this CTU's root-CU slots in global memory (SearchParams::root_slots)
+    uint8_t *groot;           // this CTU's global scratch (SearchParams::root_slots): candidate slots of the CU being evaluated
+    uint8_t *gsave;           //   and the no-split states saved per depth
     unsigned dir_part[4];     // direction search of CUs up to 8x8: first minimum of each part of the coarse modes, and the arrival counter
     int dir_cnt;
     // results of the planar / DC evaluations (phase 1) and of the winner (phase 5), per component
     unsigned pd_ssd[2][3], fin_ssd[3];
     int pd_rate[2][3], fin_rate[3];
-    // candidate slots of nodes up to 16x16: reconstruction and levels of planar, DC, dir, dir-1, dir+1, CCLM (Y at 0, Cb at 256, Cr at 320)
-    uint8_t slotRec[6][384];  // slot 5: the CCLM evaluation (chroma part only)
-    int16_t slotLv[6][384];
 };
 
 struct Shared {
@@ -1238,17 +1231,14 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
             dst[(by + y) * stride + bx + x] = B[i];
         }
     }
-    // slot 0..5: shared-memory slots of CUs up to 16x16; slot 16..21: the root CU's slots in global memory
-    const bool gslot = slot >= 16;
-    const int soff = gslot ? (c == 0 ? 0 : (c == 1 ? 1024 : 1280)) : (c == 0 ? 0 : (c == 1 ? 256 : 320));
+    // candidate slot (planar, DC, dir, dir-1, dir+1, CCLM): the evaluation's outcome goes to the CTU's global scratch, block-local raster
+    const int soff = c == 0 ? 0 : (c == 1 ? 1024 : 1280);
     uint8_t *gRec = nullptr;
-    int16_t *gLv = nullptr;
-    if (gslot) {
-        gRec = S.c->groot + (slot - 16) * ROOT_SLOT_SAMPLES + soff;
-        gLv = reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + (slot - 16) * ROOT_SLOT_SAMPLES + soff;
+    if (slot >= 0) {
+        gRec = S.c->groot + slot * ROOT_SLOT_SAMPLES + soff;
+        int16_t *gLv = reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + slot * ROOT_SLOT_SAMPLES + soff;
         for (int i = lane; i < nn; i += 32) gLv[i] = B[i];
-    } else if (slot >= 0)
-        for (int i = lane; i < nn; i += 32) S.c->slotLv[slot][soff + i] = B[i];
+    }
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
         // dequantise (quantizer.rs:1074-1075) into the pair-packed layout of the column pass
@@ -1278,8 +1268,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
             if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
             else RC(S, c, bx + x, by + y) = (uint8_t)rec;
         }
-        if (gslot) gRec[i] = (uint8_t)rec;
-        else if (slot >= 0) S.c->slotRec[slot][soff + i] = (uint8_t)rec;
+        if (slot >= 0) gRec[i] = (uint8_t)rec;
     }
     ssd_out = warp_sumu(ssd);
     rate_out = rate;
@@ -1439,12 +1428,12 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
     }
     // levels back to raster order
     const int lev = __shfl_sync(hm, q, hb + (int)((INV_SCAN4 >> (4 * gl)) & 15ull));
-    const int soff = (c == 0 ? 0 : (c == 1 ? 256 : 320)) + gl;
+    const int soff = slot * ROOT_SLOT_SAMPLES + (c == 0 ? 0 : (c == 1 ? 1024 : 1280)) + gl;
     if (commit) {
         if (c == 0) S.c->lvY[(by + y) * 32 + bx + x] = (int16_t)lev;
         else S.c->lvC[c - 1][(by + y) * 16 + bx + x] = (int16_t)lev;
     }
-    if (slot >= 0) S.c->slotLv[slot][soff] = (int16_t)lev;
+    if (slot >= 0) reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES)[soff] = (int16_t)lev;
     int r = 0;
     if (anylev) {  // dequantise (quantizer.rs:1074-1075), inverse DCT (transformer.rs:2380-2737 with n = 4)
         const int dq = min(32767, max(-32768, (lev * ls + off) >> sh));
@@ -1459,7 +1448,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
         if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
         else RC(S, c, bx + x, by + y) = (uint8_t)rec;
     }
-    if (slot >= 0) S.c->slotRec[slot][soff] = (uint8_t)rec;
+    if (slot >= 0) S.c->groot[soff] = (uint8_t)rec;
     ssd_out = (unsigned)half_sum(d * d, hm);
     rate_out = rate;
     __syncwarp(hm);
@@ -1492,26 +1481,29 @@ __device__ __noinline__ int cclm_search4(const Ctx S, const CtuGeom g, const Nod
     return s[1] <= s[2] ? MODE_T_CCLM : MODE_L_CCLM;
 }
 
-// The winner of a node up to 16x16 was already evaluated with unchanged inputs (the reference repeats that evaluation,
-// block_splitter.rs:989-1037 / 1062-1076, with identical results): copy its reconstruction and levels out of its slot.
+// The winner of a node was already evaluated with unchanged inputs (the reference repeats that evaluation,
+// block_splitter.rs:989-1037 / 1062-1076, with identical results): copy its reconstruction and levels out of its slot
+// (global scratch, written by other warps of this CTA before the last block barrier; read around L1).
 __device__ __noinline__ void commit_slot(const Ctx S, const Node nd, int c, int slot, int lane) {
     WB_SHARED_CTX(S);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
-    const int soff = c == 0 ? 0 : (c == 1 ? 256 : 320);
+    const int soff = slot * ROOT_SLOT_SAMPLES + (c == 0 ? 0 : (c == 1 ? 1024 : 1280));
+    const uint8_t *gRec = S.c->groot + soff;
+    const int16_t *gLv = reinterpret_cast<const int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + soff;
     int16_t *dst = c == 0 ? S.c->lvY : S.c->lvC[c - 1];
     const int stride = c == 0 ? 32 : 16;
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
-        dst[(by + y) * stride + bx + x] = S.c->slotLv[slot][soff + i];
-        const uint8_t r = S.c->slotRec[slot][soff + i];
+        dst[(by + y) * stride + bx + x] = __ldcg(gLv + i);
+        const uint8_t r = __ldcg(gRec + i);
         if (c == 0) RY(S, bx + x, by + y) = r;
         else RC(S, c, bx + x, by + y) = r;
     }
     __syncwarp();
 }
 
-// The same for the 32x32 root CU, whose slots live in global memory (written by other warps of this CTA before the last
-// block barrier; read around L1).
+// The same for the 32x32 root CU, four samples per lane and iteration.  (The slots were written by other warps of this CTA
+// before the last block barrier; read around L1.)
 __device__ __noinline__ void commit_root_slot(const Ctx S, int c, int slot, int lane) {
     WB_SHARED_CTX(S);
     const int n = c == 0 ? 32 : 16, l2 = c == 0 ? 5 : 4, nn = n * n;

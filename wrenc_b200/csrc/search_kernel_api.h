@@ -28,12 +28,17 @@ struct SearchParams {
     int *done;             // [pic][Wc*Hc]
     const uint32_t *items; // work list: batches of search_ctus_per_cta() slots, pic<<16 | cy<<8 | cx or 0xffffffff (empty slot)
     unsigned int *counter; // work-list cursor
-    uint8_t *root_slots;   // [CTA][CTU of the batch][ROOT_SLOT_BYTES]: candidate slots of the 32x32 root CU (too large for shared memory)
+    uint8_t *root_slots;   // [CTA][CTU of the batch][CTU_SCRATCH_BYTES]: candidate slots of the CU being evaluated + saved no-split states
+                           // (written and read back by the same CTA, L2 resident; keeps the per-CTU shared-memory context small)
     const DevTables *tab;
 };
 
 // per CTU: 6 slots (planar, DC, dir, dir-1, dir+1, CCLM) x 1536 samples (Y 1024, Cb 256, Cr 256): reconstruction u8, then levels i16
 constexpr int ROOT_SLOT_SAMPLES = 1536, ROOT_SLOTS = 6, ROOT_SLOT_BYTES = ROOT_SLOTS * ROOT_SLOT_SAMPLES * 3;
+// no-split state saved per depth (32x32, 16x16, 8x8): Y 1024 + 256 + 64 samples, Cb / Cr 256 + 64 + 16 each: reconstruction u8, then levels i16
+constexpr int SAVE_Y = 1024 + 256 + 64, SAVE_C = 256 + 64 + 16, SAVE_SAMPLES = SAVE_Y + 2 * SAVE_C;
+constexpr int CTU_SCRATCH_BYTES = ROOT_SLOT_BYTES + SAVE_SAMPLES * 3;
+static_assert(CTU_SCRATCH_BYTES % 16 == 0 && ROOT_SLOT_BYTES % 16 == 0 && SAVE_SAMPLES % 8 == 0, "alignment of the per-CTU global scratch");
 enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
 enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
 
