@@ -95,15 +95,20 @@ __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, in
 }
 
 // Tasks of a phase are handed out in list order (the large luma tasks first) to whichever warp is free: a shared-memory
-// ticket per phase (S.ticket[phase parity], reset two phases later).  32x32 luma pipelines need the large scratch buffers
-// that only the first NBIG warps own: those tasks lead the list and the first `nst` of them are taken statically by warps
-// 0..nst-1 as their first task; everything else is dynamic.
-__device__ __forceinline__ int next_task(Shared &S, int &slot, int nst, int ntot, int prev, int warp, int lane) {
-    if (ntot <= NW) return prev < 0 ? warp : ntot;  // at most one task per warp: no ticket needed
-    if (prev < 0 && warp < nst) return warp;
+// ticket per phase (S.ticket[phase parity], reset two phases later); a phase with at most one task per warp is assigned
+// statically.  32x32 luma pipelines need the large scratch buffers that only the first NBIG warps own: those `nbig` tasks lead
+// the list and have their own ticket, which the NBIG warps drain before they join the others on the general ticket.
+__device__ __forceinline__ int next_task(Shared &S, int &slot, int nbig, int ntot, int prev, int warp, int lane) {
+    if (nbig == 0 && ntot <= NW) return prev < 0 ? warp : ntot;  // at most one task per warp: no ticket needed
+    if (nbig > 0 && warp < NBIG && prev < nbig) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&S.ticket_big[slot], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t < nbig) return t;
+    }
     int t = 0;
     if (lane == 0) t = atomicAdd(&S.ticket[slot], 1);
-    return nst + __shfl_sync(0xffffffffu, t, 0);
+    return nbig + __shfl_sync(0xffffffffu, t, 0);
 }
 // node geometry + availability flags of the current node, cached per CTU (x | y << 6 | w << 12 | tree << 18 | ar << 20 | bl << 21)
 __device__ __forceinline__ unsigned pack_node(const Node n) {
@@ -122,7 +127,7 @@ __device__ __forceinline__ Node unpack_node(unsigned p) {
 #define WB_NEXT_PHASE()                                       \
     do {                                                      \
         S_slot ^= 1;                                          \
-        if (threadIdx.x == 0) S.ticket[S_slot ^ 1] = 0;       \
+        if (threadIdx.x == 0) { S.ticket[S_slot ^ 1] = 0; S.ticket_big[S_slot ^ 1] = 0; } \
     } while (0)
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -135,7 +140,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const WarpScratch ws = warp_scratch(S, warp);
     constexpr int ncomp = 3;  // SINGLE_TREE 32x32 / 16x16 CUs (smaller CUs: small_eval)
     const bool is_root = id.depth == 0;
-    int nst = 0;  // leading tasks that need the large scratch (32x32 luma pipelines of the root), see next_task
+    int nst = 0;  // number of leading tasks that need the large scratch (32x32 luma pipelines of the root), see next_task
     constexpr int sb = 0;  // every full evaluation's outcome is kept in a candidate slot of the CTU's global scratch
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));
@@ -907,7 +912,7 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
     const int tid = threadIdx.x;
     init_tables(S, P.tab, tid);
     if (tid == 0) {
-        S.ticket[0] = 0; S.ticket[1] = 0;
+        S.ticket[0] = 0; S.ticket[1] = 0; S.ticket_big[0] = 0; S.ticket_big[1] = 0;
         mbar_init(&S.tma_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }

@@ -33,10 +33,13 @@ namespace wb {
 constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
 #ifndef WB_K
-#define WB_K 4
+#define WB_K 8
 #endif
 constexpr int KC = WB_K;     // CTUs searched in lock step by one CTA
-constexpr int NBIG = NW < 3 * KC ? NW : 3 * KC;  // warps with scratch large enough for a 32x32 luma pipeline (those tasks are listed first)
+#ifndef WB_NBIG
+#define WB_NBIG 8
+#endif
+constexpr int NBIG = NW < WB_NBIG ? NW : WB_NBIG;  // warps with scratch large enough for a 32x32 luma pipeline (they drain those tasks first)
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -146,6 +149,7 @@ struct Shared {
 #endif
     unsigned long long tma_bar;  // mbarrier the TMA bulk copies of the source blocks complete on
     int ticket[2];            // dynamic task tickets of the current / previous phase
+    int ticket_big[2];        //   and of the tasks that need the large scratch (32x32 luma pipelines of the root)
     // per-warp scratch
     int16_t bigA[NBIG][1024], bigB[NBIG][1024];
     uint16_t bigW[NBIG][1024];
