@@ -669,93 +669,94 @@ __device__ __forceinline__ int sv_off_c(int d) { return d == 0 ? 0 : (d == 1 ? 2
 
 // The saved samples and levels live in the CTU's global scratch (gsave: recY | recCb | recCr | lvY | lvCb | lvCr): written
 // once per node that may split, read back only where the no-split state wins.
-__device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int tid) {
+__device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int tid, int nthr) {
     WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     uint8_t *svRecY = S.c->gsave;
     int16_t *svLvY = reinterpret_cast<int16_t *>(S.c->gsave + SAVE_SAMPLES);
-    for (int i = tid; i < w * w; i += NTHREADS) {
+    for (int i = tid; i < w * w; i += nthr) {
         int y = i >> ilog2i(w), x = i & (w - 1);
         svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
         svLvY[oy + i] = S.c->lvY[(nd.y + y) * 32 + nd.x + x];
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
-    for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
+    for (int i = tid; i < 2 * cw * cw; i += nthr) {
         int c = i >= cw * cw, j = i & (cw * cw - 1);
         int y = j >> ilog2i(cw), x = j & (cw - 1);
         svRecY[SAVE_Y + c * SAVE_C + oc + j] = RC(S, 1 + c, bx + x, by + y);
         svLvY[SAVE_Y + c * SAVE_C + oc + j] = S.c->lvC[c][(by + y) * 16 + bx + x];
     }
-    for (int i = tid; i < 64; i += NTHREADS) S.c->svLm[d][i] = S.c->lm[i];
-    for (int i = tid; i < 16; i += NTHREADS) S.c->svCm[d][i] = S.c->cm[i];
+    for (int i = tid; i < 64; i += nthr) S.c->svLm[d][i] = S.c->lm[i];
+    for (int i = tid; i < 16; i += nthr) S.c->svCm[d][i] = S.c->cm[i];
 }
-__device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int tid) {
+__device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int tid, int nthr) {
     WB_SHARED_CTX(S);
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     const uint8_t *svRecY = S.c->gsave;
     const int16_t *svLvY = reinterpret_cast<const int16_t *>(S.c->gsave + SAVE_SAMPLES);
-    for (int i = tid; i < w * w; i += NTHREADS) {
+    for (int i = tid; i < w * w; i += nthr) {
         int y = i >> ilog2i(w), x = i & (w - 1);
         RY(S, nd.x + x, nd.y + y) = __ldcg(svRecY + oy + i);
         S.c->lvY[(nd.y + y) * 32 + nd.x + x] = __ldcg(svLvY + oy + i);
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
-    for (int i = tid; i < 2 * cw * cw; i += NTHREADS) {
+    for (int i = tid; i < 2 * cw * cw; i += nthr) {
         int c = i >= cw * cw, j = i & (cw * cw - 1);
         int y = j >> ilog2i(cw), x = j & (cw - 1);
         RC(S, 1 + c, bx + x, by + y) = __ldcg(svRecY + SAVE_Y + c * SAVE_C + oc + j);
         S.c->lvC[c][(by + y) * 16 + bx + x] = __ldcg(svLvY + SAVE_Y + c * SAVE_C + oc + j);
     }
     const int cells = w >> 2;
-    for (int i = tid; i < cells * cells; i += NTHREADS) {
+    for (int i = tid; i < cells * cells; i += nthr) {
         int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         int idx = ((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx;
         S.c->lm[idx] = S.c->svLm[d][idx];
     }
     const int cc = w >> 3;
-    for (int i = tid; i < cc * cc; i += NTHREADS) {
+    for (int i = tid; i < cc * cc; i += nthr) {
         int yy = i >> ilog2i(cc), xx = i & (cc - 1);
         int idx = ((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx;
         S.c->cm[idx] = S.c->svCm[d][idx];
     }
 }
 
-// after the leaf evaluation of a node that may still split: remember its cost and state
+// after the leaf evaluation of a node that may still split: remember its cost and state.  The CTUs of the batch are handled
+// side by side, NTHREADS / KC threads each.
+constexpr int GT = NTHREADS / KC;  // threads per CTU in the save / restore passes
 __device__ void begin_split(Shared &S, const NodeId &id, int d) {
-    const int tid = threadIdx.x;
-    for (int k = 0; k < KC; k++) {
-        if (!S.c[k].active) continue;
+    const int k = threadIdx.x / GT, gt = threadIdx.x % GT;
+    if (k < KC && S.c[k].active) {
         Ctx V{&S.tb, &S.c[k]};
-        save_node(V, make_node(V.c->g, id), d, tid);
-    }
-    if (tid < KC && S.c[tid].active) {
-        CtuCtx &C = S.c[tid];
-        C.cost[d] = C.leaf_cost;
-        C.split[d] = 0.0f;
-        if (d < 2) C.mask_sv[d] = C.mask;
-    }
-    __syncthreads();
-}
-// split_cost > no_split_cost keeps the no-split state (block_splitter.rs:1125); otherwise the split is adopted
-__device__ void end_split(Shared &S, const NodeId &id, int d, int bit) {
-    const int tid = threadIdx.x;
-    if (tid < KC && S.c[tid].active) {
-        CtuCtx &C = S.c[tid];
-        if (C.split[d] > C.cost[d]) {
-            C.restore = 1;
-            if (d < 2) C.mask = C.mask_sv[d];
-            C.leaf_cost = C.cost[d];
-        } else {
-            C.restore = 0;
-            C.mask |= 1u << bit;
-            C.leaf_cost = C.split[d];
+        CtuCtx &C = *V.c;
+        save_node(V, make_node(C.g, id), d, gt, GT);
+        if (gt == 0) {
+            C.cost[d] = C.leaf_cost;
+            C.split[d] = 0.0f;
+            if (d < 2) C.mask_sv[d] = C.mask;
         }
     }
     __syncthreads();
-    for (int k = 0; k < KC; k++) {
-        if (!S.c[k].active || !S.c[k].restore) continue;
+}
+// split_cost > no_split_cost keeps the no-split state (block_splitter.rs:1125); otherwise the split is adopted.  The node's
+// final cost is added to its parent's running split cost (f32, child order) when there is a parent (dp >= 0).
+__device__ void end_split(Shared &S, const NodeId &id, int d, int bit, int dp) {
+    const int k = threadIdx.x / GT, gt = threadIdx.x % GT;
+    if (k < KC && S.c[k].active) {
         Ctx V{&S.tb, &S.c[k]};
-        restore_node(V, make_node(V.c->g, id), d, tid);
+        CtuCtx &C = *V.c;
+        const float split = C.split[d], nosplit = C.cost[d];
+        const bool restore = split > nosplit;
+        if (restore) restore_node(V, make_node(C.g, id), d, gt, GT);
+        if (gt == 0) {
+            if (restore) {
+                if (d < 2) C.mask = C.mask_sv[d];
+            } else {
+                C.mask |= 1u << bit;
+            }
+            const float cost = restore ? nosplit : split;
+            C.leaf_cost = cost;
+            if (dp >= 0) C.split[dp] = __fadd_rn(C.split[dp], cost);
+        }
     }
     __syncthreads();
 }
@@ -791,15 +792,13 @@ __device__ void ctu_search(Shared &S, const SearchParams &P, int &S_slot) {
                         }
                         NodeId nc{2, a, b, 0, DUAL_TREE_CHROMA};
                         chroma_ct_eval(S, P, nc, S_slot);
-                        end_split(S, n8, 2, 5 + a * 4 + b);
-                    }
-                    add_to_parent(S, 1);
+                        end_split(S, n8, 2, 5 + a * 4 + b, 1);
+                    } else add_to_parent(S, 1);
                 }
-                end_split(S, n16, 1, 1 + a);
-            }
-            add_to_parent(S, 0);
+                end_split(S, n16, 1, 1 + a, 0);
+            } else add_to_parent(S, 0);
         }
-        end_split(S, n32, 0, 0);
+        end_split(S, n32, 0, 0, -1);
     }
 }
 
