@@ -620,9 +620,10 @@ __device__ __forceinline__ int ang_sample_direct(const Ctx S, int c, int n, int 
     const int t = vertical ? y : x, u = vertical ? x : y;
     const int prod = (t + 1) * ang;
     const int ifact = prod & 31, base = u + (prod >> 5);
-    auto tap = [&](int idx) -> int {
-        const int f = idx >= 0 ? min(idx, 2 * n) : -min((idx * inv + 256) >> 9, n);
-        return e0[vertical ? f : -f];
+    const int sg = vertical ? 1 : -1;
+    auto tap = [&](int idx) -> int {  // ang >= 0: idx >= 0 always (no projection from the other side)
+        const int f = (ang >= 0 || idx >= 0) ? min(idx, 2 * n) : -min((idx * inv + 256) >> 9, n);
+        return e0[sg * f];
     };
     int p;
     if (c == 0) {
@@ -819,12 +820,11 @@ __device__ __noinline__ void mm_cols_q(const int8_t *M, const int32_t *P, int16_
 #define WB_LDQ(i) ((i) < 64 ? S.tb->ldq[(i)] : __ldg(&tab->ldq[min((i), 1023)]))
 #define WB_LV(i) ((i) < 64 ? S.tb->lv[(i)] : __ldg(&tab->lv[min((i), 1023)]))
 
-__device__ __forceinline__ unsigned map_compose(unsigned a, unsigned b) {  // apply a first, then b (4 x 2-bit next-state maps)
-    unsigned r = 0;
-#pragma unroll
-    for (int s = 0; s < 4; s++) r |= ((b >> (2 * ((a >> (2 * s)) & 3))) & 3) << (2 * s);
-    return r;
-}
+// Next-state maps of the walk are kept as 4 bytes (byte s = next state of state s), so that composing two maps is one byte
+// permute: the selector of __byte_perm is the first map in nibble form.
+constexpr unsigned MAP_ID = 0x03020100u;
+__device__ __forceinline__ unsigned map_nib(unsigned m) { return __byte_perm(m | (m >> 4), 0u, 0x4420u); }  // bytes -> nibbles
+__device__ __forceinline__ unsigned map_compose(unsigned a, unsigned b) { return __byte_perm(b, 0u, map_nib(a)); }  // apply a first, then b
 
 // Local candidate costs of one scan position (quantizer.rs:436-503): for delta = (state > 1) in {0,1} the two candidate
 // levels a0 = (x + delta) / 2 and a1 = a0 + 1, cost_i = 128 * |tc - dequant(q_i)| + lambda * dq_table[bits_i].
@@ -890,17 +890,14 @@ __device__ __forceinline__ unsigned vstep(const LC &l, int ldq1, int &C0, int &C
     return (unsigned)d_0 | ((unsigned)d_1 << 1) | ((unsigned)d_2 << 2) | ((unsigned)d_3 << 3);
 }
 
-// next-state map (4 x 2 bits) of one position for the walk: next(s) = 2 * (parity(a_s) ^ (s & 1)) + (s >> 1)
+// next-state map of one position for the walk: next(s) = 2 * (parity(a_s) ^ (s & 1)) + (s >> 1), a_s = a0(delta(s)) + decision bit s.
+// pos_q: the 4 bits parity(a_s) ^ (s & 1), spread to the bytes by a multiplication; pos_map_nib: the map as a permute selector.
+__device__ __forceinline__ unsigned pos_q(unsigned pk, unsigned dec) { return ((((pk & 1u) * 3u) | ((pk & 2u) * 6u)) ^ dec ^ 0xAu) & 0xFu; }
 __device__ __forceinline__ unsigned pos_map(unsigned pk, unsigned dec, bool nz) {
-    if (!nz) return 0xD8u;  // a = 0 for every state: 0->0, 1->2, 2->1, 3->3
-    unsigned m = 0;
-#pragma unroll
-    for (int s = 0; s < 4; s++) {
-        unsigned par = ((pk >> (s >> 1)) ^ (dec >> s)) & 1u;
-        m |= (2u * (par ^ (s & 1u)) + (s >> 1)) << (2 * s);
-    }
-    return m;
+    if (!nz) return 0x03010200u;  // a = 0 for every state: 0->0, 1->2, 2->1, 3->3
+    return (((pos_q(pk, dec) * 0x00204081u) & 0x01010101u) << 1) + 0x01010000u;
 }
+__device__ __forceinline__ unsigned pos_map_nib(unsigned pk, unsigned dec, bool nz) { return map_nib(pos_map(pk, dec, nz)); }
 
 // coef (raster, n x n) -> lev (raster).  Returns rate (sum of lv[] per block_splitter.rs:415-460) and whether any level != 0.
 //
@@ -986,7 +983,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
     const bool tiny = nn == 16;  // 4x4 TBs (the most numerous): one position per lane, plain sequential pass over 15 steps
     const int CS = tiny ? 1 : (nn >= 1024 ? 16 : (nn >= 256 ? 8 : 4)), nch = nn / CS, rounds = (nch + 31) >> 5;
     int carry0 = 0, carry1 = 0, carry2 = 0, carry3 = 0;
-    unsigned cmaps = 0;
+    unsigned cm0 = MAP_ID, cm1 = MAP_ID;  // walk map of this lane's chunk in round 0 / 1
     if (tiny) {
         LC l;
         l.L00 = l.L01 = l.L0s0 = 0; l.L10 = l.L11 = TR_INF; l.pk = 0;
@@ -1009,7 +1006,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         if (lane < 16) {
             Wd[lane] = (uint16_t)(w | (mydec << 12));
             const unsigned pk = lane == 0 ? ((w >> 1) & 1u) * 3u : l.pk;
-            cmaps = pos_map(pk, mydec, (w & 2048u) != 0);
+            cm0 = pos_map(pk, mydec, (w & 2048u) != 0);
         }
     } else
     for (int r = 0; r < rounds; r++) {
@@ -1077,7 +1074,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         // ---- D: replay the chunk from its true entry costs, record decisions and the chunk's walk map
         if (vc) {
             int C0 = my0, C1 = my1, C2 = my2, C3 = my3;
-            unsigned cm = 0xE4u;
+            unsigned cm = MAP_ID;
 #pragma unroll 1
             for (int i = 0; i < CS; i++) {
                 const int k = k0 + i;
@@ -1093,9 +1090,9 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
                     pk = l.pk;
                 }
                 Wd[k] = (uint16_t)(w | (dec << 12));
-                cm = map_compose(pos_map(pk, dec, (w & 2048u) != 0), cm);
+                cm = __byte_perm(cm, 0u, pos_map_nib(pk, dec, (w & 2048u) != 0));  // this position first, then the ones below
             }
-            cmaps |= cm << (8 * r);
+            if (r == 0) cm0 = cm; else cm1 = cm;
         }
     }
     __syncwarp();
@@ -1108,16 +1105,16 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         const int c = r * 32 + lane;
         const bool vc = c < nch;
         const int k0 = c * CS;
-        unsigned inc = vc ? ((cmaps >> (8 * r)) & 255u) : 0xE4u;
+        unsigned inc = vc ? (r == 0 ? cm0 : cm1) : MAP_ID;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned t = __shfl_down_sync(0xffffffffu, inc, d);
             if (lane + d < 32) inc = map_compose(t, inc);
         }
         const unsigned exc = __shfl_down_sync(0xffffffffu, inc, 1);
-        unsigned s = (lane == 31) ? state : ((exc >> (2 * state)) & 3u);
+        unsigned s = (lane == 31) ? state : ((exc >> (8 * state)) & 3u);
         const unsigned all = __shfl_sync(0xffffffffu, inc, 0);
-        state = (all >> (2 * state)) & 3u;
+        state = (all >> (8 * state)) & 3u;
         int lead = 0, irate = 0;
         bool has = false;
         if (vc) {
