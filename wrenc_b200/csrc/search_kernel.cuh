@@ -688,7 +688,8 @@ __device__ __noinline__ unsigned dir_sad(const Ctx S, const Node nd, int mode, i
         const int cs = c != 0, n = nd.w >> cs, l2 = ilog2i(n), bx = nd.x >> cs, by = nd.y >> cs;
         const int x = idx & (n - 1), y = idx >> l2;
         const int p = ang_sample_direct(S, c, n, l2, mode, x, y);
-        s += (unsigned)abs(p - org_at(S, c, bx + x, by + y));
+        const uint8_t *org = cs ? S.c->orgC[c - 1] + ((by + y) << 4) : S.c->orgY + ((by + y) << 5);
+        s += (unsigned)abs(p - (int)org[bx + x]);
     }
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -705,7 +706,8 @@ __device__ __noinline__ void dir_search_part(const Ctx S, const Node nd, int par
     WB_SHARED_CTX(S);
     const bool luma_only = nd.tree == DUAL_TREE_LUMA;  // 4x4 CU: two modes per call
     const int half = lane >> 4;
-    const int lo = part * 13 / nparts, hi = (part + 1) * 13 / nparts;
+    // coarse modes [lo, hi) of this part (nparts is 3 or 4: constant divisors)
+    const int lo = nparts == 3 ? part * 13 / 3 : part * 13 / 4, hi = nparts == 3 ? (part + 1) * 13 / 3 : (part + 1) * 13 / 4;
     unsigned bp = 0xffffffffu;
 #pragma unroll 1
     for (int i = lo; i < hi; i += luma_only ? 2 : 1) {
@@ -1178,12 +1180,14 @@ __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, con
     const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
     unsigned sad = 0;
+    const uint8_t *org = cs ? S.c->orgC[c - 1] + by * 16 + bx : S.c->orgY + by * 32 + bx;  // source block, row stride 16 / 32
+    const int osh = cs ? 4 : 5;
 #pragma unroll 1
     for (int i = lane; i < n * n; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int p = pred_sample(S, pc, x, y);
         if (pred_out) pred_out[i] = (uint8_t)p;
-        sad += abs(p - org_at(S, c, bx + x, by + y));
+        sad += abs(p - (int)org[(y << osh) + x]);
     }
     return warp_sumu(sad);
 }
