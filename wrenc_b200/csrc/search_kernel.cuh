@@ -1208,10 +1208,12 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     __syncwarp();
     int16_t *A = ws.A, *B = ws.B;
     bool anyres = anysad;
+    const uint8_t *org = cs ? S.c->orgC[c - 1] + by * 16 + bx : S.c->orgY + by * 32 + bx;  // source block, row stride 16 / 32
+    const int osh = cs ? 4 : 5;
 #pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
-        A[i] = (int16_t)(org_at(S, c, bx + x, by + y) - (int)ws.pred[i]);
+        A[i] = (int16_t)((int)org[(y << osh) + x] - (int)ws.pred[i]);
     }
     anyres = __any_sync(0xffffffffu, anyres);
     __syncwarp();
@@ -1267,7 +1269,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         int y = i >> l2, x = i & (n - 1);
         int res = anylev ? (int)A[i] : 0;
         int rec = clip8((int)(int16_t)((int)ws.pred[i] + res));
-        int d = rec - org_at(S, c, bx + x, by + y);
+        int d = rec - (int)org[(y << osh) + x];
         ssd += (unsigned)(d * d);
         if (commit) {
             if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
