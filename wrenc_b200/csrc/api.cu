@@ -49,6 +49,7 @@ struct wrenc_b200 {
     int coder_pics = 0;
     uint16_t *d_bins = nullptr;
     size_t bins_cap = 0;
+    uint16_t *d_stage = nullptr;  // per-CTU staging slots of the bin strings (stage_cap() entries each)
     int *d_bin_count = nullptr;
     unsigned long long *d_bin_offset = nullptr, *d_bin_total = nullptr;
     uint8_t *d_out = nullptr;
@@ -156,15 +157,27 @@ static int enqueue_search(wrenc_b200 *h, int n_pics, const uint8_t *d_yuv, uint8
     return 0;
 }
 
+// Entries per CTU staging slot: CTUs whose bin string is longer (busy content at low QP) are walked a second time.
+// (WRENC_B200_STAGE_CAP: dev-time override, lets the tests force the second walk.)
+static int stage_cap() {
+    static int cap = 0;
+    if (!cap) {
+        const char *e = getenv("WRENC_B200_STAGE_CAP");
+        cap = e && atoi(e) > 0 ? atoi(e) : 1024;
+    }
+    return cap;
+}
+
 static int ensure_coder(wrenc_b200 *h, int n_pics) {
     if (n_pics <= h->coder_pics) return 0;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_out); cudaFree(h->d_out_len);
-    h->d_bin_count = nullptr; h->d_bin_offset = nullptr; h->d_out = nullptr; h->d_out_len = nullptr;
+    cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_out); cudaFree(h->d_out_len); cudaFree(h->d_stage);
+    h->d_bin_count = nullptr; h->d_bin_offset = nullptr; h->d_out = nullptr; h->d_out_len = nullptr; h->d_stage = nullptr;
     const size_t nctu = (size_t)h->Wc * h->Hc * n_pics;
     h->out_cap = (size_t)h->W * h->H * 3 / 2;
     CK(cudaMalloc(&h->d_bin_count, nctu * sizeof(int)));
+    CK(cudaMalloc(&h->d_stage, nctu * stage_cap() * sizeof(uint16_t)));
     CK(cudaMalloc(&h->d_bin_offset, nctu * sizeof(unsigned long long)));
     CK(cudaMalloc(&h->d_out, (size_t)n_pics * h->out_cap));
     CK(cudaMalloc(&h->d_out_len, (size_t)n_pics * sizeof(int)));
@@ -185,6 +198,7 @@ static int enqueue_coder(wrenc_b200 *h, int n_pics, const int16_t *d_lev, const 
     Q.W = h->W; Q.H = h->H; Q.Wc = h->Wc; Q.Hc = h->Hc; Q.n_pics = n_pics; Q.qp = h->cfg.qp;
     Q.lev = d_lev; Q.records = d_records; Q.mode_map = h->d_mode_map;
     Q.bins = nullptr; Q.bin_count = h->d_bin_count; Q.bin_offset = h->d_bin_offset;
+    Q.stage = h->d_stage; Q.stage_cap = stage_cap();
     Q.out = d_out; Q.out_cap = out_cap; Q.out_len = d_out_len;
     CK(launch_syntax(Q, st));
     CK(launch_bin_scan(Q, h->d_bin_total, st));
@@ -198,9 +212,10 @@ static int enqueue_coder(wrenc_b200 *h, int n_pics, const int16_t *d_lev, const 
         CK(cudaMalloc(&h->d_bins, h->bins_cap * sizeof(uint16_t)));
     }
     Q.bins = h->d_bins;
-    CK(launch_syntax(Q, st));
+    CK(launch_syntax(Q, st));       // only the CTUs that did not fit their staging slot
+    CK(launch_bin_compact(Q, st));  // everybody else: staged string -> arena offset
     CK(launch_cabac(Q, st));
-    h->launches += 4;
+    h->launches += 5;
     return 0;
 }
 
@@ -275,7 +290,7 @@ void wrenc_b200_destroy(wrenc_b200 *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_tab); cudaFree(h->d_root_slots); cudaFree(h->d_mode_map); cudaFree(h->d_done); cudaFree(h->d_items); cudaFree(h->d_counter);
     cudaFree(h->d_orig); cudaFree(h->d_rec); cudaFree(h->d_lev); cudaFree(h->d_rec_ctu);
-    cudaFree(h->d_bins); cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_bin_total); cudaFree(h->d_out); cudaFree(h->d_out_len);
+    cudaFree(h->d_bins); cudaFree(h->d_stage); cudaFree(h->d_bin_count); cudaFree(h->d_bin_offset); cudaFree(h->d_bin_total); cudaFree(h->d_out); cudaFree(h->d_out_len);
     cudaFreeHost(h->h_out); cudaFreeHost(h->h_out_len);
     cudaFreeHost(h->h_orig); cudaFreeHost(h->h_rec); cudaFreeHost(h->h_lev); cudaFreeHost(h->h_records);
     if (h->ev_done) cudaEventDestroy(h->ev_done);

@@ -47,7 +47,9 @@ struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_dat
     const int16_t *lev;        // [pic][W*H*3/2]
     const CtuRecord *records;  // [pic][Wc*Hc]
     const uint8_t *mode_map;   // [pic][(W/4)*(H/4)]
-    uint16_t *bins;            // bin arena (entries: ctx index | bin << 9 | bypass << 10); nullptr = counting pass
+    uint16_t *bins;            // bin arena (entries: ctx index | bin << 9 | bypass << 10); nullptr = counting + staging pass
+    uint16_t *stage;           // [pic][ctu][stage_cap]: the counting pass keeps the first stage_cap entries of every CTU's bin string here, so that
+    int stage_cap;             //   only CTUs with longer strings are walked a second time; the others are copied to their arena offset
     int *bin_count;            // [pic][ctu] entries of the CTU's bin string
     unsigned long long *bin_offset;  // [pic][ctu] start of the CTU's bin string in the arena (exclusive scan of bin_count)
     uint8_t *out;              // [pic][out_cap] bytes
@@ -56,6 +58,7 @@ struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_dat
 };
 cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream);
 cudaError_t launch_bin_scan(const SyntaxParams &Q, unsigned long long *d_total, cudaStream_t stream);
+cudaError_t launch_bin_compact(const SyntaxParams &Q, cudaStream_t stream);
 cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream);
 
 struct BlockParams {

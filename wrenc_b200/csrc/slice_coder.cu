@@ -45,9 +45,9 @@ __device__ void build_sb_order(SbOrder &T) {
 
 struct Sink {
     uint16_t *p;
-    int n;
+    int n, cap;  // entries beyond cap are counted, not stored (staging pass)
     __device__ __forceinline__ void put(unsigned e) {
-        if (p) p[n] = (uint16_t)e;  // p == nullptr: counting pass
+        if (n < cap) p[n] = (uint16_t)e;
         n++;
     }
     __device__ __forceinline__ void ctx(int c, int b) { put((unsigned)c | ((unsigned)(b & 1) << 9)); }
@@ -420,9 +420,19 @@ extern "C" __global__ void __launch_bounds__(64) wrenc_b200_syntax_kernel(Syntax
     P.lev[2] = P.lev[1] + (size_t)(Q.W >> 1) * (Q.H >> 1);
     P.rec = Q.records + (size_t)pic * nctu;
     P.mode_map = Q.mode_map + (size_t)pic * (Q.W >> 2) * (Q.H >> 2);
+    // First pass (Q.bins == nullptr): count the CTU's bins and keep the first stage_cap of them in the CTU's staging slot.
+    // Second pass: only the CTUs whose string did not fit are walked again and written at their scanned arena offset (the
+    // others are copied there by wrenc_b200_bin_compact_kernel).
     Sink S;
-    S.p = Q.bins ? Q.bins + Q.bin_offset[gid] : nullptr;  // first pass counts, second pass writes at the scanned offsets
     S.n = 0;
+    if (!Q.bins) {
+        S.p = Q.stage + (size_t)gid * Q.stage_cap;
+        S.cap = Q.stage_cap;
+    } else {
+        if (Q.bin_count[gid] <= Q.stage_cap) return;
+        S.p = Q.bins + Q.bin_offset[gid];
+        S.cap = 0x7fffffff;
+    }
     uint16_t pass1[1024], absl[1024];
     TuState ts;
     ts.qp_delta_coded = false;  // quantisation group = CTU (cu_qp_delta_subdiv 0, ctu_encoder.rs:305-310)
@@ -431,6 +441,19 @@ extern "C" __global__ void __launch_bounds__(64) wrenc_b200_syntax_kernel(Syntax
     const int cx = (ctu % Q.Wc) * 32, cy = (ctu / Q.Wc) * 32;
     code_ctu(S, SO, P, P.rec[ctu], cx, cy, ts, pass1, absl);
     if (!Q.bins) Q.bin_count[gid] = S.n;
+}
+
+// staged bin strings -> their arena offsets, one warp per CTU (strings longer than the staging slot are written by the second
+// syntax pass instead)
+extern "C" __global__ void __launch_bounds__(256) wrenc_b200_bin_compact_kernel(SyntaxParams Q) {
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gid >= (long long)Q.n_pics * Q.Wc * Q.Hc) return;
+    const int cnt = Q.bin_count[gid];
+    if (cnt > Q.stage_cap) return;
+    const uint16_t *src = Q.stage + (size_t)gid * Q.stage_cap;
+    uint16_t *dst = Q.bins + Q.bin_offset[gid];
+    for (int i = lane; i < cnt; i += 32) dst[i] = src[i];
 }
 
 // exclusive prefix sum of the per-CTU bin counts over all pictures (one block; the counts are a few hundred thousand ints)
@@ -581,6 +604,11 @@ cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream) {  // Q.bi
 cudaError_t launch_bin_scan(const SyntaxParams &Q, unsigned long long *d_total, cudaStream_t stream) {
     const long long total = (long long)Q.n_pics * Q.Wc * Q.Hc;
     wrenc_b200_bin_scan_kernel<<<1, 1024, 0, stream>>>(Q.bin_count, Q.bin_offset, total, d_total);
+    return cudaGetLastError();
+}
+cudaError_t launch_bin_compact(const SyntaxParams &Q, cudaStream_t stream) {
+    const long long total = (long long)Q.n_pics * Q.Wc * Q.Hc;
+    wrenc_b200_bin_compact_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(Q);
     return cudaGetLastError();
 }
 cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream) {
