@@ -110,6 +110,18 @@ int wrenc_b200_get_consts(const wrenc_b200 *h, wrenc_b200_consts *out);
 int wrenc_b200_derive_consts(int32_t qp, const char *extra_params, wrenc_b200_consts *out, int64_t *hdr_single, int64_t *hdr_dual,
                              int64_t *hdr_chroma);
 
+/* Byte-stream NAL unit as write_byte_stream_nal_unit_bins writes it (src/nal.rs:210-299; pure host code, no GPU): three
+ * zero bytes, the start code prefix 00 00 01 (nal.rs:218-225), the two-byte NAL unit header (forbidden_zero_bit,
+ * nuh_reserved_zero_bit, nuh_layer_id u(6), nal_unit_type u(5), nuh_temporal_id_plus1 u(3); nal.rs:240-268), then the
+ * byte-aligned payload with the reference's emulation prevention: 00 00 0x (x <= 3) gets a 03 after the two zeros, but the
+ * scan only runs while idx + 3 < len, i.e. it never looks at the last three payload bytes (nal.rs:274-298).
+ * For a picture the payload is the slice header bits (byte-aligned, slice_encoder.rs:338-340) followed by the slice_data()
+ * bytes wrenc_b200_receive returns; the reference writes it with nuh_layer_id 9, IDR_W_RADL (7), temporal id 0
+ * (main.rs:383-389).  Returns the number of bytes written to out, or the (negated) number needed if cap is too small
+ * (nothing useful is written then), or WRENC_B200_EINVAL. */
+int64_t wrenc_b200_write_nal(int32_t nuh_layer_id, int32_t nal_unit_type, int32_t nuh_temporal_id, const uint8_t *payload, size_t len,
+                             uint8_t *out, size_t cap);
+
 /* Per-block entry points (host pointers): the block operations of the search, exposed for bit-exactness tests against
  * IntraPredictor::predict (src/intra_predictor.rs:56-144), Transformer::transform / inverse_transform
  * (src/transformer.rs:2040,2380), Quantizer::quantize / dequantize (src/quantizer.rs:519,761) and the rate walk of

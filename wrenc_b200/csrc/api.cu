@@ -457,6 +457,38 @@ size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n) {
     return (size_t)(h->W / 4) * (h->H / 4) * n + (size_t)h->Wc * h->Hc * n * 8 + sizeof(DevTables) + 4;
 }
 
+// nal.rs:210-299 (write_byte_stream_nal_unit_bins + write_nal_unit_bins), host only
+int64_t wrenc_b200_write_nal(int32_t nuh_layer_id, int32_t nal_unit_type, int32_t nuh_temporal_id, const uint8_t *payload, size_t len,
+                             uint8_t *out, size_t cap) {
+    if ((len && !payload) || nuh_layer_id < 0 || nuh_layer_id > 63 || nal_unit_type < 0 || nal_unit_type > 31 || nuh_temporal_id < 0 ||
+        nuh_temporal_id > 6)
+        return WRENC_B200_EINVAL;
+    // size first: every 00 00 0x found while idx + 3 < len costs one extra byte
+    size_t extra = 0;
+    for (size_t idx = 0; idx + 3 < len;) {
+        if (payload[idx] == 0 && payload[idx + 1] == 0 && payload[idx + 2] <= 3) { extra++; idx += 2; }
+        else idx++;
+    }
+    const size_t need = 6 + 2 + len + extra;
+    if (!out || cap < need) return -(int64_t)need;
+    size_t n = 0;
+    out[n++] = 0; out[n++] = 0; out[n++] = 0;   // "header_bytes" (nal.rs:218)
+    out[n++] = 0; out[n++] = 0; out[n++] = 1;   // start_code_prefix_one_3bytes
+    out[n++] = (uint8_t)(nuh_layer_id & 63);    // forbidden_zero_bit, nuh_reserved_zero_bit, nuh_layer_id
+    out[n++] = (uint8_t)((nal_unit_type << 3) | ((nuh_temporal_id + 1) & 7));
+    size_t idx = 0;
+    while (idx + 3 < len) {
+        if (payload[idx] == 0 && payload[idx + 1] == 0 && payload[idx + 2] <= 3) {
+            out[n++] = 0; out[n++] = 0; out[n++] = 3;  // the two zeros, then emulation_prevention_three_byte
+            idx += 2;
+        } else {
+            out[n++] = payload[idx++];
+        }
+    }
+    while (idx < len) out[n++] = payload[idx++];
+    return (int64_t)n;
+}
+
 int wrenc_b200_get_consts(const wrenc_b200 *h, wrenc_b200_consts *out) {
     if (!h || !out) return WRENC_B200_EINVAL;
     out->lambda_q = h->hc.lambda_q;

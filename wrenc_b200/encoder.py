@@ -23,7 +23,7 @@ EXPORTS = [
     "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident", "wrenc_b200_code_resident",
     "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
-    "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts",
+    "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts", "wrenc_b200_write_nal",
 ]
 
 
@@ -88,6 +88,8 @@ def load_library():
     L.wrenc_b200_block_quantize.restype = C.c_int
     L.wrenc_b200_block_quantize.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
     L.wrenc_b200_version.restype = C.c_char_p
+    L.wrenc_b200_write_nal.restype = C.c_int64
+    L.wrenc_b200_write_nal.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp, C.c_size_t]
     L.wrenc_b200_derive_consts.restype = C.c_int
     L.wrenc_b200_derive_consts.argtypes = [C.c_int32, C.c_char_p, C.POINTER(Consts), vp, vp, vp]
     L.wrenc_b200_measure_int32_peak.restype = C.c_int
@@ -103,6 +105,22 @@ def measure_int32_peak(device=0):
     if rc != 0:
         raise WrencB200Error(f"wrenc_b200_measure_int32_peak failed ({rc})")
     return v.value
+
+
+NAL_IDR_W_RADL, NAL_VPS, NAL_SPS, NAL_PPS, NAL_PH = 7, 14, 15, 16, 19  # nal.rs:10-42
+
+
+def write_nal(payload, nal_unit_type=NAL_IDR_W_RADL, nuh_layer_id=9, nuh_temporal_id=0):
+    """Byte-stream NAL unit around a byte-aligned payload (wrenc_b200_write_nal; host only).  For a picture the payload is
+    the reference's slice header bytes followed by the slice_data() this library returns (main.rs:383-389)."""
+    payload = bytes(payload)
+    src = (C.c_uint8 * max(1, len(payload))).from_buffer_copy(payload or b"\0")
+    cap = 8 + len(payload) + len(payload) // 2 + 1
+    out = (C.c_uint8 * cap)()
+    n = load_library().wrenc_b200_write_nal(int(nuh_layer_id), int(nal_unit_type), int(nuh_temporal_id), src, len(payload), out, cap)
+    if n < 0:
+        raise ValueError(f"wrenc_b200_write_nal failed ({n})")
+    return bytes(out[:n])
 
 
 def derive_consts(qp, extra_params=None):
