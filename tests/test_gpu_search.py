@@ -182,3 +182,24 @@ def test_full_size_decode_round_trip(W, H, qp, n):
             assert np.array_equal(d["records"][k], r["records"][k])
         mse = ((r["rec"][0].astype(float) - f[0]) ** 2).mean()
         assert 10 * np.log10(255 ** 2 / mse) > (30 if qp <= 27 else 28)
+
+
+def test_slice_coder_second_walk_path():
+    """The slice coder stages the first entries of every CTU's bin string and walks only longer strings a second time.  A
+    tiny staging slot (WRENC_B200_STAGE_CAP, read once per process, hence the subprocess) forces every CTU through the
+    second walk; the coded slice_data must not change."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = GOLD[0]
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import wrenc_b200\n"
+        "g = np.load(%r); H, W = g['y'].shape\n"
+        "enc = wrenc_b200.SearchEncoder(W, H, qp=int(g['qp']), max_split_depth=int(g['depth']), pictures_in_flight=2, extra_params=str(g['extra']) or None)\n"
+        "r = enc.encode_pictures([(g['y'], g['cb'], g['cr'])] * 2)\n"
+        "assert r[0]['slice_data'] == g['slice_data'].tobytes() and r[1]['slice_data'] == r[0]['slice_data'], 'slice_data differs'\n"
+        "print('ok', len(r[0]['slice_data']))\n" % (root, path))
+    for cap in ("8", "100000"):
+        env = dict(os.environ, WRENC_B200_STAGE_CAP=cap)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0 and out.stdout.startswith("ok"), f"stage cap {cap}: {out.stdout} {out.stderr[-400:]}"
