@@ -454,7 +454,9 @@ int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d
 
 size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n) {
     if (!h || n <= 0) return 0;
-    return (size_t)(h->W / 4) * (h->H / 4) * n + (size_t)h->Wc * h->Hc * n * 8 + sizeof(DevTables) + 4;
+    // mode map + done flags + work list per picture, the CTU scratch of the grid (independent of n), tables, counter
+    return (size_t)(h->W / 4) * (h->H / 4) * n + (size_t)h->Wc * h->Hc * n * 8 + (size_t)h->grid * search_ctus_per_cta() * CTU_SCRATCH_BYTES +
+           sizeof(DevTables) + 4;
 }
 
 // nal.rs:210-299 (write_byte_stream_nal_unit_bins + write_nal_unit_bins), host only
