@@ -868,8 +868,24 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
     }
     for (int m = tid; m < 68; m += NTHREADS) {
         const int ang = m < 67 ? c_angle[m] : 0;
+        const int inv = ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0);
         S.tb.ang[m] = (int8_t)ang;
-        S.tb.invang[m] = (int16_t)(ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0));
+        S.tb.invang[m] = (int16_t)inv;
+        for (int l2 = 2; l2 <= 5; l2++) {  // intra_predictor.rs:1342-1366 (filter choice), 355-420 (PDPC nScale)
+            unsigned ap = 0;
+            if (m >= 2 && m <= 66) {
+                if (!(m == 2 || m == 34 || m == 66)) {
+                    const int md = min(abs(m - 50), abs(m - 18));
+                    const int thr = l2 == 2 ? 24 : (l2 == 3 ? 14 : (l2 == 4 ? 2 : 0));
+                    if (md > thr) ap |= 1u;
+                }
+                if (m <= 18 || m >= 50) {
+                    const int ns = (m == 18 || m == 50) ? (2 * l2 - 2) >> 2 : min(l2 - ilog2i(3 * inv - 2) + 8, 2);
+                    if (ns >= 0) ap |= 8u | ((unsigned)ns << 1);
+                }
+            }
+            S.tb.angp[l2 - 2][m] = (uint8_t)ap;
+        }
     }
 }
 

@@ -83,6 +83,7 @@ struct Tables {
     int32_t fc[32];            // fC taps packed as 4 x int8
     int16_t invang[68];        // inverse angle per mode (sign of the angle kept; intra_predictor.rs:1330-1341)
     int8_t ang[68];            // intraPredAngle per mode
+    uint8_t angp[4][68];       // per block size (log2 - 2) and angular mode: bit 0 fG taps (luma), bits 1-2 PDPC nScale, bit 3 PDPC applies
 };
 
 struct WarpScratch {  // pointers into the scratch pool
@@ -549,19 +550,22 @@ __device__ __forceinline__ void pred_setup(const Ctx S, const CtuGeom g, const N
     __syncwarp();
 }
 
+// KIND >= 0: the caller has already branched on pc.kind (the per-sample loop then carries no dispatch)
+template <int KIND = -1>
 __device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x, int y) {
     const int n = pc.n;
+    const int kind = KIND >= 0 ? KIND : pc.kind;
     int p;
-    if (pc.kind == 3) {
+    if (kind == 3) {
         if (pc.cclm128) return 128;
         return clip8(((S.c->pds[y * n + x] * pc.a) >> pc.k) + pc.b);
     }
     const int16_t *lrs = pc.lf + 1, *ars = pc.ab;
-    if (pc.kind == 0) {
+    if (kind == 0) {
         int pv = (n - 1 - y) * ars[x] + (y + 1) * lrs[n];
         int ph = (n - 1 - x) * lrs[y] + (x + 1) * ars[n];
         p = ((pv + ph + n) >> (pc.l2 + 1)) & 255;
-    } else if (pc.kind == 1) {
+    } else if (kind == 1) {
         p = pc.dc;
     } else {
         int t = pc.vertical ? y : x, u = pc.vertical ? x : y;
@@ -625,16 +629,11 @@ __device__ __forceinline__ int ang_sample_direct(const Ctx S, int c, int n, int 
         const int f = (ang >= 0 || idx >= 0) ? min(idx, 2 * n) : -min((idx * inv + 256) >> 9, n);
         return e0[sg * f];
     };
+    const unsigned ap = S.tb->angp[l2 - 2][mode];  // mode / size dependent switches, tabulated once per CTA (init_tables)
     int p;
     if (c == 0) {
         int f0, f1, f2, f3;
-        bool use_fg = false;
-        if (!(mode == 2 || mode == 34 || mode == 66)) {
-            const int md = min(abs(mode - 50), abs(mode - 18));
-            const int thr = l2 == 2 ? 24 : (l2 == 3 ? 14 : (l2 == 4 ? 2 : 0));
-            use_fg = md > thr;
-        }
-        if (use_fg) {
+        if (ap & 1u) {
             const int h = ifact >> 1;
             f0 = 16 - h; f1 = 32 - h; f2 = 16 + h; f3 = h;
         } else {
@@ -647,27 +646,23 @@ __device__ __forceinline__ int ang_sample_direct(const Ctx S, int c, int n, int 
     } else {
         p = tap(base + 1) & 255;
     }
-    if (mode <= 18 || mode >= 50) {  // PDPC (intra_predictor.rs:355-757)
-        int ns;
-        if (mode == 18 || mode == 50) ns = (2 * l2 - 2) >> 2;
-        else ns = min(l2 - ilog2i(3 * inv - 2) + 8, 2);
-        if (ns >= 0) {
-            const int16_t *lrs = lf + 1, *ars = ab;
-            int refl = 0, reft = 0, wl = 0, wt = 0;
-            if (mode == 18 || mode == 50) {
-                const int corner = lf[0];
-                refl = lrs[y] - corner + p; reft = ars[x] - corner + p;
-                if (mode == 50) wl = pdpc_w(ns, x); else wt = pdpc_w(ns, y);
-            } else if (mode < 18) {
-                if (y < (3 << ns)) reft = ars[x + (((y + 1) * inv + 256) >> 9)];
-                wt = pdpc_w(ns, y);
-            } else {
-                if (x < (3 << ns)) refl = lrs[y + (((x + 1) * inv + 256) >> 9)];
-                wl = pdpc_w(ns, x);
-            }
-            const int v = (int16_t)(refl * wl + reft * wt + (64 - wt - wl) * p + 32);
-            p = clip8(v >> 6);
+    if (ap & 8u) {  // PDPC (intra_predictor.rs:355-757)
+        const int ns = (ap >> 1) & 3;
+        const int16_t *lrs = lf + 1, *ars = ab;
+        int refl = 0, reft = 0, wl = 0, wt = 0;
+        if (mode == 18 || mode == 50) {
+            const int corner = lf[0];
+            refl = lrs[y] - corner + p; reft = ars[x] - corner + p;
+            if (mode == 50) wl = pdpc_w(ns, x); else wt = pdpc_w(ns, y);
+        } else if (mode < 18) {
+            if (y < (3 << ns)) reft = ars[x + (((y + 1) * inv + 256) >> 9)];
+            wt = pdpc_w(ns, y);
+        } else {
+            if (x < (3 << ns)) refl = lrs[y + (((x + 1) * inv + 256) >> 9)];
+            wl = pdpc_w(ns, x);
         }
+        const int v = (int16_t)(refl * wl + reft * wt + (64 - wt - wl) * p + 32);
+        p = clip8(v >> 6);
     }
     return p;
 }
@@ -1182,12 +1177,22 @@ __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, con
     unsigned sad = 0;
     const uint8_t *org = cs ? S.c->orgC[c - 1] + by * 16 + bx : S.c->orgY + by * 32 + bx;  // source block, row stride 16 / 32
     const int osh = cs ? 4 : 5;
+    if (pc.kind == 2) {  // angular: most predictions (the 13 coarse + 4 refinement SADs, 3 of the 5 full evaluations)
 #pragma unroll 1
-    for (int i = lane; i < n * n; i += 32) {
-        int y = i >> l2, x = i & (n - 1);
-        int p = pred_sample(S, pc, x, y);
-        if (pred_out) pred_out[i] = (uint8_t)p;
-        sad += abs(p - (int)org[(y << osh) + x]);
+        for (int i = lane; i < n * n; i += 32) {
+            int y = i >> l2, x = i & (n - 1);
+            int p = pred_sample<2>(S, pc, x, y);
+            if (pred_out) pred_out[i] = (uint8_t)p;
+            sad += abs(p - (int)org[(y << osh) + x]);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < n * n; i += 32) {
+            int y = i >> l2, x = i & (n - 1);
+            int p = pred_sample(S, pc, x, y);
+            if (pred_out) pred_out[i] = (uint8_t)p;
+            sad += abs(p - (int)org[(y << osh) + x]);
+        }
     }
     return warp_sumu(sad);
 }
