@@ -866,6 +866,7 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
         for (int i = 0; i < 4; i++) pk |= ((unsigned)(uint8_t)c_fC[tid][i]) << (8 * i);
         S.tb.fc[tid] = (int)pk;
     }
+    if (tid == 0) S.tb.ls_recip = (uint32_t)(0x100000000ull / (unsigned long long)tab->ls) + 1u;
     for (int m = tid; m < 68; m += NTHREADS) {
         const int ang = m < 67 ? c_angle[m] : 0;
         const int inv = ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0);

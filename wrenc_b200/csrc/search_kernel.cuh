@@ -83,6 +83,7 @@ struct Tables {
     int32_t fc[32];            // fC taps packed as 4 x int8
     int16_t invang[68];        // inverse angle per mode (sign of the angle kept; intra_predictor.rs:1330-1341)
     int8_t ang[68];            // intraPredAngle per mode
+    uint32_t ls_recip;         // floor(2^32 / ls) + 1: the trellis divides by the (launch-constant) level scale, see div_ls
     uint8_t angp[4][68];       // per block size (log2 - 2) and angular mode: bit 0 fG taps (luma), bits 1-2 PDPC nScale, bit 3 PDPC applies
 };
 
@@ -820,6 +821,13 @@ __device__ __noinline__ void mm_cols_q(const int8_t *M, const int32_t *P, int16_
 // Next-state maps of the walk are kept as 4 bytes (byte s = next state of state s), so that composing two maps is one byte
 // permute: the selector of __byte_perm is the first map in nibble form.
 constexpr unsigned MAP_ID = 0x03020100u;
+// s / ls for s < 2^25 (|tc| << sh plus the rounding offset) without a division sequence: the estimate by the tabulated
+// reciprocal is floor(s / ls) or one more; one multiply-subtract decides.
+__device__ __forceinline__ unsigned div_ls(const Ctx S, unsigned s, unsigned ls) {
+    unsigned q = __umulhi(s, S.tb->ls_recip);
+    if ((int)(s - q * ls) < 0) q--;
+    return q;
+}
 __device__ __forceinline__ unsigned map_nib(unsigned m) { return __byte_perm(m | (m >> 4), 0u, 0x4420u); }  // bytes -> nibbles
 __device__ __forceinline__ unsigned map_compose(unsigned a, unsigned b) { return __byte_perm(b, 0u, map_nib(a)); }  // apply a first, then b
 
@@ -923,7 +931,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         unsigned x = 0, nz = tc != 0;
         if (nz) {
             unsigned s = tc > 0 ? ((unsigned)tc << sh) - (unsigned)off : ((unsigned)(-tc) << sh) + (unsigned)off;
-            x = min(s / (unsigned)ls, 2047u);
+            x = min(div_ls(S, s, (unsigned)ls), 2047u);
             anytc = true;
             if (x >= 2) kstar = k;
         }
@@ -978,7 +986,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
         Lf0 = Cs[0]; Lf1 = Cs[1]; Lf2 = Cs[2]; Lf3 = Cs[3];
     }
     const bool tiny = nn == 16;  // 4x4 TBs (the most numerous): one position per lane, plain sequential pass over 15 steps
-    const int CS = tiny ? 1 : (nn >= 1024 ? 16 : (nn >= 256 ? 8 : 4)), nch = nn / CS, rounds = (nch + 31) >> 5;
+    const int csl = tiny ? 0 : (nn >= 1024 ? 4 : (nn >= 256 ? 3 : 2)), CS = 1 << csl, nch = nn >> csl, rounds = (nch + 31) >> 5;
     int carry0 = 0, carry1 = 0, carry2 = 0, carry3 = 0;
     unsigned cm0 = MAP_ID, cm1 = MAP_ID;  // walk map of this lane's chunk in round 0 / 1
     if (tiny) {
@@ -1342,7 +1350,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
     const unsigned nz = tc != 0;
     if (nz) {
         const unsigned sc = tc > 0 ? ((unsigned)tc << sh) - (unsigned)off : ((unsigned)(-tc) << sh) + (unsigned)off;
-        xq = min(sc / (unsigned)ls, 2047u);
+        xq = min(div_ls(S, sc, (unsigned)ls), 2047u);
     }
     const unsigned w = xq | (nz << 11);
     const unsigned bstar = (__ballot_sync(hm, xq >= 2) >> hb) & 0xffffu;
