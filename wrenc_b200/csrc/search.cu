@@ -481,6 +481,17 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
         CtuCtx &C = *V.c;
         const Node nd = unpack_node(C.node);
         int dir = C.dir;
+        // 4x4 CU: fetch the five candidate slots (16 samples each, two slots per warp load) while the candidates are priced,
+        // so that the commit below does not wait for an L2 round trip after the decision
+        int pr0 = 0, pr1 = 0, pr2 = 0, pl0 = 0, pl1 = 0, pl2 = 0;
+        if (cu4) {
+            const int h = lane >> 4, i = lane & 15;
+            const uint8_t *gr = C.groot + h * ROOT_SLOT_SAMPLES + i;
+            const int16_t *gv = reinterpret_cast<const int16_t *>(C.groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + h * ROOT_SLOT_SAMPLES + i;
+            pr0 = __ldcg(gr); pl0 = __ldcg(gv);
+            pr1 = __ldcg(gr + 2 * ROOT_SLOT_SAMPLES); pl1 = __ldcg(gv + 2 * ROOT_SLOT_SAMPLES);
+            if (h == 0) { pr2 = __ldcg(gr + 4 * ROOT_SLOT_SAMPLES); pl2 = __ldcg(gv + 4 * ROOT_SLOT_SAMPLES); }
+        }
         // lane j < 5 prices candidate j: planar, DC, dir, dir-1, dir+1 (block_splitter.rs:472-473)
         float cost = FLT_MAX;
         if (lane < 5) {
@@ -518,7 +529,17 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
         }
         // the winner's luma and same-mode (DM) chroma were evaluated in phase B or C: copy them out of the slot
         const int slot = mode <= 1 ? mode : 2 + dir_cand;
-        for (int t = 0; t < ncomp; t++) commit_slot(V, nd, t, slot, lane);
+        if (cu4) {
+            const int rs = slot >> 1, i = lane & 15;
+            const int r = rs == 0 ? pr0 : (rs == 1 ? pr1 : pr2), l = rs == 0 ? pl0 : (rs == 1 ? pl1 : pl2);
+            if ((lane >> 4) == (slot & 1)) {
+                RY(V, nd.x + (i & 3), nd.y + (i >> 2)) = (uint8_t)r;
+                C.lvY[(nd.y + (i >> 2)) * 32 + nd.x + (i & 3)] = (int16_t)l;
+            }
+            __syncwarp();
+        } else {
+            for (int t = 0; t < ncomp; t++) commit_slot(V, nd, t, slot, lane);
+        }
         if (!cu4 && lane < 3) {
             const int t = lane;
             if (mode <= 1) { C.fin_ssd[t] = C.pd_ssd[mode][t]; C.fin_rate[t] = C.pd_rate[mode][t]; }
@@ -554,6 +575,12 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
         Ctx V{&S.tb, &S.c[k]};
         CtuCtx &C = *V.c;
         const Node nd = unpack_node(C.node);
+        // fetch the CCLM evaluation's slot (Cb | Cr, 16 samples each) while the costs are computed: the commit below then does not
+        // wait for an L2 round trip after the decision
+        const int pc_ = 1 + (lane >> 4), pi_ = lane & 15;
+        const int pso_ = 5 * ROOT_SLOT_SAMPLES + (pc_ == 1 ? 1024 : 1280) + pi_;
+        const int prec_ = __ldcg(C.groot + pso_);
+        const int plev_ = __ldcg(reinterpret_cast<const int16_t *>(C.groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + pso_);
         const unsigned ssdY = C.fin_ssd[0], ssdDM = C.fin_ssd[1] + C.fin_ssd[2];
         const long long rateY = C.fin_rate[0], rateDM = (long long)C.fin_rate[1] + C.fin_rate[2];
         const float cost_dm = rd_cost(ssdDM, rateDM + tab->hdr_chroma[0], tab->lambda_rd_c);
@@ -570,8 +597,10 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
                                     : rd_cost(ssdY + ssdDM, rateY + rateDM + luma_hdr(V, tab, nd, mode, 0), tab->lambda_rd);
         }
         if (cclm_wins) {  // evaluated in phase E with unchanged inputs: copy it out of its slot
-            commit_slot(V, nd, 1, 5, lane);
-            commit_slot(V, nd, 2, 5, lane);
+            const int bx_ = nd.x >> 1, by_ = nd.y >> 1;
+            RC(V, pc_, bx_ + (pi_ & 3), by_ + (pi_ >> 2)) = (uint8_t)prec_;
+            C.lvC[pc_ - 1][(by_ + (pi_ >> 2)) * 16 + bx_ + (pi_ & 3)] = (int16_t)plev_;
+            __syncwarp();
         }
         fill_cm(V, nd, cclm_wins ? cclm_mode : mode, lane);
     }
@@ -636,6 +665,12 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
         Ctx V{&S.tb, &S.c[k]};
         CtuCtx &C = *V.c;
         const Node nd = unpack_node(C.node);
+        // fetch the CCLM evaluation's slot (Cb | Cr, 16 samples each) while the costs are computed: the commit below then does not
+        // wait for an L2 round trip after the decision
+        const int pc_ = 1 + (lane >> 4), pi_ = lane & 15;
+        const int pso_ = 5 * ROOT_SLOT_SAMPLES + (pc_ == 1 ? 1024 : 1280) + pi_;
+        const int prec_ = __ldcg(C.groot + pso_);
+        const int plev_ = __ldcg(reinterpret_cast<const int16_t *>(C.groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + pso_);
         const int cclm_mode = C.cclm_mode;
         const float cost_dm = rd_cost(C.r_ssd[0] + C.r_ssd[1], (long long)C.r_rate[0] + C.r_rate[1] + tab->hdr_chroma[0], tab->lambda_rd_c);
         const int ck = 1 + (cclm_mode - MODE_LT_CCLM);
@@ -650,8 +685,10 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
             C.split[2] = __fadd_rn(C.split[2], mn);
         }
         if (cclm_wins) {  // evaluated in phase C with unchanged inputs (CCLM reads the luma and the neighbours outside the block)
-            commit_slot(V, nd, 1, 5, lane);
-            commit_slot(V, nd, 2, 5, lane);
+            const int bx_ = nd.x >> 1, by_ = nd.y >> 1;
+            RC(V, pc_, bx_ + (pi_ & 3), by_ + (pi_ >> 2)) = (uint8_t)prec_;
+            C.lvC[pc_ - 1][(by_ + (pi_ >> 2)) * 16 + bx_ + (pi_ & 3)] = (int16_t)plev_;
+            __syncwarp();
         }
         fill_cm(V, nd, cclm_wins ? cclm_mode : dm, lane);
     }
