@@ -36,7 +36,7 @@ W, H, QP, DEPTH = 1920, 1088, 32, 3
 CTUS_PER_FRAME = (W // 32) * (H // 32)
 OPS_PER_CTU = 8290304          # SURVEY.md §8(d) nominal integer ops per CTU (transforms 4 358 144 + trellis 3 932 160)
 ALG_BYTES_PER_CTU = 1536 + 1536 + 3072 + 88   # source read + recon write + level write + record
-NCU_DRAM_BYTES_PER_CTU = 33620  # dram__bytes_read.sum + dram__bytes_write.sum per CTU of the committed ncu --set full capture (profiles/)
+NCU_DRAM_BYTES_PER_CTU = 32770  # dram__bytes_read.sum + dram__bytes_write.sum per CTU of the committed ncu --set full capture (profiles/)
 METRIC = "1080p all-intra frames/s (RD search + CABAC slice_data, byte-identical vs oracle)"
 UNIT = "frames/s"
 
