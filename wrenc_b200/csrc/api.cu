@@ -116,13 +116,21 @@ static int ensure_items(wrenc_b200 *h, int n_pics) {
     // depend on each other, so a batch never crosses a level boundary; short levels leave empty slots.
     const int KC = search_ctus_per_cta();
     std::vector<uint32_t> items;
-    items.reserve(v.size() + (size_t)KC * (Wc + 2 * Hc + n_pics));
+    items.reserve(v.size() + (size_t)KC * ((size_t)(Wc + 2 * Hc + n_pics) + (size_t)h->grid * 64));
+    // A level too short to give every CTA a full batch (the ramps of the wavefront) is spread over as many batches as there
+    // are CTAs: a batch with fewer active CTUs has fewer tasks per phase and finishes sooner.
     for (size_t i = 0; i < v.size();) {
-        size_t j = i;
-        while (j < v.size() && j - i < (size_t)KC && v[j].key == v[i].key) j++;
-        for (size_t q = i; q < j; q++) items.push_back(((uint32_t)v[q].pic << 16) | ((uint32_t)v[q].cy << 8) | (uint32_t)v[q].cx);
-        for (size_t q = j - i; q < (size_t)KC; q++) items.push_back(0xffffffffu);
-        i = j;
+        size_t e = i;
+        while (e < v.size() && v[e].key == v[i].key) e++;
+        const size_t n = e - i;
+        size_t nb = (n + KC - 1) / KC;
+        if (nb < (size_t)h->grid) nb = std::min((size_t)h->grid, n);
+        for (size_t b = 0; b < nb; b++) {
+            const size_t lo = i + n * b / nb, hi = i + n * (b + 1) / nb;  // hi - lo <= KC because nb >= n / KC
+            for (size_t q = lo; q < hi; q++) items.push_back(((uint32_t)v[q].pic << 16) | ((uint32_t)v[q].cy << 8) | (uint32_t)v[q].cx);
+            for (size_t q = hi - lo; q < (size_t)KC; q++) items.push_back(0xffffffffu);
+        }
+        i = e;
     }
     if (items.size() > h->items_cap) {
         cudaFree(h->d_items);
