@@ -1039,12 +1039,15 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
                     sep_head = k == 0 || (l.pk & 4u);
                     if (sep_head) continue;
                 }
+                // new state 0 = min(a00 + old 0, a02 + old 2), state 1 = min(a10 + old 0, a12 + old 2), states 2, 3 from old 1, 3:
+                // which candidate each old state feeds depends on the parity of a0 (selected once per position, not per column)
+                const bool p0 = l.pk & 1, p1 = l.pk & 2;
+                const int a00 = p0 ? l.L10 : l.L0s0, a02 = p0 ? l.L0s0 : l.L10, a10 = p0 ? l.L00 : l.L10, a12 = p0 ? l.L10 : l.L00;
+                const int a21 = p1 ? l.L11 : l.L01, a23 = p1 ? l.L01 : l.L11, a31 = p1 ? l.L01 : l.L11, a33 = p1 ? l.L11 : l.L01;
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
-                    int X = (l.pk & 1) ? M[2][t] : M[0][t], Y = (l.pk & 1) ? M[0][t] : M[2][t];
-                    const int n0 = min(l.L0s0 + X, l.L10 + Y), n1 = min(l.L00 + Y, l.L10 + X);
-                    X = (l.pk & 2) ? M[3][t] : M[1][t]; Y = (l.pk & 2) ? M[1][t] : M[3][t];
-                    const int n2 = min(l.L01 + X, l.L11 + Y), n3 = min(l.L01 + Y, l.L11 + X);
+                    const int n0 = min(a00 + M[0][t], a02 + M[2][t]), n1 = min(a10 + M[0][t], a12 + M[2][t]);
+                    const int n2 = min(a21 + M[1][t], a23 + M[3][t]), n3 = min(a31 + M[1][t], a33 + M[3][t]);
                     M[0][t] = n0; M[1][t] = n1; M[2][t] = n2; M[3][t] = n3;
                 }
             }
@@ -1257,7 +1260,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     if (slot >= 0) {
         gRec = S.c->groot + slot * ROOT_SLOT_SAMPLES + soff;
         int16_t *gLv = reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + slot * ROOT_SLOT_SAMPLES + soff;
-        for (int i = lane; i < nn; i += 32) gLv[i] = B[i];
+        for (int i = lane; i < nn / 2; i += 32) reinterpret_cast<uint32_t *>(gLv)[i] = reinterpret_cast<const uint32_t *>(B)[i];  // two levels per store
     }
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
