@@ -30,6 +30,13 @@ namespace wb {
 #ifndef WB_MINB
 #define WB_MINB 1
 #endif
+#ifndef WB_U5
+#define WB_U5 5  // unroll of the 15-step state-per-lane pass of full_pair4
+#endif
+#ifndef WB_U2
+#define WB_U2 1  // unroll of the dp2a inner loops (measured: 1 beats 2 by 0.8 %, code size)
+#endif
+constexpr int U5 = WB_U5, U2 = WB_U2;
 constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
 #ifndef WB_K
@@ -772,7 +779,7 @@ __device__ __noinline__ void mm_rows_q(const int32_t *Q, const int16_t *in, void
         const int2 *r0 = reinterpret_cast<const int2 *>(in + (2 * yp) * n), *r1 = reinterpret_cast<const int2 *>(in + (2 * yp + 1) * n);
         const int32_t *q = Q + i;
         int s0 = 0, s1 = 0;
-#pragma unroll 2
+#pragma unroll U2
         for (int x4 = 0; x4 < nq; x4++) {
             const int w = q[x4 * n];
             const int2 a = r0[x4], b = r1[x4];
@@ -798,7 +805,7 @@ __device__ __noinline__ void mm_cols_q(const int8_t *M, const int32_t *P, int16_
         const int32_t *m0 = reinterpret_cast<const int32_t *>(M + (2 * ip) * n), *m1 = reinterpret_cast<const int32_t *>(M + (2 * ip + 1) * n);
         const int32_t *pp = P + x;
         int s0 = 0, s1 = 0;
-#pragma unroll 2
+#pragma unroll U2
         for (int y4 = 0; y4 < nq; y4++) {
             const int w0 = m0[y4], w1 = m1[y4];
             const int p0 = pp[(2 * y4) * n], p1 = pp[(2 * y4 + 1) * n];
@@ -1410,7 +1417,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
             const int srcP = hb + (s >> 1), srcQ = srcP + 2;
             const unsigned msw = (s < 2 ? m1 : m2) ^ ((s & 1) ? 0xffffu : 0u);
             const int *tp = tbl + 2 * s;
-#pragma unroll 5
+#pragma unroll U5
             for (int j = 1; j < 16; j++) {
                 const int La = tp[8 * j], Lb = tp[8 * j + 1];
                 const int P = __shfl_sync(m4, C, srcP), Q = __shfl_sync(m4, C, srcQ);
