@@ -65,6 +65,10 @@ const char *wrenc_b200_last_error(const wrenc_b200 *h); /* h may be NULL: error 
 
 /* Host planes, tightly packed I420 as main.rs:320-349 reads them. */
 int wrenc_b200_submit(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
+/* The same for planes that already lie in page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. the buffer the YUV
+ * reader fills): no staging copy, the planes are read by the copy engine asynchronously and must stay valid and unchanged
+ * until the picture has been received.  WRENC_B200_EINVAL if a plane is not page-locked. */
+int wrenc_b200_submit_pinned(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
 /* Strictly in submit order.  Launches the pending batch if it has not run yet, then blocks until the picture is ready.
  * slice_data/len: CABAC-coded slice_data() bytes of the picture (byte aligned, ends with rbsp stop bit + alignment zeros).
  * rec_*: reconstructed planes (NULL unless want_recon). Any out pointer may be NULL. */

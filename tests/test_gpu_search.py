@@ -203,3 +203,21 @@ def test_slice_coder_second_walk_path():
         env = dict(os.environ, WRENC_B200_STAGE_CAP=cap)
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0 and out.stdout.startswith("ok"), f"stage cap {cap}: {out.stdout} {out.stderr[-400:]}"
+
+
+def test_submit_pinned_matches_submit_and_rejects_pageable_memory():
+    import torch
+    W, H, qp = 96, 64, 32
+    frames = [wrenc_b200.synth_frame(W, H, frame=f) for f in range(3)]
+    enc = wrenc_b200.SearchEncoder(W, H, qp=qp, max_split_depth=3, pictures_in_flight=3)
+    ref = enc.encode_pictures(frames)
+    pinned = [torch.from_numpy(np.concatenate([a.ravel() for a in f])).pin_memory() for f in frames]
+    for i, t in enumerate(pinned):
+        a = t.numpy()
+        enc.submit(i, a[:W * H].reshape(H, W), a[W * H:W * H * 5 // 4].reshape(H // 2, W // 2), a[W * H * 5 // 4:].reshape(H // 2, W // 2), pinned=True)
+    got = [enc.receive() for _ in range(3)]
+    for o, r in zip(ref, got):
+        assert_same(o, r, "submit_pinned")
+    with pytest.raises(wrenc_b200.WrencB200Error):
+        enc.submit(0, *frames[0], pinned=True)  # pageable numpy memory
+    enc.close()

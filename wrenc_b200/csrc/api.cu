@@ -343,6 +343,34 @@ int wrenc_b200_submit(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const u
     return WRENC_B200_OK;
 }
 
+int wrenc_b200_submit_pinned(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr) {
+    if (!h || !y || !cb || !cr) return WRENC_B200_EINVAL;
+    int rc = ensure_batch_buffers(h);
+    if (rc) return rc;
+    if (h->launched || h->n_filled >= h->B) {
+        h->err = "pictures_in_flight pictures are pending; call wrenc_b200_receive first";
+        return WRENC_B200_EFULL;
+    }
+    CK(cudaSetDevice(h->cfg.device));
+    const uint8_t *src[3] = {y, cb, cr};
+    for (int i = 0; i < 3; i++) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, src[i]) != cudaSuccess || a.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            h->err = "wrenc_b200_submit_pinned: plane is not in page-locked host memory";
+            return WRENC_B200_EINVAL;
+        }
+    }
+    const size_t ps = h->pic_samples, ny = (size_t)h->W * h->H, nc = ny / 4;
+    uint8_t *dst = h->d_orig + (size_t)h->n_filled * ps;
+    CK(cudaMemcpyAsync(dst, y, ny, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dst + ny, cb, nc, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dst + ny + nc, cr, nc, cudaMemcpyHostToDevice, h->stream));
+    h->pic_ids[h->n_filled] = pic_idx;
+    h->n_filled++;
+    return WRENC_B200_OK;
+}
+
 int wrenc_b200_flush(wrenc_b200 *h) {
     if (!h) return WRENC_B200_EINVAL;
     if (h->launched || h->n_filled == 0) return WRENC_B200_OK;

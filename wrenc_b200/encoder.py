@@ -19,7 +19,7 @@ SINGLE_TREE, DUAL_TREE_LUMA, DUAL_TREE_CHROMA = 0, 1, 2
 MODE_LT_CCLM, MODE_L_CCLM, MODE_T_CCLM = 81, 82, 83
 
 EXPORTS = [
-    "wrenc_b200_create", "wrenc_b200_destroy", "wrenc_b200_last_error", "wrenc_b200_submit", "wrenc_b200_receive",
+    "wrenc_b200_create", "wrenc_b200_destroy", "wrenc_b200_last_error", "wrenc_b200_submit", "wrenc_b200_submit_pinned", "wrenc_b200_receive",
     "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident", "wrenc_b200_code_resident",
     "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
@@ -63,6 +63,8 @@ def load_library():
     L.wrenc_b200_last_error.argtypes = [vp]
     L.wrenc_b200_submit.restype = C.c_int
     L.wrenc_b200_submit.argtypes = [vp, C.c_uint64, u8p, u8p, u8p]
+    L.wrenc_b200_submit_pinned.restype = C.c_int
+    L.wrenc_b200_submit_pinned.argtypes = [vp, C.c_uint64, u8p, u8p, u8p]
     L.wrenc_b200_receive.restype = C.c_int
     L.wrenc_b200_receive.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.wrenc_b200_decisions.restype = C.c_int
@@ -179,10 +181,13 @@ class SearchEncoder:
                     lv=np.array(list(c.lv), np.int64), dq=np.array(list(c.dq), np.int64))
 
     # ---- host-plane path (the reference-facing call) ----
-    def submit(self, pic_idx, y, cb, cr):
+    def submit(self, pic_idx, y, cb, cr, pinned=False):
+        """pinned=True: the planes lie in page-locked host memory (e.g. views of a torch pin_memory() tensor) and stay valid
+        until the picture is received: wrenc_b200_submit_pinned, no staging copy."""
         y, cb, cr = (np.ascontiguousarray(a, np.uint8) for a in (y, cb, cr))
         assert y.shape == (self.height, self.width) and cb.shape == (self.height // 2, self.width // 2) and cr.shape == cb.shape
-        self._check(self.L.wrenc_b200_submit(self.h, int(pic_idx), _ptr(y), _ptr(cb), _ptr(cr)))
+        fn = self.L.wrenc_b200_submit_pinned if pinned else self.L.wrenc_b200_submit
+        self._check(fn(self.h, int(pic_idx), _ptr(y), _ptr(cb), _ptr(cr)))
 
     def pending(self):
         return self.L.wrenc_b200_pending(self.h)
