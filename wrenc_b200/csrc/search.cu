@@ -27,8 +27,9 @@ __device__ unsigned long long g_prof[128];
 //
 // The search is exhaustive (no early termination), so every CTU walks the same node sequence; only the data-dependent
 // decisions differ.  A CTA therefore runs the phases of KC CTUs together: the task list of a phase is the union of the
-// CTUs' tasks (t-major, so the large luma tasks are listed first and land on the warps that own large scratch), and the
-// decision after a phase is taken by one thread per CTU (thread k for CTU k) and published through shared memory.
+// CTUs' tasks (t-major, so the long tasks are listed first), and the decision after a phase is taken by one thread per CTU
+// (32x32 / 16x16 CUs, leaf_eval) or by one warp per CTU together with the follow-up work (CUs up to 8x8, small_eval) and
+// published through shared memory.
 // ---------------------------------------------------------------------------------------------------------------
 struct NodeId {
     int depth, a, b, c;  // position in the quad tree: child indices at depth 1, 2, 3

@@ -1,20 +1,22 @@
-// search_kernel.cuh — the all-intra RD search of one CTU per CTA, hand-written for sm_100a.
+// search_kernel.cuh — the all-intra RD search of wrenc's CTUs, hand-written for sm_100a: block functions (one warp or half a
+// warp per block) and the shared-memory layout.  The phase control that drives them is in search.cu.
 //
 // What it computes (reference file:line, all under /root/reference/src):
 //   split_ct quad-tree RD decision 32->16->8->4 (+ local dual-tree chroma CT)      block_splitter.rs:782-1154
 //   leaf evaluation: 15 coarse modes, SAD step search, 3 RD evals, chroma DM vs CCLM  block_splitter.rs:886-1078, 794-885
 //   full evaluation (predict, fwd DCT, dep-quant trellis, dequant, inv DCT, recon, SSD, rate)  block_splitter.rs:110-474,524-780
 //   intra prediction incl. reference substitution/filter, PDPC, CCLM                intra_predictor.rs:56-2055
-//   DCT-II 4..32 by matrix multiply                                                 transformer.rs:2040-2378,2380-2737
+//   DCT-II 4..32 by matrix multiply (dp2a)                                          transformer.rs:2040-2378,2380-2737
 //   dependent quantisation (memoised DFS == Viterbi with first-visit flags, H2/H3)  quantizer.rs:338-759, dequantize 761-1079
 //   MPM derivation for the mode-bit estimate (H1: in-CTU neighbours see the root CU) ctu.rs:1498-1635
 //
-// Execution model: a persistent grid; each CTA (8 warps) pulls CTUs from a work list sorted in wavefront order
-// (key = x + 2y + stagger*picture), waits on the left and above-right CTU's done flags, stages the CTU's source and the
-// neighbouring reconstruction in shared memory, and runs the whole tree search there.  Inside a CTU the candidates of one
-// decision phase are independent tasks, one warp each; the decision itself is recomputed redundantly by every thread from
-// the task results in shared memory (uniform control flow, no broadcast needed).  All arithmetic is exact integer except the
-// RD cost, which is IEEE f32 with explicit _rn intrinsics (no FMA contraction) in the reference's operation order.
+// Execution model: a persistent grid, one CTA of WB_NW warps per SM; each CTA pulls batches of WB_K
+// mutually independent CTUs from a work list sorted in wavefront order (key = x + 2y, all pictures in lock step), waits on
+// the left and above-right CTU's done flags, stages the CTUs' source (TMA) and neighbouring reconstruction in shared memory
+// and runs the whole tree search of the batch there in lock step.  The candidates of one decision phase are independent
+// tasks, one warp (4x4 TBs: half a warp) each.  What is written once and read back at most once (candidate slots, saved
+// no-split states) lives in a per-CTA global scratch.  All arithmetic is exact integer except the RD cost, which is IEEE f32
+// with explicit _rn intrinsics (no FMA contraction) in the reference's operation order.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
