@@ -435,7 +435,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
             full_task(V, tab, V.c->g, nd, 0, t, false, ws, lane, ssd, rate, t);
             if (lane == 0) { V.c->pd_ssd[t][0] = ssd; V.c->pd_rate[t][0] = rate; }
         } else if (t < (cu4 ? 0 : 2) + nparts) {
-            dir_search_part(V, nd, t - (cu4 ? 0 : 2), nparts, lane);
+            dir_search_part(V, nd, nparts - 1 - (t - (cu4 ? 0 : 2)), nparts, lane);  // the last part is the longest: it goes first
         } else {  // 4x4 TBs: planar | DC of the luma CU, or Cb | Cr of one mode
             const int half = lane >> 4;
             const int mode = cu4 ? half : t - (2 + nparts), c = cu4 ? 0 : 1 + half;
@@ -998,10 +998,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
                 C.groot = P.root_slots + ((size_t)blockIdx.x * KC + tid) * CTU_SCRATCH_BYTES;
                 C.gsave = C.groot + ROOT_SLOT_BYTES;
                 int *done = P.done + (size_t)C.pic * Wc * P.Hc;
-                if (C.cxi > 0) while (ld_relaxed(&done[C.cyi * Wc + C.cxi - 1]) != P.epoch) __nanosleep(1000);
+                if (C.cxi > 0) while (ld_relaxed(&done[C.cyi * Wc + C.cxi - 1]) != P.epoch) __nanosleep(200);
                 if (C.cyi > 0) {
                     const int ax = min(C.cxi + 1, Wc - 1);
-                    while (ld_relaxed(&done[(C.cyi - 1) * Wc + ax]) != P.epoch) __nanosleep(1000);
+                    while (ld_relaxed(&done[(C.cyi - 1) * Wc + ax]) != P.epoch) __nanosleep(200);
                 }
             }
             __threadfence();  // acquire side: order the halo loads after the flag observation
