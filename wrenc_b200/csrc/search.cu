@@ -170,7 +170,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
                     if (t < 2) { mode = t; c = 0; }
                     else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
                     unsigned ssd; int rate;
-                    full_task(V, tab, V.c->g, nd, c, mode, false, ws, lane, ssd, rate, sb + mode);
+                    full_task(V, tab, V.c->g, nd, c, mode, ws, lane, ssd, rate, sb + mode);
                     if (lane == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
                 } else {
                     int u = t - nfull;
@@ -246,7 +246,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int dir = V.c->dir;
             int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, false, ws, lane, ssd, rate, sb + 2 + cand);
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, ws, lane, ssd, rate, sb + 2 + cand);
             if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
         }
     }
@@ -347,7 +347,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
             const int k = tt % KC, t = tt / KC;
             Ctx V{&S.tb, &S.c[k]};
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, false, ws, lane, ssd, rate, sb + 5);
+            full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, ws, lane, ssd, rate, sb + 5);
             if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
         }
     __syncthreads();
@@ -432,7 +432,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
         const Node nd = unpack_node(V.c->node);
         if (!cu4 && t < 2) {  // 8x8 luma planar, DC
             unsigned ssd; int rate;
-            full_task(V, tab, V.c->g, nd, 0, t, false, ws, lane, ssd, rate, t);
+            full_task(V, tab, V.c->g, nd, 0, t, ws, lane, ssd, rate, t);
             if (lane == 0) { V.c->pd_ssd[t][0] = ssd; V.c->pd_rate[t][0] = rate; }
         } else if (t < (cu4 ? 0 : 2) + nparts) {
             dir_search_part(V, nd, nparts - 1 - (t - (cu4 ? 0 : 2)), nparts, lane);  // the last part is the longest: it goes first
@@ -457,7 +457,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
             const bool valid = t == 0 || (t == 1 ? V.c->v0 : V.c->v1);
             if (valid) {
                 unsigned ssd; int rate;
-                full_task(V, tab, V.c->g, nd, 0, t == 0 ? dir : (t == 1 ? dir - 1 : dir + 1), false, ws, lane, ssd, rate, 2 + t);
+                full_task(V, tab, V.c->g, nd, 0, t == 0 ? dir : (t == 1 ? dir - 1 : dir + 1), ws, lane, ssd, rate, 2 + t);
                 if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
             }
         } else {

@@ -1222,10 +1222,10 @@ __device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const
     return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane);
 }
 
-// full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.
-// commit: write reconstruction into the CTU window and levels into the CTU level arrays (the state split_ct leaves behind).
-__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit,
-                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out, int slot = -1) {
+// full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.  The outcome (reconstruction, levels)
+// goes to candidate slot `slot` of the CTU's global scratch; the winner is committed from there (commit_slot).
+__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode,
+                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out, int slot) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
@@ -1254,14 +1254,6 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     } else {
         for (int i = lane; i < nn; i += 32) B[i] = 0;
         __syncwarp();
-    }
-    if (commit) {
-        int16_t *dst = c == 0 ? S.c->lvY : S.c->lvC[c - 1];
-        const int stride = c == 0 ? 32 : 16;
-        for (int i = lane; i < nn; i += 32) {
-            int y = i >> l2, x = i & (n - 1);
-            dst[(by + y) * stride + bx + x] = B[i];
-        }
     }
     // candidate slot (planar, DC, dir, dir-1, dir+1, CCLM): the evaluation's outcome goes to the CTU's global scratch, block-local raster
     const int soff = c == 0 ? 0 : (c == 1 ? 1024 : 1280);
@@ -1296,10 +1288,6 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         int rec = clip8((int)(int16_t)((int)ws.pred[i] + res));
         int d = rec - (int)org[(y << osh) + x];
         ssd += (unsigned)(d * d);
-        if (commit) {
-            if (c == 0) RY(S, bx + x, by + y) = (uint8_t)rec;
-            else RC(S, c, bx + x, by + y) = (uint8_t)rec;
-        }
         if (slot >= 0) gRec[i] = (uint8_t)rec;
     }
     ssd_out = warp_sumu(ssd);
