@@ -311,37 +311,21 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 8);
     WB_NEXT_PHASE();
-    // ---- phase 5b: CCLM down-sampled luma of the committed luma reconstruction
+    // ---- phases 5b + 6: CCLM down-sampled luma of the committed luma reconstruction, then the CCLM mode by SAD (order LT,
+    //      T, L), both by one warp per CTU
     nst = 0;
     WB_FOR_TASKS(1) {
         const int k = tt % KC;
         Ctx V{&S.tb, &S.c[k]};
-        cclm_downsample(V, V.c->g, unpack_node(V.c->node), lane);
-    }
-    __syncthreads();
-    WB_PROF(pk_ + 9);
-    WB_NEXT_PHASE();
-    // ---- phase 6: CCLM SADs in the order LT, T, L
-    WB_FOR_TASKS(6) {
-        const int k = tt % KC, t = tt / KC;
-        Ctx V{&S.tb, &S.c[k]};
-        const int mi = t >> 1, c = 1 + (t & 1);
-        const int cm = mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM);
-        unsigned sad = sad_task(V, V.c->g, unpack_node(V.c->node), c, cm, ws, lane);
-        if (lane == 0) V.c->r_sad[t] = sad;
+        const Node nd = unpack_node(V.c->node);
+        cclm_downsample(V, V.c->g, nd, lane);
+        __syncwarp();
+        const int cm = cclm_search(V, V.c->g, nd, lane);
+        if (lane == 0) V.c->cclm_mode = cm;
     }
     __syncthreads();
     WB_PROF(pk_ + 10);
     WB_NEXT_PHASE();
-    if (tid < KC && S.c[tid].active) {
-        CtuCtx &C = S.c[tid];
-        float lt = __uint2float_rn(C.r_sad[0] + C.r_sad[1]), t = __uint2float_rn(C.r_sad[2] + C.r_sad[3]), l = __uint2float_rn(C.r_sad[4] + C.r_sad[5]);
-        if (lt <= t && lt <= l) C.cclm_mode = MODE_LT_CCLM;
-        else if (t <= l) C.cclm_mode = MODE_T_CCLM;
-        else C.cclm_mode = MODE_L_CCLM;
-    }
-    __syncthreads();
-    WB_PROF(pk_ + 11);
     // ---- phase 7: CCLM full evaluation (no commit)
         WB_FOR_TASKS(2) {
             const int k = tt % KC, t = tt / KC;
@@ -551,7 +535,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
             __syncwarp();
             cclm_downsample(V, C.g, nd, lane);
             __syncwarp();
-            const int cm = cclm_search4(V, C.g, nd, lane);
+            const int cm = cclm_search(V, C.g, nd, lane);
             if (lane == 0) C.cclm_mode = cm;
         }
     }
@@ -642,7 +626,7 @@ __device__ __noinline__ void chroma_ct_eval(Shared &S, const SearchParams &P, co
             full_pair4(V, tab, V.c->g, nd, 1 + h, dm, true, -1, ws, lane, ssd, rate);
             if ((lane & 15) == 0) { V.c->r_ssd[h] = ssd; V.c->r_rate[h] = rate; }
         } else {
-            const int cm = cclm_search4(V, V.c->g, nd, lane);
+            const int cm = cclm_search(V, V.c->g, nd, lane);
             if (lane == 0) V.c->cclm_mode = cm;
         }
     }

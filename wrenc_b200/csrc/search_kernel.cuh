@@ -1474,11 +1474,11 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
     __syncwarp(hm);
 }
 
-// SAD-driven choice among the three CCLM modes for 4x4 chroma blocks (block_splitter.rs:1041-1054 / 812-850), one warp.
+// SAD-driven choice among the three CCLM modes (block_splitter.rs:1041-1054 / 812-850), one warp, chroma blocks of any size.
 // The (a, k, b) derivation is scalar work, so the six (mode, component) combinations are derived at once, one per lane
-// (lanes 0-5; the other lanes repeat them), and handed to the sample lanes (0-15 Cb, 16-31 Cr) by shuffles.
-// Order LT, T, L with the reference's tie rules (LT unless strictly worse, then T).
-__device__ __noinline__ int cclm_search4(const Ctx S, const CtuGeom g, const Node nd, int lane) {
+// (lanes 0-5; the other lanes repeat them), and handed to the sample lanes (0-15 Cb, 16-31 Cr, 16 samples per iteration) by
+// shuffles.  Order LT, T, L with the reference's tie rules (LT unless strictly worse, then T).
+__device__ __noinline__ int cclm_search(const Ctx S, const CtuGeom g, const Node nd, int lane) {
     WB_SHARED_CTX(S);
     const int combo = min(lane & 7, 5);  // mode index * 2 + component - 1
     PredCtx pc;
@@ -1487,18 +1487,25 @@ __device__ __noinline__ int cclm_search4(const Ctx S, const CtuGeom g, const Nod
         cclm_params(S, g, nd, 1 + (combo & 1), mi == 0 ? MODE_LT_CCLM : (mi == 1 ? MODE_T_CCLM : MODE_L_CCLM), pc);
     }
     const int pa = pc.cclm128 ? 0 : pc.a, pk = pc.cclm128 ? 0 : pc.k, pb = pc.cclm128 ? 128 : pc.b;  // a = 0: the prediction is b
-    const int cidx = lane >> 4, gl = lane & 15, bx = nd.x >> 1, by = nd.y >> 1;
-    const int org = org_at(S, 1 + cidx, bx + (gl & 3), by + (gl >> 2)), ds = S.c->pds[gl];
-    unsigned s[3];
+    const int cidx = lane >> 4, n = nd.w >> 1, l2 = ilog2i(n), bx = nd.x >> 1, by = nd.y >> 1;
+    int a[3], k[3], b[3];
 #pragma unroll
     for (int mi = 0; mi < 3; mi++) {
         const int src = 2 * mi + cidx;
-        const int a = __shfl_sync(0xffffffffu, pa, src), k = __shfl_sync(0xffffffffu, pk, src), b = __shfl_sync(0xffffffffu, pb, src);
-        const int p = clip8(((ds * a) >> k) + b);
-        s[mi] = warp_sumu((unsigned)abs(p - org));
+        a[mi] = __shfl_sync(0xffffffffu, pa, src); k[mi] = __shfl_sync(0xffffffffu, pk, src); b[mi] = __shfl_sync(0xffffffffu, pb, src);
     }
-    if (s[0] <= s[1] && s[0] <= s[2]) return MODE_LT_CCLM;
-    return s[1] <= s[2] ? MODE_T_CCLM : MODE_L_CCLM;
+    const uint8_t *org = S.c->orgC[cidx] + by * 16 + bx;
+    unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll 1
+    for (int i = lane & 15; i < n * n; i += 16) {
+        const int o = (int)org[((i >> l2) << 4) + (i & (n - 1))], ds = S.c->pds[i];
+        s0 += (unsigned)abs(clip8(((ds * a[0]) >> k[0]) + b[0]) - o);
+        s1 += (unsigned)abs(clip8(((ds * a[1]) >> k[1]) + b[1]) - o);
+        s2 += (unsigned)abs(clip8(((ds * a[2]) >> k[2]) + b[2]) - o);
+    }
+    s0 = warp_sumu(s0); s1 = warp_sumu(s1); s2 = warp_sumu(s2);
+    if (s0 <= s1 && s0 <= s2) return MODE_LT_CCLM;
+    return s1 <= s2 ? MODE_T_CCLM : MODE_L_CCLM;
 }
 
 // The winner of a node was already evaluated with unchanged inputs (the reference repeats that evaluation,
