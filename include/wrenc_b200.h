@@ -91,7 +91,7 @@ int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t 
                                wrenc_b200_ctu_record *d_records, void *stream);
 /* Phase 2 on resident data: CABAC-codes the pictures the preceding wrenc_b200_search_resident call on this handle decided
  * (same n_pictures, its d_levels / d_records) into d_out[n_pictures][out_cap] bytes and d_out_len[n_pictures] (-1 = overflow).
- * Device pointers; runs on `stream` after the search; does not synchronise.  Synchronises `stream` once (to size the bin arena). Returns kernel launches enqueued (4) or <0.
+ * Device pointers; runs on `stream` after the search; does not synchronise.  Synchronises `stream` once (to size the bin arena). Returns kernel launches enqueued (5) or <0.
  * Replaces CtuEncoder::encode_coding_tree .. encode_residual + BoolCoder (src/ctu_encoder.rs:227-2269, src/bool_coder.rs:136-296)
  * and the end_of_slice_one_bit / byte alignment of SliceEncoder::encode (src/slice_encoder.rs:380-388,419). */
 int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d_levels, const wrenc_b200_ctu_record *d_records, uint8_t *d_out,

@@ -485,7 +485,7 @@ int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int rc = enqueue_coder(h, n_pictures, d_levels, reinterpret_cast<const CtuRecord *>(d_records), d_out, out_cap, d_out_len, st);
-    return rc ? rc : 4;
+    return rc ? rc : 5;
 }
 
 size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n) {
