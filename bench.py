@@ -36,7 +36,7 @@ W, H, QP, DEPTH = 1920, 1088, 32, 3
 CTUS_PER_FRAME = (W // 32) * (H // 32)
 OPS_PER_CTU = 8290304          # SURVEY.md §8(d) nominal integer ops per CTU (transforms 4 358 144 + trellis 3 932 160)
 ALG_BYTES_PER_CTU = 1536 + 1536 + 3072 + 88   # source read + recon write + level write + record
-NCU_DRAM_BYTES_PER_CTU = 32770  # dram__bytes_read.sum + dram__bytes_write.sum per CTU of the committed ncu --set full capture (profiles/)
+NCU_DRAM_BYTES_PER_CTU = 16990  # dram__bytes_read.sum + dram__bytes_write.sum per CTU, ncu capture of the final build (profiles/README.md)
 METRIC = "1080p all-intra frames/s (RD search + CABAC slice_data, byte-identical vs oracle)"
 UNIT = "frames/s"
 
@@ -294,10 +294,10 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = ALG_BYTES_PER_CTU * ctus / (launch_ms * 1e-3) / 1e9
     roof = {"bound": "int32", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tops/s", "frac": achieved_ops / peak_ops,
-            "traffic": NCU_DRAM_BYTES_PER_CTU * ctus, "traffic_note": "dram__bytes_read+write of one ncu --set full capture of this kernel (130 560-CTU launch, profiles/r1_search_kernel_ncu_full.txt) scaled per CTU to this launch",
+            "traffic": NCU_DRAM_BYTES_PER_CTU * ctus, "traffic_note": "dram__bytes_read+write of one ncu capture of this kernel (130 560-CTU launch, profiles/README.md) scaled per CTU to this launch",
             "kernel": "wrenc_b200_search_kernel", "launch_ms": launch_ms, "units_per_launch": ctus, "ops_per_unit": OPS_PER_CTU, "share_of_step": launch_ms / (elapsed_ms / args.steps),
             "peak_source": "IMAD-chain microbenchmark run live in bench.py (2 ops per multiply-add); not in MEASURED_PEAKS.json"}
-    roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": ALG_BYTES_PER_CTU, "ncu_dram_bytes_per_unit": NCU_DRAM_BYTES_PER_CTU, "ncu_note": "dram__bytes_read+write of one --set full capture (130 560-CTU launch, profiles/r1_search_kernel_ncu_full.txt): the algorithmic bytes plus the per-CTA scratch (candidate slots, saved states) written back from L2",
+    roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": ALG_BYTES_PER_CTU, "ncu_dram_bytes_per_unit": NCU_DRAM_BYTES_PER_CTU, "ncu_note": "dram__bytes_read+write of one ncu capture (130 560-CTU launch, profiles/README.md): the algorithmic bytes plus what still spills of the per-CTA scratch (candidate slots, saved states; kept in L2 by a persisting access window)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
     # ---- CPU baseline on a bounded sample

@@ -160,7 +160,31 @@ static int enqueue_search(wrenc_b200 *h, int n_pics, const uint8_t *d_yuv, uint8
     P.root_slots = h->d_root_slots;
     CK(cudaMemsetAsync(h->d_counter, 0, sizeof(unsigned int), st));
     int grid = std::min(h->grid, h->n_items / search_ctus_per_cta());
+    // The CTU scratch (40 MB for 148 x 8 CTUs) is rewritten for every CU: keep it resident in L2 (persisting access window)
+    // so that it is not written back to HBM over and over.  Best effort: a failure only costs DRAM traffic.
+    {
+        const size_t bytes = (size_t)h->grid * search_ctus_per_cta() * CTU_SCRATCH_BYTES;
+        static bool limit_set = false;
+        if (!limit_set) {
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes + (4u << 20));
+            limit_set = true;
+        }
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = h->d_root_slots;
+        av.accessPolicyWindow.num_bytes = bytes;
+        av.accessPolicyWindow.hitRatio = 1.0f;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     CK(launch_search(P, grid, st));
+    {   // the window applies to the search kernel only
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av);
+        cudaGetLastError();
+    }
     h->launches++;
     return 0;
 }
