@@ -126,6 +126,20 @@ int wrenc_b200_derive_consts(int32_t qp, const char *extra_params, wrenc_b200_co
 int64_t wrenc_b200_write_nal(int32_t nuh_layer_id, int32_t nal_unit_type, int32_t nuh_temporal_id, const uint8_t *payload, size_t len,
                              uint8_t *out, size_t cap);
 
+/* Complete .vvc byte streams (pure host code, no GPU).  The reference writes, once per sequence, the
+ * VPS (nuh_layer_id 1), SPS and PPS (nuh_layer_id 9) NAL units (src/main.rs:223-260: VpsEncoder / SpsEncoder / PpsEncoder::encode,
+ * src/vps_encoder.rs:29-279, src/sps_encoder.rs:29-665, src/pps_encoder.rs:29-350 incl. profile_tier_level / dpb_parameters /
+ * ref_pic_list_struct, src/ptl_encoder.rs, src/gci_encoder.rs, src/dpbp_encoder.rs, src/rpl_encoder.rs) and, per picture, a PH NAL
+ * unit (src/ph_encoder.rs:29-459, main.rs:297-316) followed by one IDR_W_RADL slice NAL unit whose payload is the byte-aligned
+ * slice header (SliceEncoder::encode_sh, src/slice_encoder.rs:32-341) + slice_data() (main.rs:380-389).  For the reference's one
+ * configuration (struct defaults of src/vps.rs, sps.rs, pps.rs, picture_header.rs, slice_header.rs) these bits depend only on
+ * width, height, --qp (qp = -1: flag absent, QP 26) and the picture index (ph_pic_order_cnt_lsb = index & 15).
+ * Each returns the bytes written, or the negated size needed when cap is too small, or WRENC_B200_EINVAL. */
+int64_t wrenc_b200_write_parameter_sets(int32_t width, int32_t height, int32_t qp, uint8_t *out, size_t cap);
+int64_t wrenc_b200_write_picture(int32_t qp, uint64_t picture_index, const uint8_t *slice_data, size_t len, uint8_t *out, size_t cap);
+/* The header bits before NAL wrapping (spec-level parse-back tests): which = 0 VPS, 1 SPS, 2 PPS, 3 PH RBSP, 4 slice header. */
+int64_t wrenc_b200_header_rbsp(int32_t which, int32_t width, int32_t height, int32_t qp, uint64_t picture_index, uint8_t *out, size_t cap);
+
 /* Per-block entry points (host pointers): the block operations of the search, exposed for bit-exactness tests against
  * IntraPredictor::predict (src/intra_predictor.rs:56-144), Transformer::transform / inverse_transform
  * (src/transformer.rs:2040,2380), Quantizer::quantize / dequantize (src/quantizer.rs:519,761) and the rate walk of

@@ -1,0 +1,59 @@
+"""GPU (-m gpu): BASELINE.json configs[0] and [1] on the REAL clips — bus / mobile CIF, 30 frames, QP 20..41 — through the C ABI.
+Every picture's slice_data and reconstruction must hash to the values tools/pin_oracle.py committed for the oracle
+(tests/golden/reference_pin.json), and the assembled .vvc must have exactly the size of the file the real reference binary
+produced (tools/evaluation/summary.json; 16 operating points).  The decoded clips travel in tests/golden/_assets (git-ignored,
+written by build() where /root/reference exists); without them the two committed frames per clip are checked."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import wrenc_b200
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(os.path.dirname(HERE), "tools"))
+import pin_oracle  # noqa: E402
+
+PIN = json.load(open(os.path.join(HERE, "golden", "reference_pin.json")))["points"]
+W, H = 352, 288
+
+
+def _frames(clip):
+    if os.path.exists(pin_oracle.clip_path(clip)):
+        return pin_oracle.load_clip(clip)
+    g = np.load(os.path.join(HERE, "golden", "cif_clips_2frames.npz"))
+    return [tuple(g[f"{clip}_{i}_{k}"] for k in ("y", "cb", "cr")) for i in (0, 1)]
+
+
+@pytest.mark.parametrize("clip", ["bus", "mobile"])
+@pytest.mark.parametrize("qp", pin_oracle.QPS)
+def test_reference_clip_operating_point(clip, qp):
+    frames = _frames(clip)
+    p = PIN["%s:%d" % (clip, qp)]
+    enc = wrenc_b200.SearchEncoder(W, H, qp=qp, max_split_depth=3, pictures_in_flight=len(frames), want_decisions=False)
+    res = enc.encode_pictures(frames)
+    enc.close()
+    assert len(res) == len(frames)
+    for i, r in enumerate(res):
+        assert hashlib.sha256(r["slice_data"]).hexdigest() == p["slice_data_sha256"][i], f"{clip} qp {qp} frame {i}: slice_data differs from the oracle's"
+        assert hashlib.sha256(b"".join(a.tobytes() for a in r["rec"])).hexdigest() == p["rec_sha256"][i], f"{clip} qp {qp} frame {i}: reconstruction differs"
+        assert [pin_oracle.ffmpeg_psnr_2dp(r["rec"][c], frames[i][c]) for c in range(3)] == p["reference_psnr"][i]
+    if len(frames) == pin_oracle.FRAMES:
+        vvc = wrenc_b200.assemble_vvc(W, H, qp, [r["slice_data"] for r in res])
+        assert len(vvc) == p["reference_file_bytes"], f"{clip} qp {qp}: .vvc is {len(vvc)} B, the reference's is {p['reference_file_bytes']} B"
+        assert hashlib.sha256(vvc).hexdigest() == p["file_sha256"]
+
+
+def test_real_clip_against_live_oracle():
+    """One real frame compared field by field (records, levels, reconstruction, slice_data) with the oracle run here."""
+    from oracle_lib import Oracle
+    from test_gpu_search import assert_same
+    f = _frames("mobile")[1]
+    enc = wrenc_b200.SearchEncoder(W, H, qp=29, pictures_in_flight=1)
+    r = enc.encode_pictures([f])[0]
+    enc.close()
+    assert_same(Oracle(29, 3).encode_picture(*f, want_slice_data=True), r, "mobile frame 1 qp 29")

@@ -221,3 +221,26 @@ def test_submit_pinned_matches_submit_and_rejects_pageable_memory():
     with pytest.raises(wrenc_b200.WrencB200Error):
         enc.submit(0, *frames[0], pinned=True)  # pageable numpy memory
     enc.close()
+
+
+def _oracle_full_frame(a):
+    W, H, qp, seed = a
+    f = wrenc_b200.synth_frame(W, H, seed=seed, frame=0)
+    return Oracle(qp, 3).encode_picture(*f, want_slice_data=True)
+
+
+def test_full_frame_oracle_parity_1080p_and_2160p():
+    """BASELINE.json configs[2] (1920x1088 QP32) and configs[3] (3840x2176 QP27): ONE COMPLETE FRAME of each against the
+    oracle — records, f32 cost bits, levels, reconstruction and slice_data.  The oracle needs ~25 s and
+    ~100 s of one host core; both run in worker processes while the GPU results are produced."""
+    from concurrent.futures import ProcessPoolExecutor
+    cases = [(3840, 2176, 27, 0xB2000003), (1920, 1088, 32, 0xB2000002)]
+    with ProcessPoolExecutor(2) as ex:
+        futs = [ex.submit(_oracle_full_frame, c) for c in cases]
+        got = []
+        for (W, H, qp, seed) in cases:
+            enc = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=1)
+            got.append(enc.encode_pictures([wrenc_b200.synth_frame(W, H, seed=seed, frame=0)])[0])
+            enc.close()
+        for (W, H, qp, _), fut, r in zip(cases, futs, got):
+            assert_same(fut.result(), r, f"{W}x{H} qp {qp} full frame")

@@ -23,7 +23,8 @@ EXPORTS = [
     "wrenc_b200_decisions", "wrenc_b200_flush", "wrenc_b200_pending", "wrenc_b200_search_resident", "wrenc_b200_code_resident",
     "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
-    "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts", "wrenc_b200_write_nal",
+    "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts", "wrenc_b200_write_nal", "wrenc_b200_write_parameter_sets",
+    "wrenc_b200_write_picture", "wrenc_b200_header_rbsp",
 ]
 
 
@@ -92,6 +93,12 @@ def load_library():
     L.wrenc_b200_version.restype = C.c_char_p
     L.wrenc_b200_write_nal.restype = C.c_int64
     L.wrenc_b200_write_nal.argtypes = [C.c_int32, C.c_int32, C.c_int32, vp, C.c_size_t, vp, C.c_size_t]
+    L.wrenc_b200_write_parameter_sets.restype = C.c_int64
+    L.wrenc_b200_write_parameter_sets.argtypes = [i32, i32, i32, vp, C.c_size_t]
+    L.wrenc_b200_write_picture.restype = C.c_int64
+    L.wrenc_b200_write_picture.argtypes = [i32, C.c_uint64, C.c_char_p, C.c_size_t, vp, C.c_size_t]
+    L.wrenc_b200_header_rbsp.restype = C.c_int64
+    L.wrenc_b200_header_rbsp.argtypes = [i32, i32, i32, i32, C.c_uint64, vp, C.c_size_t]
     L.wrenc_b200_derive_consts.restype = C.c_int
     L.wrenc_b200_derive_consts.argtypes = [C.c_int32, C.c_char_p, C.POINTER(Consts), vp, vp, vp]
     L.wrenc_b200_measure_int32_peak.restype = C.c_int
@@ -123,6 +130,40 @@ def write_nal(payload, nal_unit_type=NAL_IDR_W_RADL, nuh_layer_id=9, nuh_tempora
     if n < 0:
         raise ValueError(f"wrenc_b200_write_nal failed ({n})")
     return bytes(out[:n])
+
+
+def _sized_call(fn, *args, guess=4096):
+    buf = C.create_string_buffer(guess)
+    n = fn(*args, buf, guess)
+    if n < -16:  # negated size needed
+        buf = C.create_string_buffer(-n)
+        n = fn(*args, buf, -n)
+    if n < 0:
+        raise ValueError(f"{fn.__name__} failed ({n})")
+    return buf.raw[:n]
+
+
+def write_parameter_sets(width, height, qp=None):
+    """VPS + SPS + PPS byte-stream NAL units as reference main.rs:223-260 writes them (qp=None: no --qp flag)."""
+    return _sized_call(load_library().wrenc_b200_write_parameter_sets, int(width), int(height), -1 if qp is None else int(qp))
+
+
+def write_picture(qp, picture_index, slice_data):
+    """PH NAL unit + IDR_W_RADL slice NAL unit (slice header + slice_data) of one picture, main.rs:297-316,380-389."""
+    sd = bytes(slice_data)
+    return _sized_call(load_library().wrenc_b200_write_picture, -1 if qp is None else int(qp), int(picture_index), sd, len(sd),
+                       guess=len(sd) + len(sd) // 2 + 64)
+
+
+def header_rbsp(which, width, height, qp=None, picture_index=0):
+    """Raw header bits before NAL wrapping; which in ("vps", "sps", "pps", "ph", "sh")."""
+    k = ("vps", "sps", "pps", "ph", "sh").index(which)
+    return _sized_call(load_library().wrenc_b200_header_rbsp, k, int(width), int(height), -1 if qp is None else int(qp), int(picture_index))
+
+
+def assemble_vvc(width, height, qp, slice_datas):
+    """The complete .vvc byte stream of a sequence: parameter sets once, then PH + slice NAL units per picture."""
+    return write_parameter_sets(width, height, qp) + b"".join(write_picture(qp, i, sd) for i, sd in enumerate(slice_datas))
 
 
 def derive_consts(qp, extra_params=None):
