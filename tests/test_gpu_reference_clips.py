@@ -25,7 +25,7 @@ W, H = 352, 288
 def _frames(clip):
     if os.path.exists(pin_oracle.clip_path(clip)):
         return pin_oracle.load_clip(clip)
-    g = np.load(os.path.join(HERE, "golden", "cif_clips_2frames.npz"))
+    g = np.load(os.path.join(HERE, "golden", "clips", "cif_clips_2frames.npz"))
     return [tuple(g[f"{clip}_{i}_{k}"] for k in ("y", "cb", "cr")) for i in (0, 1)]
 
 

@@ -7,7 +7,7 @@ writers on the exactly decoded clips (tools/decode_assets.py) and commits the ou
 16/16 file sizes equal to the byte and 1440/1440 PSNR values equal.  Here:
   * the committed table is checked against summary.json itself (when /root/reference is present) and for internal consistency;
   * a subset is re-encoded live, so the table cannot go stale against the oracle: 2 frames of each clip at all 8 QPs
-    (committed as tests/golden/cif_clips_2frames.npz) and the complete 30-frame encodes of three operating points."""
+    (committed as tests/golden/clips/cif_clips_2frames.npz) and the complete 30-frame encodes of three operating points."""
 import hashlib
 import json
 import os
@@ -63,7 +63,7 @@ def test_committed_table_is_the_reference_summary_and_all_points_match():
 def _encode_subset(a):
     clip, i, qp = a
     from oracle_lib import Oracle
-    g = np.load(os.path.join(HERE, "golden", "cif_clips_2frames.npz"))
+    g = np.load(os.path.join(HERE, "golden", "clips", "cif_clips_2frames.npz"))
     f = tuple(g[f"{clip}_{i}_{k}"] for k in ("y", "cb", "cr"))
     o = Oracle(qp, 3).encode_picture(*f, want_slice_data=True)
     return (clip, i, qp, hashlib.sha256(o["slice_data"]).hexdigest(), hashlib.sha256(b"".join(p.tobytes() for p in o["rec"])).hexdigest(),
