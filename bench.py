@@ -1,24 +1,35 @@
 #!/usr/bin/env python
 """bench.py — all-intra search throughput on B200 (BASELINE.json metric: 1080p all-intra frames/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames F]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config 1080p|2160p|multistream|cif] [--scaling weak|strong] [--frames F] [--no-extra] [--no-cpu]
 
-A step = one pass of the hot path (the whole RD search of every CTU, then the CABAC coding of every picture) over F synthetic 1920x1088 I420 frames per GPU at
-QP32, --max-split-depth 3 (BASELINE.json configs[2]).  Frames are independent IDR pictures, so ranks shard picture
-ranges and there is no data-path collective ("scaling": "weak": every rank searches its own F frames per step).
+A step = one pass of the hot path (the whole RD search of every CTU, then the CABAC coding of every picture) over a batch of
+synthetic I420 frames.  Default workload: BASELINE.json configs[2], 240 frames of 1920x1088 at QP32, --max-split-depth 3,
+PER GPU ("scaling": "weak").  Frames are independent IDR pictures, so ranks shard picture ranges and there is no data-path
+collective.
 
   value        frames/s of the whole hot path (search kernel + syntax/CABAC kernels), inputs resident in HBM, timed with
                CUDA events on the launching stream, max over ranks
-  e2e          same metric through the C-ABI submit/receive calls with HOST planes: H2D of every frame and D2H of the
-               per-CTU records + quantised levels inside the timed region
-  roofline     INT32 issue roofline of the search kernel (SURVEY.md §8d): 8 290 304 nominal integer ops per CTU
+  e2e          same metric through the C-ABI submit_pinned/receive calls with HOST planes, streaming (two batches of
+               --e2e-batch pictures in flight): H2D of every frame, D2H of every picture's slice_data + CTU records inside
+               the timed region; --e2e-steps steps, spread reported
+  roofline     INT32 issue roofline of the search kernel (SURVEY.md section 8d): 8 290 304 nominal integer ops per CTU
                against the IMAD rate measured live on this GPU (2 ops per multiply-add); roofline_hbm shows why HBM is
                not the bound
-  cpu_baseline the CPU oracle (oracle/, a C++ restatement of the reference: the Rust reference cannot be built here)
-               on all host cores, one process per core, on a bounded sample (kind "port")
+  cpu_baseline the CPU oracle (oracle/, a C++ restatement of the reference pinned against the reference's own output files,
+               tests/test_reference_pin.py; the Rust reference cannot be built here) on all host cores, one process per
+               core, on a bounded sample (kind "port")
+  strong_scaling   configs[2] read literally: 240 frames IN TOTAL, picture ranges sharded over the N GPUs (fixed total work)
+  other_configs    the other configurations BASELINE.json names, each sharded over the N GPUs: 3840x2176 QP27 x 120 frames
+               (configs[3]), 64 streams of 1280x704 x 32 frames (configs[4], whole streams per GPU), CIF 352x288 x 30 frames
+               (configs[0] shape): resident frames/s and CTU/s, and e2e frames/s
   --impl reference   the same oracle arm as a stand-alone run (rank 0 only)
+Every timed output is checked outside the timed region: frame 0 of rank 0 must hash to the oracle's committed result
+(tests/golden/bench_golden.json, tools/gen_bench_golden.py) and repeated input frames must give identical output.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -32,42 +43,82 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-W, H, QP, DEPTH = 1920, 1088, 32, 3
-CTUS_PER_FRAME = (W // 32) * (H // 32)
-OPS_PER_CTU = 8290304          # SURVEY.md §8(d) nominal integer ops per CTU (transforms 4 358 144 + trellis 3 932 160)
+DEPTH = 3
+OPS_PER_CTU = 8290304          # SURVEY.md section 8(d) nominal integer ops per CTU (transforms 4 358 144 + trellis 3 932 160)
 ALG_BYTES_PER_CTU = 1536 + 1536 + 3072 + 88   # source read + recon write + level write + record
-NCU_DRAM_BYTES_PER_CTU = 16990  # dram__bytes_read.sum + dram__bytes_write.sum per CTU, ncu capture of the final build (profiles/README.md)
-METRIC = "1080p all-intra frames/s (RD search + CABAC slice_data, byte-identical vs oracle)"
+NCU_DRAM_BYTES_PER_CTU = 16990  # dram__bytes_read.sum + dram__bytes_write.sum per CTU of one ncu capture (profiles/README.md)
 UNIT = "frames/s"
 
+# The configurations BASELINE.json names.  frames = the configuration's total; frames_weak = per GPU when --scaling weak.
+CONFIGS = {
+    "1080p": dict(W=1920, H=1088, qp=32, frames=240, frames_weak=240, unique=12, seed=0xB2000002,
+                  desc="synthetic 1920x1088 yuv420p 8-bit all-intra QP32 max-split-depth 3 (BASELINE.json configs[2])"),
+    "2160p": dict(W=3840, H=2176, qp=27, frames=120, frames_weak=60, unique=4, seed=0xB2000004,
+                  desc="synthetic 3840x2176 yuv420p 8-bit all-intra QP27 max-split-depth 3, down to 4x4 CUs (BASELINE.json configs[3])"),
+    "multistream": dict(W=1280, H=704, qp=32, frames=64 * 32, frames_weak=8 * 32, unique=16, seed=0xB2000005, streams=64, frames_per_stream=32,
+                        desc="64 streams of synthetic 1280x704 x 32 frames, QP32, whole streams per GPU (BASELINE.json configs[4])"),
+    "cif": dict(W=352, H=288, qp=32, frames=30, frames_weak=30, unique=30, seed=0xB2000001,
+                desc="synthetic 352x288 x 30 frames all-intra QP32 (BASELINE.json configs[0] shape; the real clips are tests/test_gpu_reference_clips.py)"),
+}
 
-def synth_frames(n_unique, seed=0xB2000002):
+
+def metric_name(cfg_name):
+    label = {"1080p": "1080p", "2160p": "2160p", "multistream": "64x1280x704 multi-stream", "cif": "CIF"}[cfg_name]
+    return f"{label} all-intra frames/s (RD search + CABAC slice_data, byte-identical vs oracle)"
+
+
+def _synth_one(a):
     from wrenc_b200.synth import synth_frame
-    return [synth_frame(W, H, seed=seed, frame=f) for f in range(n_unique)]
+    W, H, seed, f = a
+    y, cb, cr = synth_frame(W, H, seed=seed, frame=f)
+    return np.concatenate([y.ravel(), cb.ravel(), cr.ravel()])
+
+
+def synth_host(cfg, n_unique, rank):
+    """n_unique synthetic frames of the configuration as one (n_unique, W*H*3/2) uint8 array; rank r draws its own content."""
+    import multiprocessing as mp
+    jobs = [(cfg["W"], cfg["H"], cfg["seed"] + 977 * rank, f) for f in range(n_unique)]
+    procs = max(1, min(len(jobs), (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1"))))))
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            rows = pool.map(_synth_one, jobs)
+    else:
+        rows = [_synth_one(j) for j in jobs]
+    return np.stack(rows)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# CPU arm (oracle): one process per core, each searching `rows` CTU rows of a 1080p frame
+# CPU arm (oracle): one process per core, each searching `rows` CTU rows of a frame of the configuration
 # ------------------------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    idx, rows = args
+    idx, rows, cfg_name = args
+    cfg = CONFIGS[cfg_name]
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_lib import Oracle
     from wrenc_b200.synth import synth_frame
-    y, cb, cr = synth_frame(W, H, seed=0xB2000002, frame=idx)
-    hh = rows * 32
-    o = Oracle(QP, DEPTH)
+    y, cb, cr = synth_frame(cfg["W"], cfg["H"], seed=cfg["seed"], frame=idx)
+    hh = min(rows * 32, cfg["H"])
+    o = Oracle(cfg["qp"], DEPTH)
     t0 = time.perf_counter()
     o.encode_picture(y[:hh], cb[:hh // 2], cr[:hh // 2], want_slice_data=True)  # search + syntax/CABAC, like the GPU arm
     return time.perf_counter() - t0
 
 
-def cpu_arm_step(pool, cores, rows):
+def cpu_arm_step(pool, cores, rows, cfg_name):
+    cfg = CONFIGS[cfg_name]
+    rows = min(rows, cfg["H"] // 32)
     t0 = time.perf_counter()
-    pool.map(_cpu_worker, [(i, rows) for i in range(cores)])
+    pool.map(_cpu_worker, [(i, rows, cfg_name) for i in range(cores)])
     dt = time.perf_counter() - t0
-    ctus = cores * rows * (W // 32)
-    return (ctus / CTUS_PER_FRAME) / dt, dt
+    ctus = cores * rows * (cfg["W"] // 32)
+    return (ctus / ((cfg["W"] // 32) * (cfg["H"] // 32))) / dt, dt
+
+
+def cpu_sample_text(cores, rows, cfg_name):
+    cfg = CONFIGS[cfg_name]
+    rows = min(rows, cfg["H"] // 32)
+    return (f"C++ port of the reference (oracle/, g++ -O3 -march=x86-64-v3), {cores} single-threaded processes x {rows} CTU rows "
+            f"({cfg['W']}x{rows * 32}) of a {cfg['W']}x{cfg['H']} QP{cfg['qp']} frame per step; frames = CTUs/{(cfg['W'] // 32) * (cfg['H'] // 32)}")
 
 
 def run_reference(args):
@@ -80,28 +131,47 @@ def run_reference(args):
     rows = 4
     with mp.get_context("fork").Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_arm_step(pool, cores, 1)
+            cpu_arm_step(pool, cores, 1, args.config)
         t0 = time.perf_counter()
+        frames = 0.0
         for _ in range(args.steps):
-            cpu_arm_step(pool, cores, rows)
+            v, dt = cpu_arm_step(pool, cores, rows, args.config)
+            frames += v * dt
         dt = time.perf_counter() - t0
-    frames = args.steps * cores * rows * (W // 32) / CTUS_PER_FRAME
     v = frames / dt
-    sample = f"{cores} processes x {rows} CTU rows (1920x{rows * 32}) of a 1920x1088 QP32 frame per step; frames = CTUs/2040"
-    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32/f32-cost",
-            "data": "synthetic", "config": workload_config(args, args.frames),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+    line = {"impl": "reference", "metric": metric_name(args.config), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "int32/f32-cost",
+            "data": "synthetic", "config": workload_config(args.config, args.gpus, frames_for(args, args.gpus, 0)[1], args.scaling),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(cores, rows, args.config)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
-def workload_config(args, frames):
-    return {"workload": "synthetic 1920x1088 yuv420p 8-bit all-intra QP32 max-split-depth 3 (BASELINE.json configs[2])",
-            "frames_per_gpu_per_step": frames, "ctus_per_frame": CTUS_PER_FRAME, "qp": QP, "max_split_depth": DEPTH,
-            "l2": "inputs larger than L2 (frames_per_gpu_per_step x 3.1 MB source + 9.4 MB outputs per frame)",
-            "parallelism": f"picture ranges sharded over {args.gpus} GPU(s), CTU wavefronts of all pictures interleaved per GPU"}
+def frames_for(args, world, rank, cfg_name=None, scaling=None, frames=None):
+    """(this rank's frame count, the largest per-rank count) of a configuration."""
+    from wrenc_b200.sharding import shard_range
+    cfg_name = cfg_name or args.config
+    scaling = scaling or args.scaling
+    cfg = CONFIGS[cfg_name]
+    if scaling == "weak":
+        f = frames or cfg["frames_weak"]
+        return f, f
+    total = frames or cfg["frames"]
+    if cfg_name == "multistream":  # whole streams per GPU
+        fps = cfg["frames_per_stream"]
+        b, e = shard_range(total // fps, world, rank)
+        return (e - b) * fps, ((total // fps + world - 1) // world) * fps
+    b, e = shard_range(total, world, rank)
+    return e - b, (total + world - 1) // world
+
+
+def workload_config(cfg_name, world, frames_per_gpu, scaling):
+    cfg = CONFIGS[cfg_name]
+    return {"workload": cfg["desc"], "frames_per_gpu_per_step": frames_per_gpu, "ctus_per_frame": (cfg["W"] // 32) * (cfg["H"] // 32), "qp": cfg["qp"],
+            "max_split_depth": DEPTH, "scaling": scaling,
+            "l2": f"inputs larger than L2 (frames_per_gpu_per_step x {cfg['W'] * cfg['H'] * 3 // 2 / 1e6:.1f} MB source, 3x that in outputs per frame)",
+            "parallelism": f"picture ranges sharded over {world} GPU(s), CTU wavefronts of all pictures interleaved per GPU"}
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -145,146 +215,269 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import wrenc_b200
-    from wrenc_b200.encoder import measure_int32_peak
+class Env:
+    """torch / torch.distributed plumbing of one rank."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        self.tstream = torch.cuda.Stream(device=self.dev)  # a real (non-default) stream: its handle goes through the C ABI
+        torch.cuda.set_stream(self.tstream)
+        self.stream = self.tstream.cuda_stream
+        assert self.stream != 0
 
-    F = args.frames
-    n_unique = min(F, args.unique)
-    frames = synth_frames(n_unique, seed=0xB2000002 + 977 * rank)
-    pic_bytes = W * H * 3 // 2
-    host = np.empty((n_unique, pic_bytes), np.uint8)
-    for i, (y, cb, cr) in enumerate(frames):
-        host[i] = np.concatenate([y.ravel(), cb.ravel(), cr.ravel()])
-    reps = (F + n_unique - 1) // n_unique
-    d_yuv = torch.from_numpy(host).to(dev).repeat(reps, 1)[:F].contiguous()
-    d_rec = torch.empty((F, pic_bytes), dtype=torch.uint8, device=dev)
-    d_lev = torch.empty((F, pic_bytes), dtype=torch.int16, device=dev)
-    d_records = torch.empty((F * CTUS_PER_FRAME, 88), dtype=torch.uint8, device=dev)
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    enc = wrenc_b200.SearchEncoder(W, H, qp=QP, max_split_depth=DEPTH, device=local, pictures_in_flight=args.e2e_batch,
-                                   want_recon=False, want_decisions=False, want_slice_data=True)
-    out_cap = pic_bytes
-    d_out = torch.empty((F, out_cap), dtype=torch.uint8, device=dev)
-    d_out_len = torch.empty(F, dtype=torch.int32, device=dev)
-    tstream = torch.cuda.Stream(device=dev)  # a real (non-default) stream: its handle goes through the C ABI
-    torch.cuda.set_stream(tstream)
-    stream = tstream.cuda_stream
-    assert stream != 0
+    def max_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
 
-    search_ev = []
+    def sum_over_ranks(self, v):
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
 
-    def step():  # the whole hot path: RD search of every CTU, then syntax + CABAC coding of every picture
+    def close(self):
+        if self.dist is not None:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+
+
+_GOLDEN = None
+
+
+def golden():
+    global _GOLDEN
+    if _GOLDEN is None:
+        try:
+            _GOLDEN = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_golden.json")))
+        except OSError:
+            _GOLDEN = {}
+    return _GOLDEN
+
+
+class Workload:
+    """F frames of one configuration on this rank: device-resident inputs/outputs, an encoder handle, pinned host planes."""
+
+    def __init__(self, env, cfg_name, F, e2e_batch):
+        import wrenc_b200
+        torch = env.torch
+        self.env, self.name, self.cfg, self.F = env, cfg_name, CONFIGS[cfg_name], F
+        cfg = self.cfg
+        self.W, self.H, self.qp = cfg["W"], cfg["H"], cfg["qp"]
+        self.ctus_per_frame = (self.W // 32) * (self.H // 32)
+        self.pic_bytes = self.W * self.H * 3 // 2
+        self.n_unique = max(1, min(F, cfg["unique"]))
+        self.host = synth_host(cfg, self.n_unique, env.rank)
+        reps = (F + self.n_unique - 1) // self.n_unique
+        dev = env.dev
+        self.d_yuv = torch.from_numpy(self.host).to(dev).repeat(reps, 1)[:F].contiguous()
+        self.d_rec = torch.empty((F, self.pic_bytes), dtype=torch.uint8, device=dev)
+        self.d_lev = torch.empty((F, self.pic_bytes), dtype=torch.int16, device=dev)
+        self.d_records = torch.empty((F * self.ctus_per_frame, 88), dtype=torch.uint8, device=dev)
+        self.out_cap = self.pic_bytes
+        self.d_out = torch.empty((F, self.out_cap), dtype=torch.uint8, device=dev)
+        self.d_out_len = torch.empty(F, dtype=torch.int32, device=dev)
+        self.B = max(1, min(e2e_batch, F))
+        self.enc = wrenc_b200.SearchEncoder(self.W, self.H, qp=self.qp, max_split_depth=DEPTH, device=env.local, pictures_in_flight=self.B,
+                                            want_recon=False, want_decisions=False, want_slice_data=True)
+        self.enc.prepare(F)
+        self.search_ev = []
+        self.golden_checked = False
+
+    def step(self):  # the whole hot path: RD search of every CTU, then syntax + CABAC coding of every picture
+        torch, st = self.env.torch, self.env.stream
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        n = enc.search_resident(F, d_yuv, d_rec, d_lev, d_records, stream)
+        n = self.enc.search_resident(self.F, self.d_yuv, self.d_rec, self.d_lev, self.d_records, st)
         e1.record()
-        search_ev.append((e0, e1))
-        return n + enc.code_resident(F, d_lev, d_records, d_out, out_cap, d_out_len, stream)
+        self.search_ev.append((e0, e1))
+        return n + self.enc.code_resident(self.F, self.d_lev, self.d_records, self.d_out, self.out_cap, self.d_out_len, st)
 
-    def barrier():
+    def settle_arena(self):
+        """Untimed: the slice coder sizes its bin arena from earlier batches; the first batch may outgrow the initial guess."""
+        torch = self.env.torch
+        self.step()
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
+        if int(self.d_out_len.min().item()) == -2:
+            self.enc.code_resident_retry(self.F, self.d_lev, self.d_records, self.d_out, self.out_cap, self.d_out_len, self.env.stream)
+            torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    sampler = ClockSampler(local)
+    def resident(self, steps, warmup):
+        env, torch = self.env, self.env.torch
+        self.settle_arena()
+        for _ in range(warmup):
+            self.step()
+        env.barrier()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        launches = 0
+        self.search_ev = []
+        ev[0].record()
+        for k in range(steps):
+            launches += self.step()
+            ev[k + 1].record()
+        env.barrier()
+        elapsed_ms = ev[0].elapsed_time(ev[-1])
+        kernel_ms = [a.elapsed_time(b) for a, b in self.search_ev[-steps:]]  # the search kernel alone (dominant kernel)
+        self.check_outputs()
+        coded = int(self.d_out_len.to(torch.int64).sum().item())
+        return dict(elapsed_ms=elapsed_ms, kernel_ms=kernel_ms, launches=launches, coded_bytes=coded)
+
+    def check_outputs(self):
+        """Outside the timed region: no overflow, repeated frames identical, frame 0 of rank 0 == the oracle's committed hashes."""
+        torch = self.env.torch
+        assert int(self.d_out_len.min().item()) > 0, "slice_data coder reported an overflow"
+        if self.F > self.n_unique:
+            a, b = self.d_rec[0], self.d_rec[self.n_unique]
+            assert torch.equal(a, b), "repeated input frame produced a different reconstruction"
+            la, lb = int(self.d_out_len[0]), int(self.d_out_len[self.n_unique])
+            assert la == lb and torch.equal(self.d_out[0, :la], self.d_out[self.n_unique, :lb]), "repeated input frame produced different slice_data"
+        g = golden().get(self.name)
+        if self.env.rank == 0 and g:
+            n0 = int(self.d_out_len[0])
+            sd = self.d_out[0, :n0].cpu().numpy().tobytes()
+            rec = self.d_rec[0].cpu().numpy().tobytes()
+            assert hashlib.sha256(sd).hexdigest() == g["slice_data_sha256"] and len(sd) == g["slice_data_bytes"], f"{self.name}: slice_data of frame 0 differs from the oracle's"
+            assert hashlib.sha256(rec).hexdigest() == g["rec_sha256"], f"{self.name}: reconstruction of frame 0 differs from the oracle's"
+            self.golden_checked = True
+
+    def planes(self):
+        if not hasattr(self, "_planes"):
+            self._pinned = self.env.torch.from_numpy(self.host).pin_memory()
+            hp = self._pinned.numpy()
+            W, H = self.W, self.H
+            self._planes = [(hp[i, :W * H].reshape(H, W), hp[i, W * H:W * H * 5 // 4].reshape(H // 2, W // 2), hp[i, W * H * 5 // 4:].reshape(H // 2, W // 2))
+                            for i in range(self.n_unique)]
+        return self._planes
+
+    def e2e_step(self, Fe, total=None, gather=True):
+        """Host planes through submit_pinned / receive, streaming: pictures are submitted ahead (up to two batches in flight)."""
+        enc, planes = self.enc, self.planes()
+        got, cost, coded, i = 0, 0.0, [], 0
+        first = None
+        while got < Fe:
+            while i < Fe:
+                y, cb, cr = planes[i % self.n_unique]
+                try:
+                    enc.submit(i, y, cb, cr, pinned=True)
+                except Exception as e:  # WrencB200Full: both batch slots are in flight
+                    if type(e).__name__ != "WrencB200Full":
+                        raise
+                    break
+                i += 1
+            if i == Fe:
+                enc.flush()
+            r = enc.receive(copy=False)
+            cost += float(r["records"]["cost"][0]) + len(r["slice_data"])
+            coded.append(r["slice_data"])
+            if first is None:
+                first = r["slice_data"]
+            got += 1
+        if gather and self.env.dist is not None:  # the job's only exchange: ordered gather of the per-picture byte buffers on the writer rank
+            from wrenc_b200.sharding import gather_in_order_host
+            allb = gather_in_order_host(coded, dst=0, barrier=self.env.dist.barrier, rank=self.env.rank, world=self.env.world)
+            if self.env.rank == 0 and total is not None:
+                assert len(allb) == int(total)
+        g = golden().get(self.name)
+        if self.env.rank == 0 and g and Fe > 0:
+            assert hashlib.sha256(first).hexdigest() == g["slice_data_sha256"], f"{self.name}: e2e slice_data of frame 0 differs from the oracle's"
+        return sum(len(c) for c in coded)
+
+    def e2e(self, Fe, steps):
+        env = self.env
+        total = env.sum_over_ranks(Fe)
+        self.e2e_step(Fe, total)  # warm-up: slot allocation, arena growth
+        env.barrier()
+        times, coded = [], 0
+        for _ in range(steps):
+            env.barrier()
+            t0 = time.perf_counter()
+            coded = self.e2e_step(Fe, total)
+            env.barrier()
+            times.append(env.max_over_ranks(time.perf_counter() - t0))
+        return times, coded
+
+    def close(self):
+        self.enc.close()
+        for k in ("d_yuv", "d_rec", "d_lev", "d_records", "d_out", "d_out_len"):
+            setattr(self, k, None)
+        self.env.torch.cuda.empty_cache()
+
+
+def sub_record(env, args, cfg_name, scaling, steps, warmup, e2e_steps=1, frames=None):
+    """One extra configuration: resident value + e2e, sharded over the ranks (strong) — returns the record on every rank."""
+    F, Fmax = frames_for(args, env.world, env.rank, cfg_name, scaling, frames)
+    total = env.sum_over_ranks(F)
+    wl = Workload(env, cfg_name, max(F, 1), min(args.e2e_batch, max(1, (F + 1) // 2)))
+    r = wl.resident(steps, warmup)
+    elapsed = env.max_over_ranks(r["elapsed_ms"]) if F > 0 else env.max_over_ranks(0.0)
+    value = total * steps / (elapsed * 1e-3)
+    times, _ = wl.e2e(F, e2e_steps)
+    e2e_value = total / statistics.median(times)
+    rec = {"workload": CONFIGS[cfg_name]["desc"], "scaling": scaling, "frames_total_per_step": int(total), "frames_this_gpu": F, "qp": CONFIGS[cfg_name]["qp"],
+           "value": value, "unit": UNIT, "ctus_per_s": value * wl.ctus_per_frame, "ms_per_step": elapsed / steps, "steps": steps, "warmup": warmup,
+           "search_kernel_ms_rank0": statistics.mean(r["kernel_ms"]), "e2e": {"value": e2e_value, "unit": UNIT, "steps": e2e_steps, "batch": wl.B},
+           "golden_frame0_checked": wl.golden_checked}
+    wl.close()
+    return rec
+
+
+def run_ours(args):
+    from wrenc_b200.encoder import measure_int32_peak
+    env = Env()
+    world, rank = env.world, env.rank
+    cfg = CONFIGS[args.config]
+    F, _ = frames_for(args, world, rank, frames=args.frames)
+    total_frames = env.sum_over_ranks(F)
+    wl = Workload(env, args.config, F, args.e2e_batch)
+
+    sampler = ClockSampler(env.local)
     if rank == 0:
         sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    launches = 0
-    ev[0].record()
-    for k in range(args.steps):
-        launches += step()
-        ev[k + 1].record()
-    barrier()
-    elapsed_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [a.elapsed_time(b) for a, b in search_ev[-args.steps:]]  # the search kernel alone (dominant kernel)
+    r = wl.resident(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
-    value = world * F * args.steps / (elapsed_ms * 1e-3)
+    elapsed_ms = env.max_over_ranks(r["elapsed_ms"])
+    value = total_frames * args.steps / (elapsed_ms * 1e-3)
+    kernel_ms, launches, coded_bytes = r["kernel_ms"], r["launches"], r["coded_bytes"]
 
-    # ---- parity spot check of the timed outputs (size-independent property: deterministic, equal for repeated frames)
-    if F > n_unique:
-        a = d_rec[0]
-        b = d_rec[n_unique]
-        assert torch.equal(a, b), "repeated input frame produced a different reconstruction"
-        la, lb = int(d_out_len[0]), int(d_out_len[n_unique])
-        assert la == lb and la > 0 and torch.equal(d_out[0, :la], d_out[n_unique, :lb]), "repeated input frame produced different slice_data"
-    coded_bytes = int(d_out_len.to(torch.int64).sum().item())
-    assert int(d_out_len.min().item()) > 0, "slice_data coder reported an overflow"
-
-    # ---- e2e: host planes through submit/receive
-    # the step's inputs come from pinned host memory (the buffer a YUV reader would fill): submit_pinned, no staging copy
-    host_pinned_t = torch.from_numpy(host).pin_memory()
-    hp = host_pinned_t.numpy()
-    planes = [(hp[i, :W * H].reshape(H, W), hp[i, W * H:W * H * 5 // 4].reshape(H // 2, W // 2), hp[i, W * H * 5 // 4:].reshape(H // 2, W // 2))
-              for i in range(n_unique)]
-    Fe = args.e2e_frames
-
-    def e2e_step():
-        got, cost, coded = 0, 0.0, []
-        i = 0
-        while got < Fe:
-            nb = min(args.e2e_batch, Fe - i) if i < Fe else 0
-            for _ in range(nb):
-                y, cb, cr = planes[i % n_unique]
-                enc.submit(i, y, cb, cr, pinned=True)
-                i += 1
-            while enc.pending():
-                r = enc.receive(copy=False)
-                cost += float(r["records"]["cost"][0]) + len(r["slice_data"])
-                coded.append(r["slice_data"])
-                got += 1
-        if dist is not None:  # the job's only exchange: ordered gather of the per-picture byte buffers on the writer rank
-            from wrenc_b200.sharding import gather_in_order
-            allb = gather_in_order(coded, dst=0, device=dev)
-            if rank == 0:
-                assert len(allb) == world * Fe
-        return cost
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Fe * args.e2e_steps / float(te.item())
-
-    if rank != 0:
-        if dist is not None:
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
+    # ---- e2e: pinned host planes (the buffer a YUV reader would fill) through submit_pinned / receive, streaming
+    Fe = min(args.e2e_frames or F, F) if args.scaling == "weak" else F
+    e2e_times, e2e_coded = wl.e2e(Fe, args.e2e_steps)
+    e2e_total = env.sum_over_ranks(Fe)
+    e2e_value = e2e_total / statistics.median(e2e_times)
+    e2e_sweep = {}
+    if not args.no_extra and args.config == "1080p":  # smaller batches in flight: what a latency-bound caller sees
+        for b in (32, 60):
+            if b < wl.B:
+                w2 = Workload(env, args.config, min(F, 4 * b), b)
+                t2, _ = w2.e2e(min(F, 4 * b), 2)
+                e2e_sweep[str(b)] = env.sum_over_ranks(min(F, 4 * b)) / statistics.median(t2)
+                w2.close()
 
     # ---- roofline (rank 0's GPU): INT32 issue peak measured live
-    imad = measure_int32_peak(local)
+    imad = measure_int32_peak(env.local)
     peak_ops = 2.0 * imad
     launch_ms = statistics.mean(kernel_ms)
-    ctus = F * CTUS_PER_FRAME
+    ctus = F * wl.ctus_per_frame
     achieved_ops = OPS_PER_CTU * ctus / (launch_ms * 1e-3)
     peaks = {}
     try:
@@ -294,37 +487,54 @@ def run_ours(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = ALG_BYTES_PER_CTU * ctus / (launch_ms * 1e-3) / 1e9
     roof = {"bound": "int32", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tops/s", "frac": achieved_ops / peak_ops,
-            "traffic": NCU_DRAM_BYTES_PER_CTU * ctus, "traffic_note": "dram__bytes_read+write of one ncu capture of this kernel (130 560-CTU launch, profiles/README.md) scaled per CTU to this launch",
-            "kernel": "wrenc_b200_search_kernel", "launch_ms": launch_ms, "units_per_launch": ctus, "ops_per_unit": OPS_PER_CTU, "share_of_step": launch_ms / (elapsed_ms / args.steps),
-            "peak_source": "IMAD-chain microbenchmark run live in bench.py (2 ops per multiply-add); not in MEASURED_PEAKS.json"}
-    roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": ALG_BYTES_PER_CTU, "ncu_dram_bytes_per_unit": NCU_DRAM_BYTES_PER_CTU, "ncu_note": "dram__bytes_read+write of one ncu capture (130 560-CTU launch, profiles/README.md): the algorithmic bytes plus what still spills of the per-CTA scratch (candidate slots, saved states; kept in L2 by a persisting access window)",
+            "traffic": NCU_DRAM_BYTES_PER_CTU * ctus, "traffic_note": "dram__bytes_read+write of one ncu capture of this kernel (profiles/README.md) scaled per CTU to this launch",
+            "kernel": "wrenc_b200_search_kernel", "launch_ms": launch_ms, "units_per_launch": ctus, "ops_per_unit": OPS_PER_CTU, "share_of_step": launch_ms / (r["elapsed_ms"] / args.steps),
+            "peak_source": "IMAD-chain microbenchmark run live in bench.py (64 IMAD/clk/SM x 148 SMs x clock; 2 ops per multiply-add); not in MEASURED_PEAKS.json"}
+    roof_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak, "bytes_per_unit": ALG_BYTES_PER_CTU, "ncu_dram_bytes_per_unit": NCU_DRAM_BYTES_PER_CTU,
+                "ncu_note": "dram__bytes_read+write of one ncu capture (profiles/README.md): the algorithmic bytes plus what still spills of the per-CTA scratch (candidate slots, saved states; kept in L2 by a persisting access window)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+    golden_main = wl.golden_checked
+    ctus_per_frame, pic_bytes, Bmain = wl.ctus_per_frame, wl.pic_bytes, wl.B
+    wl.close()
 
-    # ---- CPU baseline on a bounded sample
+    # ---- the configurations the metric names beyond the default workload (every rank takes part)
+    strong, others = None, {}
+    if not args.no_extra:
+        if args.config == "1080p" and args.scaling == "weak":
+            strong = sub_record(env, args, "1080p", "strong", steps=2, warmup=1, e2e_steps=2)
+        for name in ("2160p", "multistream", "cif"):
+            if name != args.config:
+                others[name] = sub_record(env, args, name, "strong", steps=2 if name != "multistream" else 1, warmup=1)
+
+    if rank != 0:
+        env.close()
+        return 0
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 semantics: the host's cores)
     cpu = None
     if not args.no_cpu:
         import multiprocessing as mp
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
         cores = os.cpu_count() or 1
-        rows = args.cpu_rows
         with mp.get_context("fork").Pool(cores) as pool:
-            v, dt = cpu_arm_step(pool, cores, rows)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{cores} processes x {rows} CTU rows (1920x{rows * 32}) of a 1920x1088 QP32 frame, {dt:.1f} s wall; frames = CTUs/2040"}
+            v, dt = cpu_arm_step(pool, cores, args.cpu_rows, args.config)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(cores, args.cpu_rows, args.config) + f", {dt:.1f} s wall"}
 
     h2d = Fe * pic_bytes
-    d2h = Fe * (CTUS_PER_FRAME * 88) + int(coded_bytes / F * Fe)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int32/f32-cost", "data": f"synthetic ({n_unique} unique frames per GPU, repeated to {F})",
-            "config": workload_config(args, F), "ctus_per_s": value * CTUS_PER_FRAME, "coded_bytes_per_frame": coded_bytes / F,
+    d2h = Fe * (ctus_per_frame * 88) + e2e_coded
+    line = {"metric": metric_name(args.config), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "int32/f32-cost", "data": f"synthetic ({wl.n_unique} unique frames per GPU, repeated to {F})",
+            "config": workload_config(args.config, world, F, args.scaling), "ctus_per_s": value * ctus_per_frame, "coded_bytes_per_frame": coded_bytes / max(F, 1),
+            "parity": {"golden_frame0_vs_oracle": golden_main, "note": "frame 0 of rank 0 (resident and e2e) must hash to the oracle's committed slice_data / reconstruction (tests/golden/bench_golden.json); repeated frames must give identical output; checked outside the timed region"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "frames_per_step": Fe,
-                    "steps": args.e2e_steps, "batch": args.e2e_batch, "note": "pinned host planes -> submit_pinned/receive (H2D of every frame in the timed region); D2H = CABAC-coded slice_data of every picture + CTU records"},
-            "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "clocks": clocks}
+                    "steps": args.e2e_steps, "step_s": e2e_times, "spread": (max(e2e_times) - min(e2e_times)) / statistics.median(e2e_times), "batch": Bmain, "batches_in_flight": 2,
+                    "by_batch": e2e_sweep,
+                    "note": "pinned host planes -> submit_pinned/receive, streaming with two batches in flight (H2D of every frame in the timed region); D2H = CABAC-coded slice_data of every picture + CTU records; N>1: + ordered gather of the byte buffers on rank 0 through host shared memory"},
+            "gpu_launches": launches, "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu, "clocks": clocks,
+            "strong_scaling": strong, "other_configs": others}
     print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    env.close()
     return 0
 
 
@@ -334,13 +544,15 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=240, help="frames per GPU per step")
-    ap.add_argument("--unique", type=int, default=12, help="unique synthetic frames generated on the host (repeated on device)")
-    ap.add_argument("--e2e-frames", type=int, default=240)
-    ap.add_argument("--e2e-batch", type=int, default=240)
-    ap.add_argument("--e2e-steps", type=int, default=1)
+    ap.add_argument("--config", default="1080p", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--frames", type=int, default=None, help="frames per GPU per step (weak) / in total (strong); default: the configuration's")
+    ap.add_argument("--e2e-frames", type=int, default=None)
+    ap.add_argument("--e2e-batch", type=int, default=120, help="pictures per batch of the submit/receive path (two batches in flight)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-rows", type=int, default=6)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the strong-scaling and other-configuration sub-records")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

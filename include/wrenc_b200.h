@@ -35,8 +35,9 @@ enum {
     WRENC_B200_ENODEV = -2,  /* no CUDA device / not sm_100 capable */
     WRENC_B200_ECUDA = -3,   /* CUDA runtime error */
     WRENC_B200_EAGAIN = -4,  /* receive with nothing submitted */
-    WRENC_B200_EFULL = -5,   /* submit while pictures_in_flight pictures are pending (call receive first) */
-    WRENC_B200_EOVERFLOW = -6 /* slice_data of a picture did not fit the coder's buffers */
+    WRENC_B200_EFULL = -5,   /* submit while every batch slot holds pictures that have not been received (call receive first) */
+    WRENC_B200_EOVERFLOW = -6 /* slice_data of a picture did not fit its output buffer (twice the raw picture); the picture is still
+                                 consumed: pic_idx, reconstruction and decisions are returned, *len = 0, and the handle stays usable */
 };
 
 typedef struct {
@@ -44,7 +45,8 @@ typedef struct {
     int32_t qp;                   /* slice QP == --qp (reference default 26 when absent) */
     int32_t max_split_depth;      /* 0..3, --max-split-depth (default 3: CUs 32,16,8,4) */
     int32_t device;               /* CUDA device ordinal (one handle per GPU; shard picture ranges across handles) */
-    int32_t pictures_in_flight;   /* pictures searched by one kernel launch (CTU wavefronts of all of them interleave) */
+    int32_t pictures_in_flight;   /* pictures per batch = per search-kernel launch (CTU wavefronts of all of them interleave); two batches
+                                     are in flight: one is searched while the next is filled and the previous is coded / copied back */
     int32_t want_recon;           /* copy reconstructed planes back (--reconst) */
     int32_t want_decisions;       /* copy per-CTU records + quantised levels back (parity / phase-1 consumers) */
     int32_t want_slice_data;      /* CABAC-code the decided pictures on the device and return slice_data() bytes */
@@ -63,39 +65,58 @@ int wrenc_b200_create(const wrenc_b200_config *cfg, wrenc_b200 **out);
 void wrenc_b200_destroy(wrenc_b200 *h);
 const char *wrenc_b200_last_error(const wrenc_b200 *h); /* h may be NULL: error of the last failed create */
 
-/* Host planes, tightly packed I420 as main.rs:320-349 reads them. */
+/* Host planes, tightly packed I420 as main.rs:320-349 reads them.  The planes are copied before submit returns and the
+ * host-to-device copy is started at once; when the batch is complete (pictures_in_flight pictures) it is launched without
+ * waiting for anything, so the caller can keep submitting the next batch while this one runs (streaming: the reference's
+ * per-picture loop main.rs:294-402 becomes "read ahead and submit; receive and append" with up to 2 x pictures_in_flight
+ * pictures between the reader and the writer).  May allocate (first use of a slot). */
 int wrenc_b200_submit(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
 /* The same for planes that already lie in page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. the buffer the YUV
  * reader fills): no staging copy, the planes are read by the copy engine asynchronously and must stay valid and unchanged
  * until the picture has been received.  WRENC_B200_EINVAL if a plane is not page-locked. */
 int wrenc_b200_submit_pinned(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
-/* Strictly in submit order.  Launches the pending batch if it has not run yet, then blocks until the picture is ready.
- * slice_data/len: CABAC-coded slice_data() bytes of the picture (byte aligned, ends with rbsp stop bit + alignment zeros).
- * rec_*: reconstructed planes (NULL unless want_recon). Any out pointer may be NULL. */
+/* Strictly in submit order.  Launches the pending batch if it has not run yet, then blocks until THIS picture's outputs have
+ * landed in host memory (pictures of one batch become ready together when its coder kernel ends; their bytes are then copied
+ * back picture by picture, each with its own event).  slice_data/len: CABAC-coded slice_data() bytes of the picture (byte
+ * aligned, ends with rbsp stop bit + alignment zeros).  rec_*: reconstructed planes (NULL unless want_recon).  Any out pointer
+ * may be NULL.  The pointers stay valid until 2 x pictures_in_flight further pictures have been submitted, or destroy. */
 int wrenc_b200_receive(wrenc_b200 *h, uint64_t *pic_idx, const uint8_t **slice_data, size_t *len, const uint8_t **rec_y,
                        const uint8_t **rec_cb, const uint8_t **rec_cr);
 /* Decisions of the picture returned by the LAST receive (want_decisions must be set): records[(H/32)*(W/32)], and the
  * final quantised levels as int16 planes (luma W*H, chroma W/2*H/2), each TB stored at its own position. */
 int wrenc_b200_decisions(wrenc_b200 *h, const wrenc_b200_ctu_record **records, const int16_t **lev_y, const int16_t **lev_cb,
                          const int16_t **lev_cr);
-/* Launch whatever is pending without waiting (receive does this implicitly). */
+/* Launch a partly filled batch without waiting (receive does this implicitly; a full batch is launched by submit). */
 int wrenc_b200_flush(wrenc_b200 *h);
 /* Number of pictures submitted and not yet received. */
 int wrenc_b200_pending(const wrenc_b200 *h);
 
+/* Allocates the workspace and uploads the wavefront work list for batches of n_pictures (device-synchronising, blocking), so
+ * that later search_resident / code_resident calls with at most that many pictures neither allocate nor block.  Without it
+ * the first resident call with a new (larger) n_pictures does this work itself. */
+int wrenc_b200_prepare(wrenc_b200 *h, int32_t n_pictures);
 /* Device-resident entry (throughput path / bench "value"): n_pictures I420 pictures already in HBM, contiguous, each
  * width*height*3/2 bytes; outputs written to device buffers of the same geometry (rec: u8, levels: i16 per sample),
  * records: n_pictures*(H/32)*(W/32).  All pointers are DEVICE pointers on cfg.device and all are required.  Runs on
- * `stream` (a cudaStream_t, or NULL for the handle's own stream) and does not synchronise.  Returns the number of search-kernel launches enqueued (>=1) or <0. */
+ * `stream` (a cudaStream_t, or NULL for the handle's own stream).  After wrenc_b200_prepare (or an earlier call with at least
+ * as many pictures) it only enqueues work: no allocation, no synchronisation.  A handle runs ONE search at a time (the
+ * searches share a per-grid scratch): do not run resident calls on different streams, or resident calls and submit/receive,
+ * concurrently on one handle.  Returns the number of search-kernel launches enqueued (>=1) or <0. */
 int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t *d_yuv, uint8_t *d_rec, int16_t *d_levels,
                                wrenc_b200_ctu_record *d_records, void *stream);
 /* Phase 2 on resident data: CABAC-codes the pictures the preceding wrenc_b200_search_resident call on this handle decided
  * (same n_pictures, its d_levels / d_records) into d_out[n_pictures][out_cap] bytes and d_out_len[n_pictures] (-1 = overflow).
- * Device pointers; runs on `stream` after the search; does not synchronise.  Synchronises `stream` once (to size the bin arena). Returns kernel launches enqueued (5) or <0.
+ * (-1 = the picture's output buffer is too small, -2 = the bin arena, which is sized from earlier batches, was too small for
+ * this batch: call wrenc_b200_code_resident_retry).  Device pointers; runs on `stream` after the search; does not synchronise.
+ * Returns kernel launches enqueued (5) or <0.
  * Replaces CtuEncoder::encode_coding_tree .. encode_residual + BoolCoder (src/ctu_encoder.rs:227-2269, src/bool_coder.rs:136-296)
  * and the end_of_slice_one_bit / byte alignment of SliceEncoder::encode (src/slice_encoder.rs:380-388,419). */
 int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d_levels, const wrenc_b200_ctu_record *d_records, uint8_t *d_out,
                              size_t out_cap, int32_t *d_out_len, void *stream);
+/* After a code_resident whose d_out_len reported -2: grows the bin arena to the size that call measured and codes the same
+ * pictures again.  Blocks (reads the measured total back).  Returns kernel launches enqueued (3) or <0. */
+int wrenc_b200_code_resident_retry(wrenc_b200 *h, int32_t n_pictures, const int16_t *d_levels, const wrenc_b200_ctu_record *d_records, uint8_t *d_out,
+                                   size_t out_cap, int32_t *d_out_len, void *stream);
 /* Workspace the resident entry needs for n_pictures (bytes of device memory it will allocate once and keep). */
 size_t wrenc_b200_workspace_bytes(const wrenc_b200 *h, int32_t n_pictures);
 

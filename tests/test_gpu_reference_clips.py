@@ -57,3 +57,33 @@ def test_real_clip_against_live_oracle():
     r = enc.encode_pictures([f])[0]
     enc.close()
     assert_same(Oracle(29, 3).encode_picture(*f, want_slice_data=True), r, "mobile frame 1 qp 29")
+
+
+def test_cli_writes_the_reference_sized_vvc_file(tmp_path):
+    """wrenc_b200_cli (the reference's flags, src/main.rs:85-115) on the bus clip: `-i bus.yuv --input-size 352x288 --output-size
+    352x288 --num-pictures 30 --qp 32 -o out.vvc --reconst rec.yuv` — the file must have the size of the reference's own output
+    (301 521 B, summary.json:1571-1574), hash to the oracle-composed stream, and --reconst must be the oracle's reconstruction."""
+    import subprocess
+    root = os.path.dirname(HERE)
+    cli = os.path.join(root, "wrenc_b200", "wrenc_b200_cli")
+    assert os.path.exists(cli), "wrenc_b200_cli is not built (build())"
+    frames = _frames("bus")
+    src = tmp_path / "bus.yuv"
+    src.write_bytes(b"".join(p.tobytes() for f in frames for p in f))
+    out, rec = tmp_path / "out.vvc", tmp_path / "rec.yuv"
+    r = subprocess.run([cli, "-i", str(src), "--input-size", "352x288", "--output-size", "352x288", "--num-pictures", str(len(frames)), "--qp", "32",
+                        "-o", str(out), "--reconst", str(rec), "--pictures-in-flight", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    p = PIN["bus:32"]
+    data = out.read_bytes()
+    if len(frames) == pin_oracle.FRAMES:
+        assert len(data) == p["reference_file_bytes"] == 301521
+        assert hashlib.sha256(data).hexdigest() == p["file_sha256"]
+    recd = rec.read_bytes()
+    n = W * H * 3 // 2
+    assert len(recd) == n * len(frames)
+    for i in range(len(frames)):
+        assert hashlib.sha256(recd[i * n:(i + 1) * n]).hexdigest() == p["rec_sha256"][i]
+    # the reference's error behaviour: a bad size prints an error and exits 0 (main.rs:181-187)
+    r = subprocess.run([cli, "-i", str(src), "--input-size", "352", "--output-size", "352x288", "--num-pictures", "1", "-o", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Invalid input-size" in r.stderr

@@ -88,10 +88,60 @@ def test_api_errors():
         enc.receive()  # nothing submitted
     f = wrenc_b200.synth_frame(64, 64)
     enc.submit(7, *f)
-    with pytest.raises(wrenc_b200.WrencB200Error):
-        enc.submit(8, *f)  # pictures_in_flight exceeded
+    enc.submit(8, *f)  # second batch slot
+    with pytest.raises(wrenc_b200.WrencB200Full):
+        enc.submit(9, *f)  # both batch slots hold un-received pictures
+    assert enc.pending() == 2
     assert enc.receive()["pic_idx"] == 7
+    enc.submit(9, *f)  # the first slot is free again
+    assert [enc.receive()["pic_idx"] for _ in range(2)] == [8, 9]
+    assert enc.pending() == 0
     enc.close()
+
+
+def test_streaming_submit_receive_many_batches():
+    """The pipelined boundary (two batch slots, four streams): pictures are submitted ahead while earlier batches are searched /
+    coded / copied back; results come back strictly in submit order and equal the one-picture-at-a-time results, also with a
+    partly filled last batch and with receives interleaved at every position."""
+    W, H, qp = 96, 64, 32
+    frames = [wrenc_b200.synth_frame(W, H, frame=f) for f in range(11)]
+    one = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=1)
+    want = one.encode_pictures(frames)
+    one.close()
+    for B, lead in ((3, 6), (4, 1), (2, 3)):
+        enc = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=B)
+        got, nsub = [], 0
+        while len(got) < len(frames):
+            while nsub < len(frames) and nsub - len(got) < min(lead, 2 * B):
+                enc.submit(100 + nsub, *frames[nsub])
+                nsub += 1
+            got.append(enc.receive())
+        enc.close()
+        assert [r["pic_idx"] for r in got] == [100 + i for i in range(len(frames))]
+        for i, (o, r) in enumerate(zip(want, got)):
+            assert_same(o, r, f"B={B} lead={lead} frame {i}")
+
+
+def test_two_handles_in_one_process_and_interleaved_use():
+    """Two handles (different geometry and QP) used alternately in one process: per-handle / per-device state only (the L2
+    persisting limit, the shared-memory opt-in and the work lists are not process-wide singletons)."""
+    fa = [wrenc_b200.synth_frame(96, 64, frame=f) for f in range(3)]
+    fb = [wrenc_b200.random_frame(64, 96, 40 + f) for f in range(3)]
+    a = wrenc_b200.SearchEncoder(96, 64, qp=32, pictures_in_flight=2)
+    b = wrenc_b200.SearchEncoder(64, 96, qp=27, pictures_in_flight=1)
+    ra, rb = [], []
+    for i in range(3):
+        a.submit(i, *fa[i])
+        b.submit(i, *fb[i])
+        rb.append(b.receive())
+    while a.pending():
+        ra.append(a.receive())
+    a.close()
+    oa, ob = Oracle(32, 3), Oracle(27, 3)
+    for i in range(3):
+        assert_same(oa.encode_picture(*fa[i], want_slice_data=True), ra[i], f"handle a frame {i}")
+        assert_same(ob.encode_picture(*fb[i], want_slice_data=True), rb[i], f"handle b frame {i}")
+    b.close()
 
 
 def test_full_size_properties_1080p():
@@ -244,3 +294,23 @@ def test_full_frame_oracle_parity_1080p_and_2160p():
             enc.close()
         for (W, H, qp, _), fut, r in zip(cases, futs, got):
             assert_same(fut.result(), r, f"{W}x{H} qp {qp} full frame")
+
+
+def test_bin_arena_grow_and_retry_path():
+    """The slice coder sizes its bin arena from earlier batches and never synchronises mid-path; a batch that outgrows it
+    reports -2 lengths, the host grows the arena and codes the batch again.  A one-entry-per-CTU initial arena
+    (WRENC_B200_ARENA_ENTRIES_PER_CTU, read per allocation, hence the subprocess) forces that path; slice_data must not change."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = GOLD[-1]
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import wrenc_b200\n"
+        "g = np.load(%r); H, W = g['y'].shape\n"
+        "enc = wrenc_b200.SearchEncoder(W, H, qp=int(g['qp']), max_split_depth=int(g['depth']), pictures_in_flight=2, extra_params=str(g['extra']) or None)\n"
+        "r = enc.encode_pictures([(g['y'], g['cb'], g['cr'])] * 5)\n"
+        "assert all(x['slice_data'] == g['slice_data'].tobytes() for x in r), 'slice_data differs'\n"
+        "print('ok', len(r[0]['slice_data']))\n" % (root, path))
+    env = dict(os.environ, WRENC_B200_ARENA_ENTRIES_PER_CTU="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), f"{out.stdout} {out.stderr[-400:]}"

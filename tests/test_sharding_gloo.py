@@ -27,6 +27,10 @@ def _worker(rank, world, port, q):
     b, e = shard_range(n, world, rank)
     bufs = [bytes([p]) * (p * 37 % 11 + (0 if p == 3 else 1)) for p in range(b, e)]  # variable lengths, picture 3 empty
     out = gather_in_order(bufs, dst=0)
+    from wrenc_b200.sharding import gather_in_order_host
+    for _ in range(2):  # the host shared-memory variant, twice (per-call sequence numbers keep the files apart)
+        out_h = gather_in_order_host(bufs, dst=0)
+        assert (out_h == out) if rank == 0 else (out_h is None)
     if rank == 0:
         q.put([bytes(x) for x in out])
     else:

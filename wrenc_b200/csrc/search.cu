@@ -1206,15 +1206,46 @@ static size_t smem_request() {  // dev-time knob: WRENC_B200_SMEM_PAD bytes of e
     return sizeof(Shared) + pad;
 }
 
-cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wrenc_b200_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request());
+// The dynamic shared memory opt-in is a per-device function attribute: set once per device, not once per process.
+static cudaError_t ensure_smem_attr() {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        e = cudaFuncSetAttribute(wrenc_b200_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_request());
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    wrenc_b200_search_kernel<<<grid, NTHREADS, smem_request(), stream>>>(P);
-    return cudaGetLastError();
+    return cudaSuccess;
+}
+
+cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream, const void *persist_base, size_t persist_bytes) {
+    cudaError_t e = ensure_smem_attr();
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem_request();
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (persist_base && persist_bytes) {  // per-launch attribute: the caller's stream attributes are left alone
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void *>(persist_base);
+        attr[0].val.accessPolicyWindow.num_bytes = persist_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    e = cudaLaunchKernelEx(&cfg, wrenc_b200_search_kernel, P);
+    if (e != cudaSuccess && cfg.numAttrs) {  // best effort: without the window the launch only costs DRAM traffic
+        cudaGetLastError();
+        cfg.numAttrs = 0;
+        e = cudaLaunchKernelEx(&cfg, wrenc_b200_search_kernel, P);
+    }
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 int search_ctas_per_sm() {

@@ -48,6 +48,8 @@ struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_dat
     const CtuRecord *records;  // [pic][Wc*Hc]
     const uint8_t *mode_map;   // [pic][(W/4)*(H/4)]
     uint16_t *bins;            // bin arena (entries: ctx index | bin << 9 | bypass << 10); nullptr = counting + staging pass
+    unsigned long long bins_cap;  // entries the arena holds: strings that would end beyond it are not written and their picture reports
+                               //   out_len = -2, so that the host can grow the arena and run the passes again WITHOUT a mid-path sync
     uint16_t *stage;           // [pic][ctu][stage_cap]: the counting pass keeps the first stage_cap entries of every CTU's bin string here, so that
     int stage_cap;             //   only CTUs with longer strings are walked a second time; the others are copied to their arena offset
     int *bin_count;            // [pic][ctu] entries of the CTU's bin string
@@ -76,6 +78,7 @@ cudaError_t launch_block(const BlockParams &P, int grid, cudaStream_t stream);
 size_t search_smem_bytes();
 int search_ctas_per_sm();
 int search_ctus_per_cta();  // CTUs one CTA searches in lock step; the work list is made of batches of this many slots
-cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream);
+// persist_base/persist_bytes: L2 persisting access window for this launch only (the per-CTA scratch), or nullptr/0
+cudaError_t launch_search(const SearchParams &P, int grid, cudaStream_t stream, const void *persist_base = nullptr, size_t persist_bytes = 0);
 
 }  // namespace wb

@@ -430,6 +430,7 @@ extern "C" __global__ void __launch_bounds__(64) wrenc_b200_syntax_kernel(Syntax
         S.cap = Q.stage_cap;
     } else {
         if (Q.bin_count[gid] <= Q.stage_cap) return;
+        if (Q.bin_offset[gid] + (unsigned long long)Q.bin_count[gid] > Q.bins_cap) return;  // arena too small: the coder kernel reports it
         S.p = Q.bins + Q.bin_offset[gid];
         S.cap = 0x7fffffff;
     }
@@ -451,6 +452,7 @@ extern "C" __global__ void __launch_bounds__(256) wrenc_b200_bin_compact_kernel(
     if (gid >= (long long)Q.n_pics * Q.Wc * Q.Hc) return;
     const int cnt = Q.bin_count[gid];
     if (cnt > Q.stage_cap) return;
+    if (Q.bin_offset[gid] + (unsigned long long)cnt > Q.bins_cap) return;  // arena too small: the coder kernel reports it
     const uint16_t *src = Q.stage + (size_t)gid * Q.stage_cap;
     uint16_t *dst = Q.bins + Q.bin_offset[gid];
     for (int i = lane; i < cnt; i += 32) dst[i] = src[i];
@@ -544,6 +546,10 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
     const size_t g0 = (size_t)pic * nctu;
     const unsigned long long beg = Q.bin_offset[g0];
     const unsigned long long end = Q.bin_offset[g0 + nctu - 1] + (unsigned long long)Q.bin_count[g0 + nctu - 1];
+    if (end > Q.bins_cap) {  // this picture's strings did not fit the arena (sized from earlier batches): nothing was written for it
+        if (lane == 0) Q.out_len[pic] = -2;
+        return;
+    }
     const uint16_t *b = Q.bins + beg;
     const long long total = (long long)(end - beg);
     unsigned nxt = lane < total ? b[lane] : 0u;

@@ -24,7 +24,7 @@ EXPORTS = [
     "wrenc_b200_workspace_bytes", "wrenc_b200_get_consts", "wrenc_b200_block_predict", "wrenc_b200_block_fwd_dct",
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
     "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts", "wrenc_b200_write_nal", "wrenc_b200_write_parameter_sets",
-    "wrenc_b200_write_picture", "wrenc_b200_header_rbsp",
+    "wrenc_b200_write_picture", "wrenc_b200_header_rbsp", "wrenc_b200_prepare", "wrenc_b200_code_resident_retry",
 ]
 
 
@@ -41,6 +41,10 @@ class Consts(C.Structure):
 
 class WrencB200Error(RuntimeError):
     pass
+
+
+class WrencB200Full(WrencB200Error):
+    """submit: every batch slot holds pictures that have not been received (WRENC_B200_EFULL)."""
 
 
 _lib = None
@@ -78,6 +82,10 @@ def load_library():
     L.wrenc_b200_search_resident.argtypes = [vp, i32, vp, vp, vp, vp, vp]
     L.wrenc_b200_code_resident.restype = C.c_int
     L.wrenc_b200_code_resident.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, vp, vp]
+    L.wrenc_b200_code_resident_retry.restype = C.c_int
+    L.wrenc_b200_code_resident_retry.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, vp, vp]
+    L.wrenc_b200_prepare.restype = C.c_int
+    L.wrenc_b200_prepare.argtypes = [vp, i32]
     L.wrenc_b200_workspace_bytes.restype = C.c_size_t
     L.wrenc_b200_workspace_bytes.argtypes = [vp, i32]
     L.wrenc_b200_get_consts.restype = C.c_int
@@ -211,6 +219,8 @@ class SearchEncoder:
     __del__ = close
 
     def _check(self, rc):
+        if rc == -5:
+            raise WrencB200Full(self.L.wrenc_b200_last_error(self.h).decode())
         if rc < 0:
             raise WrencB200Error(f"wrenc_b200 error {rc}: {self.L.wrenc_b200_last_error(self.h).decode()}")
         return rc
@@ -263,10 +273,13 @@ class SearchEncoder:
         """frames: iterable of (y, cb, cr).  Returns the per-picture results in order (batches of pictures_in_flight)."""
         results = []
         for i, (y, cb, cr) in enumerate(frames):
-            self.submit(i, y, cb, cr)
-            if self.pending() == self.pictures_in_flight:
-                while self.pending():
-                    results.append(self.receive())
+            while True:
+                try:
+                    self.submit(i, y, cb, cr)
+                    break
+                except WrencB200Full:  # every batch slot is in flight: take the oldest batch's pictures first
+                    for _ in range(min(self.pending(), self.pictures_in_flight)):
+                        results.append(self.receive())
         while self.pending():
             results.append(self.receive())
         return results
@@ -283,6 +296,17 @@ class SearchEncoder:
             return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
         st = C.c_void_p(int(stream)) if stream else None
         return self._check(self.L.wrenc_b200_code_resident(self.h, int(n_pictures), p(d_levels), p(d_records), p(d_out), int(out_cap), p(d_out_len), st))
+
+    def code_resident_retry(self, n_pictures, d_levels, d_records, d_out, out_cap, d_out_len, stream=None):
+        """After code_resident reported -2 lengths (bin arena too small for this batch): grow it and code again (blocks)."""
+        def p(t):
+            return C.c_void_p(t.data_ptr() if hasattr(t, "data_ptr") else int(t))
+        st = C.c_void_p(int(stream)) if stream else None
+        return self._check(self.L.wrenc_b200_code_resident_retry(self.h, int(n_pictures), p(d_levels), p(d_records), p(d_out), int(out_cap), p(d_out_len), st))
+
+    def prepare(self, n_pictures):
+        """Allocate the resident workspace and upload the work list for batches of n_pictures (blocking), so that the resident calls only enqueue."""
+        return self._check(self.L.wrenc_b200_prepare(self.h, int(n_pictures)))
 
     # ---- per-block entry points ----
     def block_predict(self, rec, x, y, w, tree, ar, bl, c, mode):

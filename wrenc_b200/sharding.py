@@ -45,3 +45,43 @@ def gather_in_order(buffers, dst=0, device=None):
             out.append(data[off:off + s])
             off += s
     return out
+
+
+_seq = 0
+
+
+def gather_in_order_host(buffers, dst=0, barrier=None, rank=None, world=None, directory="/dev/shm"):
+    """The same ordered gather for ranks of ONE node without touching a device or a collective's staging buffers
+    ("D2H per GPU + host concatenation in pic_idx order"): every rank drops its pictures' sizes and
+    bytes into a host shared-memory file, one barrier, and the writer rank concatenates the files in rank order.  `barrier`
+    defaults to torch.distributed.barrier; rank / world default to the process group's."""
+    global _seq
+    import os
+    import struct
+    if rank is None or world is None:
+        rank, world = dist.get_rank(), dist.get_world_size()
+    barrier = barrier or dist.barrier
+    job = os.environ.get("MASTER_PORT", "0") + "_" + os.environ.get("TORCHELASTIC_RUN_ID", "x")
+    _seq += 1
+    name = lambda r: os.path.join(directory, f"wrenc_b200_gather_{job}_{_seq}_{r}")  # noqa: E731
+    with open(name(rank) + ".tmp", "wb") as f:
+        f.write(struct.pack("<q", len(buffers)))
+        f.write(struct.pack(f"<{len(buffers)}q", *[len(b) for b in buffers]))
+        for b in buffers:
+            f.write(b)
+    os.replace(name(rank) + ".tmp", name(rank))
+    barrier()
+    if rank != dst:
+        return None
+    out = []
+    for r in range(world):
+        with open(name(r), "rb") as f:
+            data = f.read()
+        os.unlink(name(r))
+        n = struct.unpack_from("<q", data, 0)[0]
+        sizes = struct.unpack_from(f"<{n}q", data, 8)
+        off = 8 + 8 * n
+        for s in sizes:
+            out.append(data[off:off + s])
+            off += s
+    return out
