@@ -75,6 +75,10 @@ int wrenc_b200_submit(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const u
  * reader fills): no staging copy, the planes are read by the copy engine asynchronously and must stay valid and unchanged
  * until the picture has been received.  WRENC_B200_EINVAL if a plane is not page-locked. */
 int wrenc_b200_submit_pinned(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, const uint8_t *cb, const uint8_t *cr);
+/* Page-locked host memory for the caller's frame reader (what submit_pinned wants): cudaHostAlloc / cudaFreeHost without making
+ * the caller link the CUDA runtime.  alloc returns NULL on failure. */
+void *wrenc_b200_alloc_pinned(size_t bytes);
+void wrenc_b200_free_pinned(void *p);
 /* Strictly in submit order.  Launches the pending batch if it has not run yet, then blocks until THIS picture's outputs have
  * landed in host memory (pictures of one batch become ready together when its coder kernel ends; their bytes are then copied
  * back picture by picture, each with its own event).  slice_data/len: CABAC-coded slice_data() bytes of the picture (byte

@@ -548,6 +548,19 @@ int wrenc_b200_submit_pinned(wrenc_b200 *h, uint64_t pic_idx, const uint8_t *y, 
     return submit_common(h, pic_idx, y, cb, cr, true);
 }
 
+void *wrenc_b200_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void wrenc_b200_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+    cudaGetLastError();
+}
+
 int wrenc_b200_flush(wrenc_b200 *h) {
     if (!h) return WRENC_B200_EINVAL;
     Slot &s = h->slots[h->fill];

@@ -394,7 +394,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
     const WarpScratch ws = warp_scratch(S, warp);
     const bool cu4 = id.depth == 3;  // 4x4 luma CU (else the 8x8 SINGLE_TREE CU)
     const int ncomp = cu4 ? 1 : 3;
-    const int nparts = cu4 ? 3 : 4;
+    const int nparts = cu4 ? 1 : 4;  // 4x4 luma CU: eight modes per pass, the whole direction search is one warp task
     constexpr int nst = 0;
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     // ---- A
@@ -419,7 +419,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
             full_task(V, tab, V.c->g, nd, 0, t, ws, lane, ssd, rate, t);
             if (lane == 0) { V.c->pd_ssd[t][0] = ssd; V.c->pd_rate[t][0] = rate; }
         } else if (t < (cu4 ? 0 : 2) + nparts) {
-            dir_search_part(V, nd, nparts - 1 - (t - (cu4 ? 0 : 2)), nparts, lane);  // the last part is the longest: it goes first
+            dir_search_part(V, nd, nparts - 1 - (t - (cu4 ? 0 : 2)), nparts, reinterpret_cast<uint8_t *>(ws.refx), lane);  // the last part is the longest: it goes first
         } else {  // 4x4 TBs: planar | DC of the luma CU, or Cb | Cr of one mode
             const int half = lane >> 4;
             const int mode = cu4 ? half : t - (2 + nparts), c = cu4 ? 0 : 1 + half;
@@ -889,6 +889,7 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
         S.tb.fc[tid] = (int)pk;
     }
     if (tid == 0) S.tb.ls_recip = (uint32_t)(0x100000000ull / (unsigned long long)tab->ls) + 1u;
+    if (tid == 32) a4::fill_tap_tables(S.tb.taps, c_fC);
     for (int m = tid; m < 68; m += NTHREADS) {
         const int ang = m < 67 ? c_angle[m] : 0;
         const int inv = ang > 0 ? (512 * 32 + ang / 2) / ang : (ang < 0 ? -((512 * 32 + (-ang) / 2) / -ang) : 0);
@@ -1047,6 +1048,18 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, WB_MINB) wrenc_b200_searc
         mbar_wait(&S.tma_bar, tma_phase);  // all source bytes have landed
         tma_phase ^= 1;
         __syncthreads();
+        // transposed copy of the source blocks (the horizontal angular modes predict column-wise, four samples of a column per lane)
+        for (int i = tid; i < KC * 1536; i += NTHREADS) {
+            const int k = i / 1536, j = i - k * 1536;
+            CtuCtx &C = S.c[k];
+            if (!C.active) continue;
+            if (j < 1024) C.orgYT[(j & 31) * 32 + (j >> 5)] = C.orgY[j];
+            else {
+                const int c = (j - 1024) >> 8, q = (j - 1024) & 255;
+                C.orgCT[c][(q & 15) * 16 + (q >> 4)] = C.orgC[c][q];
+            }
+        }
+        __syncthreads();
         WB_PROF(82);
         ctu_search(S, P, S_slot);
         __syncthreads();
@@ -1134,9 +1147,9 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
             if (P.mode > 66) cclm_downsample(V, g, nd, lane);
             else build_refs(V, g, nd, c, lane);
             __syncwarp();
-            PredCtx pc;
-            pred_setup(V, g, nd, c, P.mode, ws.refx, lane, pc);
-            for (int i = lane; i < n * n; i += 32) P.out8[i] = (uint8_t)pred_sample(V, pc, i % n, i / n);
+            predict_block(V, g, nd, c, P.mode, ws.refx, ws.pred, lane);  // the search kernel's own prediction path (the SAD it returns is not used here)
+            __syncwarp();
+            for (int i = lane; i < n * n; i += 32) P.out8[i] = ws.pred[i];
         }
         return;
     }

@@ -22,6 +22,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "ang4.cuh"
 #include "search_kernel_api.h"
 
 namespace wb {
@@ -94,6 +95,7 @@ struct Tables {
     int8_t ang[68];            // intraPredAngle per mode
     uint32_t ls_recip;         // floor(2^32 / ls) + 1: the trellis divides by the (launch-constant) level scale, see div_ls
     uint8_t angp[4][68];       // per block size (log2 - 2) and angular mode: bit 0 fG taps (luma), bits 1-2 PDPC nScale, bit 3 PDPC applies
+    a4::TapTables taps;        // fC / fG / doubled chroma taps, packed 4 x int8 per iFact (ang4.cuh)
 };
 
 struct WarpScratch {  // pointers into the scratch pool
@@ -104,6 +106,7 @@ struct WarpScratch {  // pointers into the scratch pool
 };
 
 constexpr int MAXTASK = 48;
+constexpr int LN_OFF = 40, LN_SIZE = 120;  // byte reference lines: index range [-32 - slack, 2 * 32 + 3 + slack]
 
 struct CtuGeom {
     int cx, cy;  // absolute luma position of the CTU
@@ -125,6 +128,11 @@ struct alignas(16) CtuCtx {
     int16_t seqF[132];        // the same line of the [1 2 1] filtered luma references
     int16_t refL[3][2][68];
     int16_t refA[3][2][64];
+    // the same reference samples as BYTES in two mirrored lines per component (ang4.cuh): ln[v][0] = up (corner, above...),
+    // ln[v][1] = dn (corner, left...), v = 0 luma, 1 luma [1 2 1]-filtered, 2 Cb, 3 Cr; index 0 at byte LN_OFF, valid [-n, 2n+3]
+    alignas(8) uint8_t ln[4][2][LN_SIZE];
+    alignas(16) uint8_t orgYT[1024];     // the source block transposed (orgYT[x * 32 + y]): the horizontal angular modes predict column-wise
+    alignas(16) uint8_t orgCT[2][256];
     uint8_t pds[256];         // CCLM down-sampled luma of the current node
     uint8_t leftModes[8];     // final luma modes of the left CTU's right-most 4x4 column
     // task results
@@ -164,11 +172,11 @@ struct Shared {
     // per-warp scratch
     int16_t bigA[NBIG][1024], bigB[NBIG][1024];
     uint16_t bigW[NBIG][1024];
-    uint8_t bigP[NBIG][1024];
+    alignas(16) uint8_t bigP[NBIG][1024];
     int16_t smA[NW - NBIG + 1][256], smB[NW - NBIG + 1][256];
     uint16_t smW[NW - NBIG + 1][256];
-    uint8_t smP[NW - NBIG + 1][256];
-    int16_t refx[NW][100];
+    alignas(16) uint8_t smP[NW - NBIG + 1][256];
+    alignas(16) int16_t refx[NW][100];  // per-warp scratch line: projected references of the negative-angle modes (as bytes)
 };
 
 static_assert(offsetof(CtuCtx, lvY) % 8 == 0 && offsetof(CtuCtx, lvC) % 8 == 0 && sizeof(CtuCtx) % 8 == 0, "commit_root_slot stores the levels as 64-bit words");
@@ -240,6 +248,22 @@ __device__ __forceinline__ float rd_cost(unsigned ssd, long long level, float la
 // ---------------------------------------------------------------------------------------------------------------
 // reference samples (intra_predictor.rs:146-353), one warp per component
 // ---------------------------------------------------------------------------------------------------------------
+// byte reference lines (ang4.cuh): store left sample li (li = 0: the corner) / above sample ai of line variant v into both
+// mirrored lines, with the three copies of the last sample that stand for ref[min(idx, 2n)]
+__device__ __forceinline__ int ln_variant(int c, int filt) { return c == 0 ? filt : 1 + c; }
+__device__ __forceinline__ void ln_put_left(const Ctx S, int v, int li, int n, int val) {
+    uint8_t *up = S.c->ln[v][0] + LN_OFF, *dn = S.c->ln[v][1] + LN_OFF;
+    dn[li] = (uint8_t)val;
+    if (li <= n) up[-li] = (uint8_t)val;
+    if (li == 2 * n) { dn[li + 1] = (uint8_t)val; dn[li + 2] = (uint8_t)val; dn[li + 3] = (uint8_t)val; }
+}
+__device__ __forceinline__ void ln_put_above(const Ctx S, int v, int ai, int n, int val) {
+    uint8_t *up = S.c->ln[v][0] + LN_OFF, *dn = S.c->ln[v][1] + LN_OFF;
+    up[1 + ai] = (uint8_t)val;
+    if (1 + ai <= n) dn[-(1 + ai)] = (uint8_t)val;
+    if (ai == 2 * n - 1) { up[2 * n + 1] = (uint8_t)val; up[2 * n + 2] = (uint8_t)val; up[2 * n + 3] = (uint8_t)val; }
+}
+
 __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node nd, int c, int lane) {
     WB_SHARED_CTX(S);
     const int cs = c != 0;
@@ -302,8 +326,8 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
         if (r < rounds) {
             int j = r * 32 + lane;
             if (j < tot) {
-                if (j < nl) L[nl - 1 - j] = (int16_t)vals[r];
-                else A[j - nl] = (int16_t)vals[r];
+                if (j < nl) { L[nl - 1 - j] = (int16_t)vals[r]; ln_put_left(S, ln_variant(c, 0), nl - 1 - j, n, vals[r]); }
+                else { A[j - nl] = (int16_t)vals[r]; ln_put_above(S, ln_variant(c, 0), j - nl, n, vals[r]); }
                 seq[j] = (int16_t)vals[r];
             }
         }
@@ -318,6 +342,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             else v = (L[i + 1] + 2 * L[i] + L[i - 1] + 2) >> 2;
             LF[i] = (int16_t)v;
             S.c->seqF[nl - 1 - i] = (int16_t)v;
+            ln_put_left(S, 1, i, n, v);
         }
         for (int i = lane; i < na; i += 32) {
             int v;
@@ -326,6 +351,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             else v = (A[i - 1] + 2 * A[i] + A[i + 1] + 2) >> 2;
             AF[i] = (int16_t)v;
             S.c->seqF[nl + i] = (int16_t)v;
+            ln_put_above(S, 1, i, n, v);
         }
     }
     __syncwarp();
@@ -354,8 +380,8 @@ __device__ __noinline__ void build_refs4(const Ctx S, const CtuGeom g, const Nod
     int val = __shfl_sync(0xffffffffu, v, src);
     if (!mask) val = 128;
     if (j < tot) {
-        if (j < nl) S.c->refL[c][0][nl - 1 - j] = (int16_t)val;
-        else S.c->refA[c][0][j - nl] = (int16_t)val;
+        if (j < nl) { S.c->refL[c][0][nl - 1 - j] = (int16_t)val; ln_put_left(S, ln_variant(c, 0), nl - 1 - j, 4, val); }
+        else { S.c->refA[c][0][j - nl] = (int16_t)val; ln_put_above(S, ln_variant(c, 0), j - nl, 4, val); }
         S.c->seq[c][j] = (int16_t)val;
     }
     __syncwarp();
@@ -365,13 +391,11 @@ __device__ __noinline__ void build_refs4(const Ctx S, const CtuGeom g, const Nod
 // prediction (per-sample evaluation after a per-task setup)
 // ---------------------------------------------------------------------------------------------------------------
 struct PredCtx {
-    int kind;  // 0 planar, 1 dc, 2 angular, 3 cclm
+    int kind;  // 0 planar, 1 dc, 3 cclm (angular modes: ang4.cuh)
     int mode, c, n, l2;
     const int16_t *lf;  // left incl. corner at [0]
     const int16_t *ab;  // above
-    int dc;
-    int ang, inv_angle, vertical, use_fg, nscale, pdpc;
-    const int16_t *rx;  // refx + n
+    int dc, nscale;
     int a, k, b;        // cclm
     bool cclm128;
 };
@@ -493,14 +517,13 @@ __device__ __noinline__ void cclm_params(const Ctx S, const CtuGeom g, const Nod
     }
 }
 
-// per-task setup: picks the reference arrays, builds the angular projection array, DC value, CCLM parameters
-__device__ __forceinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, int lane, PredCtx &pc) {
+// per-task setup of the non-angular modes: picks the reference arrays, DC value, CCLM parameters
+__device__ __forceinline__ void pred_setup(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int lane, PredCtx &pc) {
     WB_SHARED_CTX(S);
-    WB_SHARED_PTR(refx);
     const int cs = c != 0;
     const int n = nd.w >> cs;
     pc.mode = mode; pc.c = c; pc.n = n; pc.l2 = ilog2i(n);
-    pc.pdpc = 0; pc.nscale = 0; pc.dc = 0; pc.ang = 0; pc.inv_angle = 0; pc.vertical = 0; pc.use_fg = 0; pc.rx = refx + n;
+    pc.nscale = (2 * pc.l2 - 2) >> 2; pc.dc = 0;
     pc.a = pc.k = pc.b = 0; pc.cclm128 = false;
     if (mode > 66) {
         pc.kind = 3;
@@ -508,117 +531,39 @@ __device__ __forceinline__ void pred_setup(const Ctx S, const CtuGeom g, const N
         cclm_params(S, g, nd, c, mode, pc);
         return;
     }
-    const int filt = (c == 0 && n >= 8 && (mode == 0 || mode == 2 || mode == 34 || mode == 66)) ? 1 : 0;
+    const int filt = (c == 0 && n >= 8 && mode == 0) ? 1 : 0;
     pc.lf = S.c->refL[c][filt];
     pc.ab = S.c->refA[c][filt];
     if (mode == MODE_PLANAR) {
-        pc.kind = 0; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
+        pc.kind = 0;
         return;
     }
-    if (mode == MODE_DC) {
-        pc.kind = 1; pc.pdpc = 1; pc.nscale = (2 * pc.l2 - 2) >> 2;
-        int s = 0;
-        for (int i = lane; i < n; i += 32) s += pc.ab[i] + pc.lf[1 + i];
-        s = warp_sum(s) + n;
-        pc.dc = (s >> (pc.l2 + 1)) & 255;
-        return;
-    }
-    pc.kind = 2;
-    const int ang = S.tb->ang[mode];
-    pc.ang = ang;
-    pc.inv_angle = S.tb->invang[mode];
-    pc.vertical = mode >= 34;
-    if (mode == 2 || mode == 34 || mode == 66) pc.use_fg = 0;
-    else {
-        int md = min(abs(mode - 50), abs(mode - 18));
-        int thr = pc.l2 == 2 ? 24 : (pc.l2 == 3 ? 14 : (pc.l2 == 4 ? 2 : 0));
-        pc.use_fg = md > thr;
-    }
-    if (mode <= 18 || mode >= 50) {
-        pc.pdpc = 1;
-        if (mode == 18 || mode == 50) pc.nscale = (2 * pc.l2 - 2) >> 2;
-        else pc.nscale = min(pc.l2 - ilog2i(3 * pc.inv_angle - 2) + 8, 2);
-        if (pc.nscale < 0) pc.pdpc = 0;
-    }
-    // projection array r[idx], idx in [-n, 2n+2]  (intra_predictor.rs:1398-1414 / 1480-1495)
-    int16_t *r = refx + n;
-    const int lo = ang < 0 ? -n : 0, hi = ang < 0 ? n + 1 : 2 * n + 2;
-    for (int idx = lo + lane; idx <= hi; idx += 32) {
-        int v;
-        if (pc.vertical) {
-            if (idx < 0) v = pc.lf[min((idx * pc.inv_angle + 256) >> 9, n)];
-            else if (idx == 0) v = pc.lf[0];
-            else v = pc.ab[min(idx - 1, 2 * n - 1)];
-        } else {
-            if (idx < 0) {
-                int t = min((idx * pc.inv_angle + 256) >> 9, n);
-                v = t == 0 ? pc.lf[0] : pc.ab[t - 1];
-            } else v = pc.lf[min(idx, 2 * n)];
-        }
-        r[idx] = (int16_t)v;
-    }
-    __syncwarp();
+    pc.kind = 1;
+    int s = 0;
+    for (int i = lane; i < n; i += 32) s += pc.ab[i] + pc.lf[1 + i];
+    s = warp_sum(s) + n;
+    pc.dc = (s >> (pc.l2 + 1)) & 255;
 }
 
-// KIND >= 0: the caller has already branched on pc.kind (the per-sample loop then carries no dispatch)
-template <int KIND = -1>
+// planar (0), DC (1) incl. PDPC, CCLM (3)
 __device__ __forceinline__ int pred_sample(const Ctx S, const PredCtx &pc, int x, int y) {
     const int n = pc.n;
-    const int kind = KIND >= 0 ? KIND : pc.kind;
-    int p;
-    if (kind == 3) {
+    if (pc.kind == 3) {
         if (pc.cclm128) return 128;
         return clip8(((S.c->pds[y * n + x] * pc.a) >> pc.k) + pc.b);
     }
     const int16_t *lrs = pc.lf + 1, *ars = pc.ab;
-    if (kind == 0) {
+    int p;
+    if (pc.kind == 0) {
         int pv = (n - 1 - y) * ars[x] + (y + 1) * lrs[n];
         int ph = (n - 1 - x) * lrs[y] + (x + 1) * ars[n];
         p = ((pv + ph + n) >> (pc.l2 + 1)) & 255;
-    } else if (kind == 1) {
-        p = pc.dc;
     } else {
-        int t = pc.vertical ? y : x, u = pc.vertical ? x : y;
-        int prod = (t + 1) * pc.ang;
-        int iidx = prod >> 5, ifact = prod & 31;
-        const int16_t *r = pc.rx + u + iidx;
-        if (pc.c == 0) {
-            int f0, f1, f2, f3;
-            if (pc.use_fg) {
-                int h = ifact >> 1;
-                f0 = 16 - h; f1 = 32 - h; f2 = 16 + h; f3 = h;
-            } else {
-                int pk = S.tb->fc[ifact];
-                f0 = (int8_t)(pk & 255); f1 = (int8_t)((pk >> 8) & 255); f2 = (int8_t)((pk >> 16) & 255); f3 = (int8_t)((pk >> 24) & 255);
-            }
-            int s = f0 * r[0] + f1 * r[1] + f2 * r[2] + f3 * r[3];
-            p = clip8((s + 32) >> 6);
-        } else if (ifact != 0) {
-            p = (((32 - ifact) * r[1] + ifact * r[2] + 16) >> 5) & 255;
-        } else {
-            p = r[1] & 255;
-        }
+        p = pc.dc;
     }
-    if (pc.pdpc) {
-        int refl = 0, reft = 0, wl = 0, wt = 0;
-        const int mode = pc.mode, ns = pc.nscale;
-        if (mode < 2) {
-            refl = lrs[y]; reft = ars[x]; wl = pdpc_w(ns, x); wt = pdpc_w(ns, y);
-        } else if (mode == 18 || mode == 50) {
-            int corner = pc.lf[0];
-            refl = lrs[y] - corner + p; reft = ars[x] - corner + p;
-            if (mode == 50) wl = pdpc_w(ns, x); else wt = pdpc_w(ns, y);
-        } else if (mode < 18) {
-            if (y < (3 << ns)) reft = ars[x + (((y + 1) * pc.inv_angle + 256) >> 9)];
-            wt = pdpc_w(ns, y);
-        } else {
-            if (x < (3 << ns)) refl = lrs[y + (((x + 1) * pc.inv_angle + 256) >> 9)];
-            wl = pdpc_w(ns, x);
-        }
-        int v = (int16_t)(refl * wl + reft * wt + (64 - wt - wl) * p + 32);
-        p = clip8(v >> 6);
-    }
-    return p;
+    const int wl = pdpc_w(pc.nscale, x), wt = pdpc_w(pc.nscale, y);
+    const int v = (int16_t)(lrs[y] * wl + ars[x] * wt + (64 - wt - wl) * p + 32);
+    return clip8(v >> 6);
 }
 
 // Angular prediction of one sample straight from the reference line (no per-task projection array): with
@@ -677,77 +622,145 @@ __device__ __forceinline__ int ang_sample_direct(const Ctx S, int c, int n, int 
     return p;
 }
 
-// SAD of one angular mode for the direction search, summed over the CU's components.  8x8 SINGLE_TREE CU: the warp covers
-// the 64 luma samples in two iterations, then Cb | Cr by the two half-warps (result uniform over the warp).  4x4 luma CU:
-// one iteration, and the two half-warps evaluate two different modes (`mode` is per half; result uniform within a half).
-__device__ __noinline__ unsigned dir_sad(const Ctx S, const Node nd, int mode, int lane) {
+// ---------------------------------------------------------------------------------------------------------------
+// angular prediction, four samples per lane (ang4.cuh)
+// ---------------------------------------------------------------------------------------------------------------
+// per (mode, component, block size) constants; mode may differ from lane to lane
+__device__ __forceinline__ a4::Mode a4_setup(const Ctx S, int c, int n, int l2, int mode) {
+    a4::Mode m;
+    const unsigned ap = S.tb->angp[l2 - 2][mode];  // mode / size dependent switches, tabulated once per CTA (init_tables)
+    m.ang = S.tb->ang[mode];
+    m.inv = S.tb->invang[mode];
+    const int v = ln_variant(c, (c == 0 && n >= 8 && (mode == 2 || mode == 34 || mode == 66)) ? 1 : 0);
+    const int vert = mode >= 34;
+    m.main = S.c->ln[v][vert ? 0 : 1] + LN_OFF;
+    m.side = S.c->ln[v][vert ? 1 : 0] + LN_OFF;
+    m.taps = c ? 2 : (int)(ap & 1u);
+    m.pdpc = (ap & 8u) ? ((mode == 18 || mode == 50) ? 1 : 2) : 0;
+    m.ns = (int)((ap >> 1) & 3u);
+    return m;
+}
+
+// source samples matching a quad of a (t, u) line: rows of the block for the vertical modes, rows of the TRANSPOSED block for the
+// horizontal ones (bx, by: block origin in its component plane)
+__device__ __forceinline__ unsigned org_quad(const Ctx S, int c, int mode, int bx, int by, int t, int u0) {
+    if (mode >= 34) return *reinterpret_cast<const unsigned *>((c ? S.c->orgC[c - 1] + ((by + t) << 4) : S.c->orgY + ((by + t) << 5)) + bx + u0);
+    return *reinterpret_cast<const unsigned *>((c ? S.c->orgCT[c - 1] + ((bx + t) << 4) : S.c->orgYT + ((bx + t) << 5)) + by + u0);
+}
+
+// SAD of ONE angular mode over the three components of an 8x8 SINGLE_TREE CU in one pass: lanes 0-15 the 16 quads of the luma
+// block, lanes 16-19 / 20-23 the four quads of the Cb / Cr 4x4 blocks.  scr: the warp's scratch line (>= 80 bytes).
+__device__ __noinline__ unsigned dir_sad8(const Ctx S, const Node nd, int mode, uint8_t *scr, int lane) {
     WB_SHARED_CTX(S);
-    const bool luma_only = nd.tree == DUAL_TREE_LUMA;
-    const int nit = luma_only ? 1 : 3;
-    unsigned s = 0;
-#pragma unroll 1
-    for (int j = 0; j < nit; j++) {
-        const bool last = j == nit - 1;
-        const int c = (last && !luma_only) ? 1 + (lane >> 4) : 0;
-        const int idx = last ? (lane & 15) : 32 * j + lane;
-        const int cs = c != 0, n = nd.w >> cs, l2 = ilog2i(n), bx = nd.x >> cs, by = nd.y >> cs;
-        const int x = idx & (n - 1), y = idx >> l2;
-        const int p = ang_sample_direct(S, c, n, l2, mode, x, y);
-        const uint8_t *org = cs ? S.c->orgC[c - 1] + ((by + y) << 4) : S.c->orgY + ((by + y) << 5);
-        s += (unsigned)abs(p - (int)org[bx + x]);
+    WB_SHARED_PTR(scr);
+    const int c = lane < 16 ? 0 : (lane < 20 ? 1 : 2);
+    const int n = c ? 4 : 8, l2 = c ? 2 : 3;
+    const int t = c ? (lane & 3) : (lane >> 1), u0 = c ? 0 : (lane & 1) * 4;
+    a4::Mode m = a4_setup(S, c, n, l2, mode);
+    if (m.ang < 0) {  // uniform: project the side line below index 0 (luma 18 elements, chroma 10 each) into the scratch line
+        uint8_t *pl = scr + 12, *pcb = scr + 36, *pcr = scr + 56;  // index 0 of the three projected lines ([-n-3, n+6] each)
+        if (lane < 18) {
+            const a4::Mode my = a4_setup(S, 0, 8, 3, mode);
+            a4::project_elem(pl, my.main, my.side, 8, my.inv, lane);
+        } else if (lane < 28) {
+            const a4::Mode my = a4_setup(S, 1, 4, 2, mode);
+            a4::project_elem(pcb, my.main, my.side, 4, my.inv, lane - 18);
+        }
+        if (lane < 10) {
+            const a4::Mode my = a4_setup(S, 2, 4, 2, mode);
+            a4::project_elem(pcr, my.main, my.side, 4, my.inv, lane);
+        }
+        __syncwarp();
+        m.main = c == 0 ? pl : (c == 1 ? pcb : pcr);
     }
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (!luma_only) s += __shfl_xor_sync(0xffffffffu, s, 16);
+    unsigned s = 0;
+    if (lane < 24) s = a4::sad4(a4::quad(m, S.tb->taps, t, u0), org_quad(S, c, mode, nd.x >> (c != 0), nd.y >> (c != 0), t, u0), 0u);
+    s = warp_sumu(s);
+    __syncwarp();  // the scratch line is rewritten by the next mode
     return s;
 }
 
-// The SAD-driven direction search of one CU up to 8x8 (block_splitter.rs:887-973: 13 coarse angular modes, then
-// step_search +-2 and +-1 on the summed SAD, first-minimum rules H6).  The coarse modes are split over `nparts` warp tasks;
-// each leaves its first minimum as (sad << 4 | index), and the warp that finishes last (shared-memory counter) takes the
-// overall first minimum and runs the two refinement steps.  The SADs are integers below 2^24, so the reference's f32
-// comparisons are integer comparisons.  Leaves dir, v0 (dir-1 valid), v1 (dir+1 valid) in the CTU context.
-__device__ __noinline__ void dir_search_part(const Ctx S, const Node nd, int part, int nparts, int lane) {
+// SADs of up to EIGHT angular modes of a 4x4 luma CU in one pass: four lanes (one quad = one line each) per mode; lanes
+// 4k .. 4k+3 evaluate `mode` (per lane; mode < 0: idle).  Returns the SAD of the lane's group.  scr >= 168 bytes.
+__device__ __noinline__ unsigned dir_sad4(const Ctx S, const Node nd, int mode, uint8_t *scr, int lane) {
     WB_SHARED_CTX(S);
-    const bool luma_only = nd.tree == DUAL_TREE_LUMA;  // 4x4 CU: two modes per call
-    const int half = lane >> 4;
-    // coarse modes [lo, hi) of this part (nparts is 3 or 4: constant divisors)
-    const int lo = nparts == 3 ? part * 13 / 3 : part * 13 / 4, hi = nparts == 3 ? (part + 1) * 13 / 3 : (part + 1) * 13 / 4;
+    WB_SHARED_PTR(scr);
+    const int slot = lane >> 2, t = lane & 3;
+    const bool act = mode >= 2;
+    a4::Mode m = a4_setup(S, 0, 4, 2, act ? mode : 2);
+    if (act && m.ang < 0) {  // per group: 10 projected elements, spread over the group's four lanes
+        uint8_t *pr = scr + 7 + 20 * slot;  // index 0; [-7, 10] used
+        a4::project_elem(pr, m.main, m.side, 4, m.inv, t);
+        a4::project_elem(pr, m.main, m.side, 4, m.inv, t + 4);
+        if (t < 2) a4::project_elem(pr, m.main, m.side, 4, m.inv, t + 8);
+        m.main = pr;
+    }
+    __syncwarp();
+    unsigned s = 0;
+    if (act) s = a4::sad4(a4::quad(m, S.tb->taps, t, 0), org_quad(S, 0, mode, nd.x, nd.y, t, 0), 0u);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    __syncwarp();
+    return s;
+}
+
+__device__ __forceinline__ unsigned warp_minu(unsigned v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// The SAD-driven direction search of one CU up to 8x8 (block_splitter.rs:887-973: 13 coarse angular modes, then
+// step_search +-2 and +-1 on the summed SAD, first-minimum rules H6).  The SADs are integers below 2^24, so the reference's
+// f32 comparisons are integer comparisons.  Leaves dir, v0 (dir-1 valid), v1 (dir+1 valid) in the CTU context.
+// 8x8 CU: the coarse modes are split over `nparts` warp tasks, one mode per pass (dir_sad8); each part leaves its first minimum
+// as (sad << 4 | index), and the warp that finishes last (shared-memory counter) takes the overall first minimum and runs the
+// two refinement steps.  4x4 luma CU (nparts = 1): eight modes per pass (dir_sad4): 13 coarse modes in two passes, each
+// refinement step in one.
+__device__ __noinline__ void dir_search_part(const Ctx S, const Node nd, int part, int nparts, uint8_t *scr, int lane) {
+    WB_SHARED_CTX(S);
+    const bool luma_only = nd.tree == DUAL_TREE_LUMA;
     unsigned bp = 0xffffffffu;
+    if (luma_only) {
 #pragma unroll 1
-    for (int i = lo; i < hi; i += luma_only ? 2 : 1) {
-        const int mi = luma_only ? min(i + half, hi - 1) : i;
-        const unsigned s = dir_sad(S, nd, c_cand15[2 + mi], lane);
-        const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
-        bp = min(bp, (s0 << 4) | (unsigned)i);
-        if (luma_only && i + 1 < hi) bp = min(bp, (s1 << 4) | (unsigned)(i + 1));
-    }
-    int last = 0;
-    if (lane == 0) {
-        S.c->dir_part[part] = bp;
+        for (int pass = 0; pass < 2; pass++) {
+            const int i = pass * 8 + (lane >> 2);
+            const unsigned s = dir_sad4(S, nd, i < 13 ? c_cand15[2 + i] : -1, scr, lane);
+            if (i < 13) bp = min(bp, (s << 4) | (unsigned)i);
+        }
+        bp = warp_minu(bp);
+    } else {
+        // coarse modes [lo, hi) of this part (nparts = 4: constant divisor)
+        const int lo = part * 13 / 4, hi = (part + 1) * 13 / 4;
+#pragma unroll 1
+        for (int i = lo; i < hi; i++) bp = min(bp, (dir_sad8(S, nd, c_cand15[2 + i], scr, lane) << 4) | (unsigned)i);
+        int last = 0;
+        if (lane == 0) {
+            S.c->dir_part[part] = bp;
+            __threadfence_block();
+            last = atomicAdd(&S.c->dir_cnt, 1) == nparts - 1;
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) return;
         __threadfence_block();
-        last = atomicAdd(&S.c->dir_cnt, 1) == nparts - 1;
+        for (int q = 0; q < nparts; q++) bp = min(bp, *(volatile unsigned *)&S.c->dir_part[q]);
+        if (lane == 0) S.c->dir_cnt = 0;
     }
-    last = __shfl_sync(0xffffffffu, last, 0);
-    if (!last) return;
-    __threadfence_block();
-    for (int q = 0; q < nparts; q++) bp = min(bp, *(volatile unsigned *)&S.c->dir_part[q]);
-    if (lane == 0) S.c->dir_cnt = 0;
     int cur = c_cand15[2 + (bp & 15u)];
     unsigned cur_cost = bp >> 4;
 #pragma unroll 1
     for (int step = 2; step >= 1; step >>= 1) {
         const bool v0 = !(cur < 2 + step), v1 = !(cur + step > 66);
         unsigned c0 = 0xffffffffu, c1 = 0xffffffffu;
-#pragma unroll 1
-        for (int cand = 0; cand < (luma_only ? 1 : 2); cand++) {
-            const int side = luma_only ? half : cand;  // 0: cur - step, 1: cur + step
-            const int m = side ? (v1 ? cur + step : 66) : (v0 ? cur - step : 2);
-            const unsigned s = dir_sad(S, nd, m, lane);
-            const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 16);
-            if (luma_only) { if (v0) c0 = s0; if (v1) c1 = s1; }
-            else if (cand == 0) { if (v0) c0 = s0; }
-            else if (v1) c1 = s0;
+        if (luma_only) {  // group 0: cur - step, group 1: cur + step
+            const int g = lane >> 2;
+            const unsigned s = dir_sad4(S, nd, g == 0 ? (v0 ? cur - step : -1) : (g == 1 ? (v1 ? cur + step : -1) : -1), scr, lane);
+            const unsigned s0 = __shfl_sync(0xffffffffu, s, 0), s1 = __shfl_sync(0xffffffffu, s, 4);
+            if (v0) c0 = s0;
+            if (v1) c1 = s1;
+        } else {
+            if (v0) c0 = dir_sad8(S, nd, cur - step, scr, lane);
+            if (v1) c1 = dir_sad8(S, nd, cur + step, scr, lane);
         }
         const unsigned mn = min(min(cur_cost, c0), c1);
         if (cur_cost == mn) {
@@ -1184,35 +1197,53 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
     return ws;
 }
 
-// prediction of one (mode, component) block: the only place pred_sample is instantiated in the search kernel.
-// Writes the samples to pred_out (may be null) and returns the SAD against the source block.
+// prediction of one (mode, component) block of size >= 4 by one warp.  Writes the samples to pred_out (may be null; raster,
+// 4-byte aligned) and returns the SAD against the source block.  Angular modes: four samples per lane and iteration (ang4.cuh);
+// planar / DC / CCLM: one sample per lane (pred_sample).
 __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *refx, uint8_t *pred_out, int lane) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(refx);
     if (pred_out) WB_SHARED_PTR(pred_out);
-    PredCtx pc_mem;  // cclm_params takes its address
-    pred_setup(S, g, nd, c, mode, refx, lane, pc_mem);
-    const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
-    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = pc.l2;
+    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n);
     unsigned sad = 0;
+    if (mode >= 2 && mode <= 66) {  // most predictions: the 13 coarse + 4 refinement SADs, 3 of the 5 full evaluations
+        a4::Mode m = a4_setup(S, c, n, l2, mode);
+        if (m.ang < 0) {  // project the side line below index 0 into the warp's scratch line ([-n-3, n+6] around index 0)
+            uint8_t *pr = reinterpret_cast<uint8_t *>(refx) + 36;
+            for (int i = lane; i < 2 * n + 2; i += 32) a4::project_elem(pr, m.main, m.side, n, m.inv, i);
+            __syncwarp();
+            m.main = pr;
+        }
+        const int qsh = l2 - 2, nquads = n << qsh;
+        const bool vert = mode >= 34;
+#pragma unroll 1
+        for (int q = lane; q < nquads; q += 32) {
+            const int t = q >> qsh, u0 = (q & ((1 << qsh) - 1)) << 2;
+            const unsigned p4 = a4::quad(m, S.tb->taps, t, u0);
+            sad = a4::sad4(p4, org_quad(S, c, mode, bx, by, t, u0), sad);
+            if (pred_out) {
+                if (vert) *reinterpret_cast<unsigned *>(pred_out + (t << l2) + u0) = p4;
+                else {
+                    uint8_t *d = pred_out + (u0 << l2) + t;
+                    d[0] = (uint8_t)p4; d[n] = (uint8_t)(p4 >> 8); d[2 * n] = (uint8_t)(p4 >> 16); d[3 * n] = (uint8_t)(p4 >> 24);
+                }
+            }
+        }
+        sad = warp_sumu(sad);
+        __syncwarp();
+        return sad;
+    }
+    PredCtx pc_mem;  // cclm_params takes its address
+    pred_setup(S, g, nd, c, mode, lane, pc_mem);
+    const PredCtx pc = pc_mem;  // private copy whose address never escapes: the per-sample loop keeps it in registers
     const uint8_t *org = cs ? S.c->orgC[c - 1] + by * 16 + bx : S.c->orgY + by * 32 + bx;  // source block, row stride 16 / 32
     const int osh = cs ? 4 : 5;
-    if (pc.kind == 2) {  // angular: most predictions (the 13 coarse + 4 refinement SADs, 3 of the 5 full evaluations)
 #pragma unroll 1
-        for (int i = lane; i < n * n; i += 32) {
-            int y = i >> l2, x = i & (n - 1);
-            int p = pred_sample<2>(S, pc, x, y);
-            if (pred_out) pred_out[i] = (uint8_t)p;
-            sad += abs(p - (int)org[(y << osh) + x]);
-        }
-    } else {
-#pragma unroll 1
-        for (int i = lane; i < n * n; i += 32) {
-            int y = i >> l2, x = i & (n - 1);
-            int p = pred_sample(S, pc, x, y);
-            if (pred_out) pred_out[i] = (uint8_t)p;
-            sad += abs(p - (int)org[(y << osh) + x]);
-        }
+    for (int i = lane; i < n * n; i += 32) {
+        int y = i >> l2, x = i & (n - 1);
+        int p = pred_sample(S, pc, x, y);
+        if (pred_out) pred_out[i] = (uint8_t)p;
+        sad += abs(p - (int)org[(y << osh) + x]);
     }
     return warp_sumu(sad);
 }

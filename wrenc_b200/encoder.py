@@ -25,6 +25,7 @@ EXPORTS = [
     "wrenc_b200_block_inv_dct", "wrenc_b200_block_quantize", "wrenc_b200_block_dequantize", "wrenc_b200_version",
     "wrenc_b200_measure_int32_peak", "wrenc_b200_derive_consts", "wrenc_b200_write_nal", "wrenc_b200_write_parameter_sets",
     "wrenc_b200_write_picture", "wrenc_b200_header_rbsp", "wrenc_b200_prepare", "wrenc_b200_code_resident_retry",
+    "wrenc_b200_alloc_pinned", "wrenc_b200_free_pinned",
 ]
 
 
