@@ -14,4 +14,4 @@ def test_ang4_matches_oracle_prediction(tmp_path):
                            os.path.join(ROOT, "oracle", "wrenc_oracle.cpp"), "-I", ROOT])
     out = subprocess.run([str(exe), "3"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "0 mismatches" in out.stdout and "52000 blocks" in out.stdout
+    assert "0 mismatches" in out.stdout and "78000 blocks" in out.stdout
