@@ -112,7 +112,8 @@ def test_streaming_submit_receive_many_batches():
         enc = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=B)
         got, nsub = [], 0
         while len(got) < len(frames):
-            while nsub < len(frames) and nsub - len(got) < min(lead, 2 * B):
+            # a batch slot is free again once ALL its pictures were received: batches got // B and got // B + 1 may be outstanding
+            while nsub < len(frames) and nsub - len(got) < lead and nsub < (len(got) // B + 2) * B:
                 enc.submit(100 + nsub, *frames[nsub])
                 nsub += 1
             got.append(enc.receive())
