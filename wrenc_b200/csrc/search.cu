@@ -159,22 +159,15 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     // ---- phase 1: planar / DC full evaluations, 13 coarse angular SADs
     {
         {
-            // 16x16 CU: the four 8x8 chroma TBs (planar / DC x Cb / Cr) of one CTU are one task, quantised together (full_multi8)
-            const int nfull = is_root ? 2 * ncomp : 3, ntask = nfull + 13 * ncomp;
-            nst = is_root ? 2 * KC : KC;
+            const int nfull = 2 * ncomp, ntask = nfull + 13 * ncomp;
+            nst = is_root ? 2 * KC : 0;
             WB_FOR_TASKS(ntask) {
                 const int k = tt % KC, t = tt / KC;
                 Ctx V{&S.tb, &S.c[k]};
                 const Node nd = unpack_node(V.c->node);
-                if (!is_root && t == 0) {
-                    unsigned ssd; int rate;
-                    full_multi8(V, tab, V.c->g, nd, 4, tb_desc(1, 0, sb + 0), tb_desc(2, 0, sb + 0), tb_desc(1, 1, sb + 1), tb_desc(2, 1, sb + 1), S.bigA[warp], S.bigB[warp],
-                                S.bigW[warp], S.bigP[warp], ws.refx, lane, ssd, rate);
-                    if (lane < 4) { V.c->pd_ssd[lane >> 1][1 + (lane & 1)] = ssd; V.c->pd_rate[lane >> 1][1 + (lane & 1)] = rate; }
-                } else if (t < nfull) {
+                if (t < nfull) {
                     int mode, c;
-                    if (!is_root) { mode = t - 1; c = 0; }
-                    else if (t < 2) { mode = t; c = 0; }
+                    if (t < 2) { mode = t; c = 0; }
                     else { mode = (t - 2) >> 1; c = 1 + ((t - 2) & 1); }
                     unsigned ssd; int rate;
                     full_task(V, tab, V.c->g, nd, c, mode, ws, lane, ssd, rate, sb + mode);
@@ -183,7 +176,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
                     int u = t - nfull;
                     int c = u / 13, mi = u - c * 13;
                     unsigned sad = sad_task(V, V.c->g, nd, c, c_cand15[2 + mi], ws, lane);
-                    if (lane == 0) V.c->r_sad[6 + u] = sad;
+                    if (lane == 0) V.c->r_sad[t] = sad;
                 }
             }
         }
@@ -193,7 +186,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         nst = 0;
         if (tid < KC && S.c[tid].active) {
             CtuCtx &C = S.c[tid];
-            constexpr int nfull = 6;  // r_sad[6 + 13 c + i]: coarse mode i of component c
+            const int nfull = 2 * ncomp;
             int best = 0;
             float bc = 0.f;
             for (int i = 0; i < 13; i++) {
@@ -241,38 +234,20 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
         }
     }
     // ---- phase 4: full evaluation of dir, dir-1, dir+1 (step_search aux=false)
-    // 16x16 CU: the (up to) six 8x8 chroma TBs of one CTU are two tasks of (up to) three TBs each (full_multi8)
-    nst = is_root ? 3 * KC : 2 * KC;
-    WB_FOR_TASKS(is_root ? 9 : 5) {
+    nst = is_root ? 3 * KC : 0;
+    WB_FOR_TASKS(9) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
-        const int dir = V.c->dir;
-        if (!is_root && t < 2) {
-            // the valid (candidate, component) pairs in order (dir always, dir-1 if v0, dir+1 if v1; Cb then Cr): task 0 takes the
-            // first three, task 1 the rest
-            const bool v0 = V.c->v0, v1 = V.c->v1;
-            const int nl = 2 * (1 + (int)v0 + (int)v1), first = t * 3, ntb = max(0, min(3, nl - first));
-            if (ntb > 0) {
-                auto cand_of = [&](int i) { const int o = (first + i) >> 1; return o == 0 ? 0 : ((o == 1 && v0) ? 1 : 2); };
-                auto desc_of = [&](int i) { const int cand = cand_of(i); return tb_desc(1 + ((first + i) & 1), cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1), sb + 2 + cand); };
-                unsigned ssd; int rate;
-                full_multi8(V, tab, V.c->g, unpack_node(V.c->node), ntb, desc_of(0), desc_of(1), desc_of(2), 0, S.bigA[warp], S.bigB[warp], S.bigW[warp], S.bigP[warp], ws.refx,
-                            lane, ssd, rate);
-                if (lane < ntb) { const int r = 3 + 2 * cand_of(lane) + ((first + lane) & 1); V.c->r_ssd[r] = ssd; V.c->r_rate[r] = rate; }
-            }
-            continue;
-        }
-        const int tl = is_root ? t : t - 2;  // root: 0-2 luma, 3-8 chroma; 16x16 CU: luma candidates only
         int cand, c;
-        if (tl < 3) { cand = tl; c = 0; }
-        else { cand = (tl - 3) >> 1; c = 1 + ((tl - 3) & 1); }
+        if (t < 3) { cand = t; c = 0; }
+        else { cand = (t - 3) >> 1; c = 1 + ((t - 3) & 1); }
         bool valid = cand == 0 || (cand == 1 ? V.c->v0 : V.c->v1);
         if (valid) {
+            const int dir = V.c->dir;
             int mode = cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1);
             unsigned ssd; int rate;
             full_task(V, tab, V.c->g, unpack_node(V.c->node), c, mode, ws, lane, ssd, rate, sb + 2 + cand);
-            const int r = c == 0 ? cand : 3 + 2 * cand + (c - 1);
-            if (lane == 0) { V.c->r_ssd[r] = ssd; V.c->r_rate[r] = rate; }
+            if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
         }
     }
     __syncthreads();
@@ -351,26 +326,17 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     __syncthreads();
     WB_PROF(pk_ + 10);
     WB_NEXT_PHASE();
-    // ---- phase 7: CCLM full evaluation (no commit); 16x16 CU: Cb and Cr of one CTU are one task (full_multi8)
-    nst = is_root ? 0 : KC;
-    WB_FOR_TASKS(is_root ? 2 : 1) {
-        const int k = tt % KC, t = tt / KC;
-        Ctx V{&S.tb, &S.c[k]};
-        unsigned ssd; int rate;
-        if (is_root) {
+    // ---- phase 7: CCLM full evaluation (no commit)
+        WB_FOR_TASKS(2) {
+            const int k = tt % KC, t = tt / KC;
+            Ctx V{&S.tb, &S.c[k]};
+            unsigned ssd; int rate;
             full_task(V, tab, V.c->g, unpack_node(V.c->node), 1 + t, V.c->cclm_mode, ws, lane, ssd, rate, sb + 5);
             if (lane == 0) { V.c->r_ssd[8 + t] = ssd; V.c->r_rate[8 + t] = rate; }
-        } else {
-            const int cm = V.c->cclm_mode;
-            full_multi8(V, tab, V.c->g, unpack_node(V.c->node), 2, tb_desc(1, cm, sb + 5), tb_desc(2, cm, sb + 5), 0, 0, S.bigA[warp], S.bigB[warp], S.bigW[warp], S.bigP[warp],
-                        ws.refx, lane, ssd, rate);
-            if (lane < 2) { V.c->r_ssd[8 + lane] = ssd; V.c->r_rate[8 + lane] = rate; }
         }
-    }
     __syncthreads();
     WB_PROF(pk_ + 12);
     WB_NEXT_PHASE();
-    nst = 0;
     if (tid < KC && S.c[tid].active) {
         Ctx V{&S.tb, &S.c[tid]};
         CtuCtx &C = *V.c;
@@ -429,7 +395,7 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
     const bool cu4 = id.depth == 3;  // 4x4 luma CU (else the 8x8 SINGLE_TREE CU)
     const int ncomp = cu4 ? 1 : 3;
     const int nparts = cu4 ? 1 : 4;  // 4x4 luma CU: eight modes per pass, the whole direction search is one warp task
-    int nst = 0;  // number of leading tasks that need a warp with a large scratch (next_task)
+    constexpr int nst = 0;
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     // ---- A
     WB_FOR_TASKS(ncomp) {
@@ -444,21 +410,19 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
     WB_PROF(pk_ + 1);
     WB_NEXT_PHASE();
     // ---- B
-    // 8x8 CU: task 0 = the planar and DC luma TBs of one CTU, quantised together by a warp with a large scratch (full_multi8)
-    nst = cu4 ? 0 : KC;
-    WB_FOR_TASKS(cu4 ? nparts + 1 : nparts + 3) {
+    WB_FOR_TASKS(cu4 ? nparts + 1 : nparts + 4) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = unpack_node(V.c->node);
-        if (!cu4 && t == 0) {  // 8x8 luma planar, DC
+        if (!cu4 && t < 2) {  // 8x8 luma planar, DC
             unsigned ssd; int rate;
-            full_multi8(V, tab, V.c->g, nd, 2, tb_desc(0, 0, 0), tb_desc(0, 1, 1), 0, 0, S.bigA[warp], S.bigB[warp], S.bigW[warp], S.bigP[warp], ws.refx, lane, ssd, rate);
-            if (lane < 2) { V.c->pd_ssd[lane][0] = ssd; V.c->pd_rate[lane][0] = rate; }
-        } else if (t < (cu4 ? 0 : 1) + nparts) {
-            dir_search_part(V, nd, nparts - 1 - (t - (cu4 ? 0 : 1)), nparts, reinterpret_cast<uint8_t *>(ws.refx), lane);  // the last part is the longest: it goes first
+            full_task(V, tab, V.c->g, nd, 0, t, ws, lane, ssd, rate, t);
+            if (lane == 0) { V.c->pd_ssd[t][0] = ssd; V.c->pd_rate[t][0] = rate; }
+        } else if (t < (cu4 ? 0 : 2) + nparts) {
+            dir_search_part(V, nd, nparts - 1 - (t - (cu4 ? 0 : 2)), nparts, reinterpret_cast<uint8_t *>(ws.refx), lane);  // the last part is the longest: it goes first
         } else {  // 4x4 TBs: planar | DC of the luma CU, or Cb | Cr of one mode
             const int half = lane >> 4;
-            const int mode = cu4 ? half : t - (1 + nparts), c = cu4 ? 0 : 1 + half;
+            const int mode = cu4 ? half : t - (2 + nparts), c = cu4 ? 0 : 1 + half;
             unsigned ssd; int rate;
             full_pair4(V, tab, V.c->g, nd, c, mode, false, mode, ws, lane, ssd, rate);
             if ((lane & 15) == 0) { V.c->pd_ssd[mode][c] = ssd; V.c->pd_rate[mode][c] = rate; }
@@ -468,22 +432,21 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
     WB_PROF(pk_ + 2);
     WB_NEXT_PHASE();
     // ---- C
-    // 8x8 CU: task 0 = the luma TBs of dir, dir-1, dir+1 of one CTU (full_multi8), tasks 1-3 the chroma pairs
-    WB_FOR_TASKS(cu4 ? 2 : 4) {
+    WB_FOR_TASKS(cu4 ? 2 : 6) {
         const int k = tt % KC, t = tt / KC;
         Ctx V{&S.tb, &S.c[k]};
         const Node nd = unpack_node(V.c->node);
         const int dir = V.c->dir;
-        if (!cu4 && t == 0) {
-            const bool v0 = V.c->v0, v1 = V.c->v1;
-            const int d1 = v0 ? tb_desc(0, dir - 1, 3) : tb_desc(0, dir + 1, 4), d2 = tb_desc(0, dir + 1, 4);
-            unsigned ssd; int rate;
-            full_multi8(V, tab, V.c->g, nd, 1 + (int)v0 + (int)v1, tb_desc(0, dir, 2), d1, d2, 0, S.bigA[warp], S.bigB[warp], S.bigW[warp], S.bigP[warp], ws.refx, lane, ssd, rate);
-            const int cand = lane == 0 ? 0 : ((lane == 1 && v0) ? 1 : 2);  // TB `lane` is candidate cand
-            if (lane < 1 + (int)v0 + (int)v1) { V.c->r_ssd[cand] = ssd; V.c->r_rate[cand] = rate; }
+        if (!cu4 && t < 3) {
+            const bool valid = t == 0 || (t == 1 ? V.c->v0 : V.c->v1);
+            if (valid) {
+                unsigned ssd; int rate;
+                full_task(V, tab, V.c->g, nd, 0, t == 0 ? dir : (t == 1 ? dir - 1 : dir + 1), ws, lane, ssd, rate, 2 + t);
+                if (lane == 0) { V.c->r_ssd[t] = ssd; V.c->r_rate[t] = rate; }
+            }
         } else {
             const int half = lane >> 4;
-            const int cand = cu4 ? 2 * t + half : t - 1, c = cu4 ? 0 : 1 + half;
+            const int cand = cu4 ? 2 * t + half : t - 3, c = cu4 ? 0 : 1 + half;
             const bool valid = cand == 0 || (cand == 1 ? V.c->v0 : (cand == 2 && V.c->v1));
             if (valid) {
                 unsigned ssd; int rate;
@@ -496,7 +459,6 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
     __syncthreads();
     WB_PROF(pk_ + 6);
     WB_NEXT_PHASE();
-    nst = 0;
     // ---- D
     WB_FOR_TASKS(1) {
         const int k = tt % KC;
@@ -1193,21 +1155,6 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
     }
     if (warp != 0) return;
     const int l2 = P.l2, n = 1 << l2, nn = n * n, to = tab_off(l2);
-    if (P.op == 3 && l2 == 3) {  // 8x8 TBs: the search kernel quantises them up to four at a time (trellis8_multi)
-        for (int blk0 = blockIdx.x * 4; blk0 < P.count; blk0 += gridDim.x * 4) {
-            const int nb = min(4, P.count - blk0);
-            for (int t = 0; t < nb; t++)
-                for (int i = lane; i < 64; i += 32) S.bigW[0][t * TB8_STRIDE + i] = (uint16_t)P.in[(size_t)(blk0 + t) * 64 + i];
-            __syncwarp();
-            int rate; unsigned any;
-            trellis8_multi(V, P.tab, nb, S.bigW[0], S.bigA[0], S.bigB[0], lane, rate, any);
-            for (int t = 0; t < nb; t++)
-                for (int i = lane; i < 64; i += 32) P.out16[(size_t)(blk0 + t) * 64 + i] = (int16_t)S.bigW[0][t * TB8_STRIDE + 64 + i];
-            if (lane < nb) P.outi[blk0 + lane] = rate;
-            __syncwarp();
-        }
-        return;
-    }
     for (int blk = blockIdx.x; blk < P.count; blk += gridDim.x) {
         const int16_t *in = P.in + (size_t)blk * nn;
         int16_t *out = P.out16 + (size_t)blk * nn;

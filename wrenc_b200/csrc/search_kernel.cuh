@@ -170,9 +170,8 @@ struct Shared {
     int ticket[2];            // dynamic task tickets of the current / previous phase
     int ticket_big[2];        //   and of the tasks that need the large scratch (32x32 luma pipelines of the root)
     // per-warp scratch
-    alignas(16) int16_t bigA[NBIG][1024];
-    alignas(16) int16_t bigB[NBIG][1024];
-    alignas(16) uint16_t bigW[NBIG][1024];
+    int16_t bigA[NBIG][1024], bigB[NBIG][1024];
+    uint16_t bigW[NBIG][1024];
     alignas(16) uint8_t bigP[NBIG][1024];
     int16_t smA[NW - NBIG + 1][256], smB[NW - NBIG + 1][256];
     uint16_t smW[NW - NBIG + 1][256];
@@ -937,6 +936,12 @@ __device__ __forceinline__ unsigned pos_map_nib(unsigned pk, unsigned dec, bool 
 // iteration, (D) each lane replays its chunk from its true entry costs to record the decisions, (F) the walk from the last
 // position (quantizer.rs:686-721) is a prefix scan over per-chunk next-state maps followed by a per-lane walk.  Costs are
 // int32 relative to the running minimum; the decisions are identical to the reference's i64 comparisons.
+// Why int32 is enough: a step adds at most 128 * |tc - dequant(q)| + ldq[bits] with |tc - dequant| <= 2 quantiser steps + 1
+// < 2^15.2 (x is the clamped quotient, so the candidates bracket tc) and ldq <= 2^26 (HostConsts::init rejects larger tables;
+// the default tuning stays below 2^24.5 at QP 63); every state reaches every other within two steps, so after the per-chunk
+// renormalisation the four state costs are at most 2 steps apart (< 2^27.1), and a chunk of 16 steps adds < 2^30.1 even at the
+// theoretical bound (< 2^26 with the default tables): all sums stay below 2^31.  TR_INF = 2^28 marks the absent candidate a1 of
+// a zero coefficient: it only has to exceed cost differences (<= 3 steps), never absolute path costs.
 __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ tab, const int16_t *coef, int l2, uint16_t *Wd, int16_t *lev, int lane,
                         int &rate_out, bool &any_out) {
     WB_SHARED_CTX(S);
@@ -1185,209 +1190,6 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Dependent quantisation of up to FOUR 8x8 TBs by one warp (the most numerous TBs >= 8x8: 128 of the 165 per CTU).
-// Same arithmetic as trellis(), organised the other way round: instead of cutting one TB into chunks and paying for the
-// (min,+) matrices, the chunk-by-chunk pass and the replay, the backward Viterbi pass runs as ONE sequential chain per TB with
-// one trellis STATE per lane (lanes 4g .. 4g+3 = TB g), so that up to eight chains advance with every instruction, over local
-// costs that all 32 lanes tabulated beforehand (one 16-byte row per position: candidate a0 / a1 for delta 0 / 1).  A chain
-// step is two shuffles (the two predecessor states), one 8-byte table read and ~10 integer instructions.
-//   W:   per TB t a block of 256 halfwords: coefficients (raster, int16) at 0, levels (out, raster) at 64, x / non-zero words at 128
-//   lcA, lcB: the cost tables, 1 kB per TB (TB 0, 1 in lcA, TB 2, 3 in lcB)
-// Returns in lane t the rate of TB t (block_splitter.rs:415-460) and in bit t of any_out whether TB t has a non-zero level.
-// Cost bound (int32 is enough, as in trellis()): a step adds at most 128 * d + ldq <= 2^22.2 + 2^26 (HostConsts::init), the
-// states of one position are at most two steps apart, and the chain is renormalised at every sub-block start.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int TB8_STRIDE = 256;  // halfwords per TB in W
-__device__ __noinline__ void trellis8_multi(const Ctx S, const DevTables *__restrict__ tab, int ntb, uint16_t *W, int16_t *lcA, int16_t *lcB, int lane, int &rate_out,
-                                            unsigned &any_out) {
-    WB_SHARED_CTX(S);
-    WB_SHARED_PTR(W); WB_SHARED_PTR(lcA); WB_SHARED_PTR(lcB);
-    constexpr int sh = 7, off = 64;
-    const int ls = tab->ls, ldq1 = S.tb->ldq[1];
-    const uint16_t *scan = S.tb->scan + tab_off(3);
-    const int g = lane >> 2, s = lane & 3;
-    const int sc_lo = scan[lane], sc_hi = scan[lane + 32];  // this lane's two scan positions: lane and lane + 32
-    // ---- A: x = S / ls, k* (H2), local costs of every position -> table; per-chain bit masks (kept by the lanes of group t)
-    unsigned msw_lo = 0, msw_hi = 0, fix_lo = 0, fix_hi = 0, adj = 0, act = 0, x0 = 0;
-    int tc0 = 0, kst = -1;
-#pragma unroll 1
-    for (int t = 0; t < ntb; t++) {
-        const int16_t *coef = reinterpret_cast<const int16_t *>(W + t * TB8_STRIDE);
-        uint16_t *Wd = W + t * TB8_STRIDE + 128;
-        const int tcl = coef[sc_lo], tch = coef[sc_hi];
-        unsigned xl = 0, xh = 0;
-        if (tcl != 0) xl = min(div_ls(S, tcl > 0 ? ((unsigned)tcl << sh) - (unsigned)off : ((unsigned)(-tcl) << sh) + (unsigned)off, (unsigned)ls), 2047u);
-        if (tch != 0) xh = min(div_ls(S, tch > 0 ? ((unsigned)tch << sh) - (unsigned)off : ((unsigned)(-tch) << sh) + (unsigned)off, (unsigned)ls), 2047u);
-        if (!__any_sync(0xffffffffu, (tcl | tch) != 0)) {  // every level is 0, rate 0 (as in trellis())
-            reinterpret_cast<uint32_t *>(W + t * TB8_STRIDE + 64)[lane] = 0u;
-            continue;
-        }
-        act |= 1u << t;
-        const int kstar = warp_max(xh >= 2 ? lane + 32 : (xl >= 2 ? lane : -1));
-        const unsigned wl = xl | ((unsigned)(tcl != 0) << 11), wh = xh | ((unsigned)(tch != 0) << 11);
-        Wd[lane] = (uint16_t)wl;
-        Wd[lane + 32] = (uint16_t)wh;
-        const LC ll = local_costs(S, tab, tcl, wl, lane, kstar, ls, sh, off, ldq1), lh = local_costs(S, tab, tch, wh, lane + 32, kstar, ls, sh, off, ldq1);
-        int4 *lc = reinterpret_cast<int4 *>((t < 2 ? lcA : lcB) + (t & 1) * 512);
-        lc[lane] = make_int4(ll.L00, ll.L10, ll.L01, ll.L11);
-        lc[lane + 32] = make_int4(lh.L00, lh.L10, lh.L01, lh.L11);
-        // state 0 sees candidate a0 = 0 of a flagged position without its rate (LC::L0s0 = L00 - ldq[1])
-        const unsigned p1l = __ballot_sync(0xffffffffu, ll.pk & 1u), p2l = __ballot_sync(0xffffffffu, ll.pk & 2u);
-        const unsigned p1h = __ballot_sync(0xffffffffu, lh.pk & 1u), p2h = __ballot_sync(0xffffffffu, lh.pk & 2u);
-        const unsigned mzl = __ballot_sync(0xffffffffu, lane > kstar && (xl >> 1) == 0), mzh = __ballot_sync(0xffffffffu, lane + 32 > kstar && (xh >> 1) == 0);
-        const int t0 = __shfl_sync(0xffffffffu, tcl, 0);
-        const unsigned xx0 = __shfl_sync(0xffffffffu, xl, 0);
-        if (g == t) {
-            const unsigned inv = (s & 1) ? 0xffffffffu : 0u;
-            msw_lo = (s < 2 ? p1l : p2l) ^ inv; msw_hi = (s < 2 ? p1h : p2h) ^ inv;
-            fix_lo = s == 0 ? mzl : 0u; fix_hi = s == 0 ? mzh : 0u;
-            adj = s == 0 ? ((unsigned)(16 > kstar) | ((unsigned)(32 > kstar) << 1) | ((unsigned)(48 > kstar) << 2)) : 0u;  // quantizer.rs:512-514 at k = 16, 32, 48
-            kst = kstar; tc0 = t0; x0 = xx0;
-        }
-    }
-    __syncwarp();
-    // ---- B: the chains.  Lane (g, s): state s of TB g; idle groups run along on TB 0's table (their results are not used).
-    unsigned dlo = 0, dhi = 0;
-    {
-        const int gt = (g < ntb) ? g : 0;
-        const char *lp = reinterpret_cast<const char *>((gt < 2 ? lcA : lcB) + (gt & 1) * 512) + (s >> 1) * 8;
-        int C;
-        {   // DC leaf (quantizer.rs:367-409) for this lane's state
-            const bool itz = (s == 0) && (kst < 0);
-            if (tc0 == 0) {
-                C = itz ? -ldq1 : ldq1;
-            } else {
-                const int delta = s > 1;
-                const int A0 = (int)(x0 >> 1);
-                int q0 = (int)(int16_t)(2 * A0 - delta);  // H3: usize wrap gives -1 for a0 == 0, delta == 1
-                if (tc0 < 0) q0 = -q0;
-                const int d0 = abs(tc0 - ((q0 * ls + off) >> sh));
-                const int bits0 = (A0 != 0 || !itz) ? A0 + 1 : 0;
-                const int cost0 = 128 * d0 + WB_LDQ(bits0);
-                const int A1 = A0 + 1;
-                int q1 = 2 * A1 - delta;
-                if (tc0 < 0) q1 = -q1;
-                const int d1 = abs(tc0 - ((q1 * ls + off) >> sh));
-                const int cost1 = 128 * d1 + WB_LDQ(A1 + 1);
-                if (cost0 <= cost1) {
-                    C = cost0;
-                    if (itz && A0 == 0) C -= ldq1;
-                } else {
-                    C = cost1;
-                    dlo = 1u;
-                }
-            }
-        }
-        // states 0,1 continue from {0,2}, states 2,3 from {1,3}; which of the two feeds candidate a0 depends on the parity of a0
-        const int srcP = (lane & ~3) | (s >> 1), srcQ = srcP + 2;
-#pragma unroll 1
-        for (int h = 0; h < 2; h++) {
-            const unsigned msw = h ? msw_hi : msw_lo, fix = h ? fix_hi : fix_lo;
-            unsigned dec = 0;
-            const char *lph = lp + h * 512;
-#pragma unroll 1
-            for (int q4 = 0; q4 < 2; q4++) {  // one sub-block of 16 positions per iteration
-                const int jb = q4 * 16;
-                if (h | q4) {  // sub-block start: renormalise, then the step with the post-comparison adjustment
-                    int mn = min(C, __shfl_xor_sync(0xffffffffu, C, 1));
-                    mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
-                    C -= mn;
-                    const int2 L = *reinterpret_cast<const int2 *>(lph + jb * 16);
-                    const int P = __shfl_sync(0xffffffffu, C, srcP), Q = __shfl_sync(0xffffffffu, C, srcQ);
-                    const bool sw = (msw >> jb) & 1u;
-                    const int La = L.x - (((fix >> jb) & 1u) ? ldq1 : 0);
-                    const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
-                    const bool d = c1 < c0;  // ties keep a0 (quantizer.rs:505)
-                    C = d ? c1 : c0;
-                    if (((adj >> (2 * h + q4 - 1)) & 1u) && !d) C -= ldq1;
-                    dec |= (unsigned)d << jb;
-                }
-#pragma unroll 5
-                for (int jj = 1; jj < 16; jj++) {
-                    const int j = jb + jj;
-                    const int2 L = *reinterpret_cast<const int2 *>(lph + j * 16);
-                    const int P = __shfl_sync(0xffffffffu, C, srcP), Q = __shfl_sync(0xffffffffu, C, srcQ);
-                    const bool sw = (msw >> j) & 1u;
-                    const int La = L.x - (((fix >> j) & 1u) ? ldq1 : 0);
-                    const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
-                    const bool d = c1 < c0;
-                    C = d ? c1 : c0;
-                    dec |= (unsigned)d << j;
-                }
-            }
-            if (h) dhi = dec; else dlo |= dec;
-        }
-    }
-    // ---- F: walk from the last scan position with state 0 (quantizer.rs:686-721) + rate (block_splitter.rs:415-460), TB by TB,
-    //      this lane again owning positions lane and lane + 32
-    int my_rate = 0;
-    unsigned any = 0;
-    const int lv0 = S.tb->lv[0];
-#pragma unroll 1
-    for (int t = 0; t < ntb; t++) {
-        if (!((act >> t) & 1u)) continue;
-        const int16_t *coef = reinterpret_cast<const int16_t *>(W + t * TB8_STRIDE);
-        int16_t *lev = reinterpret_cast<int16_t *>(W + t * TB8_STRIDE + 64);
-        const uint16_t *Wd = W + t * TB8_STRIDE + 128;
-        unsigned mdl = 0, mdh = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            mdl |= ((__shfl_sync(0xffffffffu, dlo, 4 * t + q) >> lane) & 1u) << q;
-            mdh |= ((__shfl_sync(0xffffffffu, dhi, 4 * t + q) >> lane) & 1u) << q;
-        }
-        const unsigned wl = Wd[lane], wh = Wd[lane + 32];
-        const unsigned xl = wl & 2047u, xh = wh & 2047u;
-        const unsigned pkl = lane == 0 ? ((xl >> 1) & 1u) * 3u : (((xl >> 1) & 1u) | ((((xl + 1) >> 1) & 1u) << 1));
-        const unsigned pkh = ((xh >> 1) & 1u) | ((((xh + 1) >> 1) & 1u) << 1);
-        unsigned inc = pos_map(pkh, mdh, (wh & 2048u) != 0);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned u = __shfl_down_sync(0xffffffffu, inc, d);
-            if (lane + d < 32) inc = map_compose(u, inc);
-        }
-        unsigned exc = __shfl_down_sync(0xffffffffu, inc, 1);
-        const unsigned sth = lane == 31 ? 0u : (exc & 3u);            // state entering position lane + 32
-        const unsigned mid = __shfl_sync(0xffffffffu, inc, 0) & 3u;   // state entering position 31
-        inc = pos_map(pkl, mdl, (wl & 2048u) != 0);
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const unsigned u = __shfl_down_sync(0xffffffffu, inc, d);
-            if (lane + d < 32) inc = map_compose(u, inc);
-        }
-        exc = __shfl_down_sync(0xffffffffu, inc, 1);
-        const unsigned stl = lane == 31 ? mid : ((exc >> (8 * mid)) & 3u);
-        int qh = 0, ql = 0;
-        const int dh = sth > 1, dl = stl > 1;
-        if (wh & 2048u) {
-            const unsigned a = ((xh + dh) >> 1) + ((mdh >> sth) & 1u);
-            qh = a > 0 ? 2 * (int)a - dh : 0;
-            if (coef[sc_hi] < 0) qh = -qh;
-        }
-        if (wl & 2048u) {
-            const unsigned a = (lane == 0 ? (xl >> 1) : ((xl + dl) >> 1)) + ((mdl >> stl) & 1u);
-            if (lane == 0) ql = (int)(int16_t)(2 * (int)a - dl);
-            else ql = a > 0 ? 2 * (int)a - dl : 0;
-            if (coef[sc_lo] < 0) ql = -ql;
-        }
-        lev[sc_hi] = (int16_t)qh;
-        lev[sc_lo] = (int16_t)ql;
-        // a zero level costs lv[0] iff a non-zero level precedes it in the walk (= sits at a higher scan position)
-        const unsigned bh = __ballot_sync(0xffffffffu, qh != 0), bl = __ballot_sync(0xffffffffu, ql != 0);
-        int r = 0;
-        if (qh != 0) r += WB_LV((abs(qh) + dh) >> 1);
-        else if (lane < 31 && (bh >> (lane + 1)) != 0) r += lv0;
-        if (ql != 0) r += WB_LV((abs(ql) + dl) >> 1);
-        else if (bh != 0 || (lane < 31 && (bl >> (lane + 1)) != 0)) r += lv0;
-        r = warp_sum(r);
-        if (lane == t) my_rate = r;
-        if ((bh | bl) != 0) any |= 1u << t;
-    }
-    rate_out = my_rate;
-    any_out = any;
-    __syncwarp();
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // tasks
 // ---------------------------------------------------------------------------------------------------------------
 __device__ WarpScratch warp_scratch(Shared &S, int warp) {
@@ -1457,45 +1259,40 @@ __device__ __forceinline__ unsigned sad_task(const Ctx S, const CtuGeom g, const
     return predict_block(S, g, nd, c, mode, ws.refx, nullptr, lane);
 }
 
-// First half of a full evaluation of one (mode, component) TB >= 8x8 (block_splitter.rs:148-160): prediction -> pred, residual,
-// forward DCT.  Leaves the coefficients in A (B is the transform's intermediate) and returns whether the residual is non-zero
-// (an all-zero residual skips the transforms: exact; A then holds the all-zero residual = the all-zero coefficients).
-__device__ __noinline__ bool tb_prepare(const Ctx S, const CtuGeom g, const Node nd, int c, int mode, int16_t *A, int16_t *B, uint8_t *pred, int16_t *refx, int lane) {
+// full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.  The outcome (reconstruction, levels)
+// goes to candidate slot `slot` of the CTU's global scratch; the winner is committed from there (commit_slot).
+__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode,
+                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out, int slot) {
     WB_SHARED_CTX(S);
-    WB_SHARED_PTR(A); WB_SHARED_PTR(B); WB_SHARED_PTR(pred); WB_SHARED_PTR(refx);
+    WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
-    const bool anysad = predict_block(S, g, nd, c, mode, refx, pred, lane) != 0;
+    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
     __syncwarp();
+    int16_t *A = ws.A, *B = ws.B;
+    bool anyres = anysad;
     const uint8_t *org = cs ? S.c->orgC[c - 1] + by * 16 + bx : S.c->orgY + by * 32 + bx;  // source block, row stride 16 / 32
     const int osh = cs ? 4 : 5;
 #pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
-        A[i] = (int16_t)((int)org[(y << osh) + x] - (int)pred[i]);
+        A[i] = (int16_t)((int)org[(y << osh) + x] - (int)ws.pred[i]);
     }
-    const bool anyres = __any_sync(0xffffffffu, anysad);
+    anyres = __any_sync(0xffffffffu, anyres);
     __syncwarp();
+    const int to = tab_off(l2);
+    bool anylev = false;
+    int rate = 0;
     if (anyres) {
-        const int to = tab_off(l2);
         mm_rows_q<true>(S.tb->Qr + to / 4, A, B, n, l2, 1 << (l2 - 2), l2 - 1, lane);
         __syncwarp();
         mm_cols_q(S.tb->T + to, reinterpret_cast<const int32_t *>(B), A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
         __syncwarp();
+        trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
+    } else {
+        for (int i = lane; i < nn; i += 32) B[i] = 0;
+        __syncwarp();
     }
-    return anyres;
-}
-
-// Second half (block_splitter.rs:161-183): the levels in B go to candidate slot `slot` of the CTU's global scratch (planar, DC,
-// dir, dir-1, dir+1, CCLM; the winner is committed from there, commit_slot), then dequantisation, inverse DCT (A is scratch),
-// reconstruction into the slot and the SSD against the source.
-__device__ __noinline__ unsigned tb_finish(const Ctx S, const DevTables *__restrict__ tab, const Node nd, int c, int16_t *A, int16_t *B, const uint8_t *pred, int lane,
-                                           bool anylev, int slot) {
-    WB_SHARED_CTX(S);
-    WB_SHARED_PTR(A); WB_SHARED_PTR(B); WB_SHARED_PTR(pred);
-    const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
-    const uint8_t *org = cs ? S.c->orgC[c - 1] + by * 16 + bx : S.c->orgY + by * 32 + bx;
-    const int osh = cs ? 4 : 5;
-    const int to = tab_off(l2);
+    // candidate slot (planar, DC, dir, dir-1, dir+1, CCLM): the evaluation's outcome goes to the CTU's global scratch, block-local raster
     const int soff = c == 0 ? 0 : (c == 1 ? 1024 : 1280);
     uint8_t *gRec = nullptr;
     if (slot >= 0) {
@@ -1525,63 +1322,14 @@ __device__ __noinline__ unsigned tb_finish(const Ctx S, const DevTables *__restr
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int res = anylev ? (int)A[i] : 0;
-        int rec = clip8((int)(int16_t)((int)pred[i] + res));
+        int rec = clip8((int)(int16_t)((int)ws.pred[i] + res));
         int d = rec - (int)org[(y << osh) + x];
         ssd += (unsigned)(d * d);
         if (slot >= 0) gRec[i] = (uint8_t)rec;
     }
-    ssd = warp_sumu(ssd);
+    ssd_out = warp_sumu(ssd);
+    rate_out = rate;
     __syncwarp();
-    return ssd;
-}
-
-// full evaluation of one (mode, component): block_splitter.rs:148-183 + rate 415-460.  The outcome (reconstruction, levels)
-// goes to candidate slot `slot` of the CTU's global scratch; the winner is committed from there (commit_slot).
-__device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode,
-                          const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out, int slot) {
-    WB_SHARED_CTX(S);
-    WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
-    const int cs = c != 0, n = nd.w >> cs, l2 = ilog2i(n), nn = n * n;
-    bool anylev = false;
-    int rate = 0;
-    if (tb_prepare(S, g, nd, c, mode, ws.A, ws.B, ws.pred, ws.refx, lane)) {
-        trellis(S, tab, ws.A, l2, ws.Wd, ws.B, lane, rate, anylev);
-    } else {
-        for (int i = lane; i < nn; i += 32) ws.B[i] = 0;
-        __syncwarp();
-    }
-    ssd_out = tb_finish(S, tab, nd, c, ws.A, ws.B, ws.pred, lane, anylev, slot);
-    rate_out = rate;
-}
-
-// Full evaluation of up to four 8x8 TBs of ONE node by one warp that owns a large scratch (bigA / bigB: the cost tables of
-// trellis8_multi, bigW: coefficients / levels / x words, bigP: predictions): the TBs are predicted and transformed one after
-// the other, quantised together, and finished one after the other.  desc d_i = c | mode << 2 | slot << 10.  Lane t returns the SSD
-// and the rate of TB t.
-__device__ __forceinline__ int tb_desc(int c, int mode, int slot) { return c | (mode << 2) | (slot << 10); }
-__device__ __noinline__ void full_multi8(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int ntb, int d0, int d1, int d2, int d3,
-                                         int16_t *bigA, int16_t *bigB, uint16_t *bigW, uint8_t *bigP, int16_t *refx, int lane, unsigned &ssd_out, int &rate_out) {
-    WB_SHARED_CTX(S);
-    WB_SHARED_PTR(bigA); WB_SHARED_PTR(bigB); WB_SHARED_PTR(bigW); WB_SHARED_PTR(bigP); WB_SHARED_PTR(refx);
-#pragma unroll 1
-    for (int t = 0; t < ntb; t++) {
-        const int d = t == 0 ? d0 : (t == 1 ? d1 : (t == 2 ? d2 : d3));
-        int16_t *A = reinterpret_cast<int16_t *>(bigW + t * TB8_STRIDE);
-        tb_prepare(S, g, nd, d & 3, (d >> 2) & 255, A, A + 64, bigP + t * 64, refx, lane);  // an all-zero residual leaves all-zero coefficients
-    }
-    int rate;
-    unsigned any;
-    trellis8_multi(S, tab, ntb, bigW, bigA, bigB, lane, rate, any);
-    unsigned my_ssd = 0;
-#pragma unroll 1
-    for (int t = 0; t < ntb; t++) {
-        const int d = t == 0 ? d0 : (t == 1 ? d1 : (t == 2 ? d2 : d3));
-        int16_t *A = reinterpret_cast<int16_t *>(bigW + t * TB8_STRIDE);
-        const unsigned ssd = tb_finish(S, tab, nd, d & 3, A, A + 64, bigP + t * 64, lane, (any >> t) & 1u, d >> 10);
-        if (lane == t) my_ssd = ssd;
-    }
-    ssd_out = my_ssd;
-    rate_out = rate;
 }
 
 // Full evaluation of a 4x4 TB by HALF a warp (lanes 0-15 and 16-31 evaluate two independent TBs of the same node: two modes

@@ -92,7 +92,10 @@ struct HostConsts {
             lv64[i] = (long long)(std::pow((double)i + u.lv_offset, u.lv_pow) * 16384.0);
             dq64[i] = (long long)std::pow((double)(i * 16384), u.quant_lv_pow);
             long long l = lambda_q * dq64[i];
-            if (l < 0 || l > (1ll << 27) || lv64[i] < 0 || lv64[i] > (1ll << 30)) {
+            // 2^26: the dependent quantisation keeps its path costs in int32 relative to the running minimum (search_kernel.cuh, trellis):
+            // a step adds at most 128 * |tc - dequant| + ldq <= 2^22.2 + 2^26, the four states of a position are at most two steps
+            // apart, and TR_INF = 2^28 must exceed three such steps
+            if (l < 0 || l > (1ll << 26) || lv64[i] < 0 || lv64[i] > (1ll << 30)) {
                 err = "tuning constants out of the supported range";
                 return false;
             }
