@@ -882,7 +882,7 @@ __device__ void init_tables(Shared &S, const DevTables *tab, int tid) {
             y = x; x = 0;
         }
     }
-    for (int i = tid; i < 64; i += NTHREADS) { S.tb.ldq[i] = tab->ldq[i]; S.tb.lv[i] = tab->lv[i]; }
+    for (int i = tid; i < WB_TAB_N; i += NTHREADS) { S.tb.ldq[i] = tab->ldq[i]; S.tb.lv[i] = tab->lv[i]; }
     if (tid < 32) {
         unsigned pk = 0;
         for (int i = 0; i < 4; i++) pk |= ((unsigned)(uint8_t)c_fC[tid][i]) << (8 * i);

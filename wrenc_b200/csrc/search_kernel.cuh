@@ -88,8 +88,11 @@ struct Tables {
     int32_t Qr[TAB_TOTAL / 4]; // packed for the row passes: Qr[x4*n + i] = bytes T[i][4*x4 + 0..3]   (forward horizontal pass)
     int32_t Qc[TAB_TOTAL / 4]; //                            Qc[i4*n + x] = bytes T[4*i4 + 0..3][x]   (inverse horizontal pass)
     uint16_t scan[TAB_TOTAL];  // forward scan index k (sub-block diagonal, then 4x4 diagonal; ctu.rs:14-81) -> raster offset
-    int32_t ldq[64];
-    int32_t lv[64];
+#ifndef WB_TAB_N
+#define WB_TAB_N 1024  // entries of the two rate tables kept in shared memory (1024 = all: no global-memory fallback branch in the trellis; 64: +8 kB of L1, measured 1.6 % slower)
+#endif
+    int32_t ldq[WB_TAB_N];
+    int32_t lv[WB_TAB_N];
     int32_t fc[32];            // fC taps packed as 4 x int8
     int16_t invang[68];        // inverse angle per mode (sign of the angle kept; intra_predictor.rs:1330-1341)
     int8_t ang[68];            // intraPredAngle per mode
@@ -837,8 +840,13 @@ __device__ __noinline__ void mm_cols_q(const int8_t *M, const int32_t *P, int16_
 // ---------------------------------------------------------------------------------------------------------------
 // dependent quantisation (quantizer.rs:338-517 search_dq + 686-721 walk) and the rate walk (block_splitter.rs:415-460)
 // ---------------------------------------------------------------------------------------------------------------
-#define WB_LDQ(i) ((i) < 64 ? S.tb->ldq[(i)] : __ldg(&tab->ldq[min((i), 1023)]))
-#define WB_LV(i) ((i) < 64 ? S.tb->lv[(i)] : __ldg(&tab->lv[min((i), 1023)]))
+#if WB_TAB_N >= 1024
+#define WB_LDQ(i) (S.tb->ldq[min((i), 1023)])
+#define WB_LV(i) (S.tb->lv[min((i), 1023)])
+#else
+#define WB_LDQ(i) ((i) < WB_TAB_N ? S.tb->ldq[(i)] : __ldg(&tab->ldq[min((i), 1023)]))
+#define WB_LV(i) ((i) < WB_TAB_N ? S.tb->lv[(i)] : __ldg(&tab->lv[min((i), 1023)]))
+#endif
 
 // Next-state maps of the walk are kept as 4 bytes (byte s = next state of state s), so that composing two maps is one byte
 // permute: the selector of __byte_perm is the first map in nibble form.
