@@ -273,67 +273,53 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
     const int n = nd.w >> cs, xt = nd.x >> cs, yt = nd.y >> cs;
     const int nl = 2 * n + 1, na = 2 * n, tot = nl + na;
     int16_t *seq = S.c->seq[c];
-    unsigned masks[5];
     const int rounds = (tot + 31) >> 5;
-    // sequence order: left[nl-1] ... left[0], above[0] ... above[na-1]
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        masks[r] = 0;
-        if (r < rounds) {
-            int j = r * 32 + lane;
-            int v = -1;
-            if (j < tot) {
-                if (j < nl) {
-                    int y = (nl - 1 - j) - 1;
-                    int yr = (y == -1) ? -1 : (y & ~3);
-                    if (nb_avail(g, nd, (xt - 1) << cs, (yt + yr) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt - 1, yt + y);
-                } else {
-                    int x = j - nl;
-                    int xr = x & ~3;
-                    if (nb_avail(g, nd, (xt + xr) << cs, (yt - 1) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt + x, yt - 1);
-                }
-                seq[j] = (int16_t)v;
-            }
-            masks[r] = __ballot_sync(0xffffffffu, v >= 0);
-        }
-    }
-    __syncwarp();
+    // sequence order: left[nl-1] ... left[0], above[0] ... above[na-1].  Pass 1: the available samples (-1: not available) and the
+    // first available position.  (Rolled loops on purpose: this function runs at the start of every node, and what it costs is the
+    // instruction-cache lines it touches)
     int first = -1;
-#pragma unroll
-    for (int r = 4; r >= 0; r--)
-        if (r < rounds && masks[r]) first = r * 32 + __ffs(masks[r]) - 1;
-    int16_t *L = S.c->refL[c][0], *A = S.c->refA[c][0];
-    int vals[5];
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        vals[r] = 128;
-        if (r < rounds) {
-            int j = r * 32 + lane;
-            if (j < tot && first >= 0) {
-                unsigned mm = masks[r] & (0xffffffffu >> (31 - lane));
-                int src = -1;
-                if (mm) src = r * 32 + 31 - __clz(mm);
-                else {
-#pragma unroll
-                    for (int q = 4; q >= 0; q--)
-                        if (q < r && src < 0 && masks[q]) src = q * 32 + 31 - __clz(masks[q]);
-                    if (src < 0) src = first;
-                }
-                vals[r] = seq[src];
+#pragma unroll 1
+    for (int r = 0; r < rounds; r++) {
+        const int j = r * 32 + lane;
+        int v = -1;
+        if (j < tot) {
+            if (j < nl) {
+                const int y = (nl - 1 - j) - 1;
+                const int yr = (y == -1) ? -1 : (y & ~3);
+                if (nb_avail(g, nd, (xt - 1) << cs, (yt + yr) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt - 1, yt + y);
+            } else {
+                const int x = j - nl;
+                const int xr = x & ~3;
+                if (nb_avail(g, nd, (xt + xr) << cs, (yt - 1) << cs, nd.ar, nd.bl)) v = rec_at(S, c, xt + x, yt - 1);
             }
+            seq[j] = (int16_t)v;
         }
+        const unsigned m = __ballot_sync(0xffffffffu, v >= 0);
+        if (first < 0 && m) first = r * 32 + __ffs(m) - 1;
     }
     __syncwarp();
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        if (r < rounds) {
-            int j = r * 32 + lane;
-            if (j < tot) {
-                if (j < nl) { L[nl - 1 - j] = (int16_t)vals[r]; ln_put_left(S, ln_variant(c, 0), nl - 1 - j, n, vals[r]); }
-                else { A[j - nl] = (int16_t)vals[r]; ln_put_above(S, ln_variant(c, 0), j - nl, n, vals[r]); }
-                seq[j] = (int16_t)vals[r];
-            }
+    // Pass 2: substitution = the nearest available sample at or before the position, else the first available one, else 128
+    // (intra_predictor.rs:214-301).  A source position is always an available one, which this pass leaves unchanged.
+    int16_t *L = S.c->refL[c][0], *A = S.c->refA[c][0];
+    int prev = -1;  // last available position of the rounds before this one
+#pragma unroll 1
+    for (int r = 0; r < rounds; r++) {
+        const int j = r * 32 + lane;
+        const int own = j < tot ? (int)seq[j] : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, own >= 0);
+        int val = 128;
+        if (j < tot && first >= 0) {
+            const unsigned mm = m & (0xffffffffu >> (31 - lane));
+            const int src = mm ? r * 32 + 31 - __clz(mm) : (prev >= 0 ? prev : first);
+            val = seq[src];
         }
+        __syncwarp();
+        if (j < tot) {
+            if (j < nl) { L[nl - 1 - j] = (int16_t)val; ln_put_left(S, ln_variant(c, 0), nl - 1 - j, n, val); }
+            else { A[j - nl] = (int16_t)val; ln_put_above(S, ln_variant(c, 0), j - nl, n, val); }
+            seq[j] = (int16_t)val;
+        }
+        if (m) prev = r * 32 + 31 - __clz(m);
     }
     __syncwarp();
     if (c == 0 && n >= 8) {  // [1 2 1] filtered copy, used by modes 0,2,34,66 (intra_predictor.rs:304-352)
