@@ -82,6 +82,7 @@ __device__ __forceinline__ long long luma_hdr(const Ctx S, const DevTables *tab,
 
 __device__ __forceinline__ void fill_lm(const Ctx S, const Node nd, int mode, int lane) {
     int cells = nd.w >> 2;
+#pragma unroll RU
     for (int i = lane; i < cells * cells; i += 32) {
         int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         S.c->lm[((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx] = (uint8_t)mode;
@@ -89,6 +90,7 @@ __device__ __forceinline__ void fill_lm(const Ctx S, const Node nd, int mode, in
 }
 __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, int lane) {
     int cells = nd.w >> 3;
+#pragma unroll RU
     for (int i = lane; i < cells * cells; i += 32) {
         int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         S.c->cm[((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx] = (uint8_t)mode;
@@ -99,7 +101,15 @@ __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, in
 // ticket per phase (S.ticket[phase parity], reset two phases later); a phase with at most one task per warp is assigned
 // statically.  32x32 luma pipelines need the large scratch buffers that only the first NBIG warps own: those `nbig` tasks lead
 // the list and have their own ticket, which the NBIG warps drain before they join the others on the general ticket.
-__device__ __forceinline__ int next_task(Shared &S, int &slot, int nbig, int ntot, int prev, int warp, int lane) {
+#ifndef WB_NT_NOINLINE
+#define WB_NT_NOINLINE 0
+#endif
+#if WB_NT_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+int next_task(Shared &S, int &slot, int nbig, int ntot, int prev, int warp, int lane) {
     if (nbig == 0 && ntot <= NW) return prev < 0 ? warp : ntot;  // at most one task per warp: no ticket needed
     if (nbig > 0 && warp < NBIG && prev < nbig) {
         int t = 0;
@@ -696,19 +706,23 @@ __device__ __noinline__ void save_node(const Ctx S, const Node nd, int d, int ti
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     uint8_t *svRecY = S.c->gsave;
     int16_t *svLvY = reinterpret_cast<int16_t *>(S.c->gsave + SAVE_SAMPLES);
+#pragma unroll RU
     for (int i = tid; i < w * w; i += nthr) {
         int y = i >> ilog2i(w), x = i & (w - 1);
         svRecY[oy + i] = RY(S, nd.x + x, nd.y + y);
         svLvY[oy + i] = S.c->lvY[(nd.y + y) * 32 + nd.x + x];
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
+#pragma unroll RU
     for (int i = tid; i < 2 * cw * cw; i += nthr) {
         int c = i >= cw * cw, j = i & (cw * cw - 1);
         int y = j >> ilog2i(cw), x = j & (cw - 1);
         svRecY[SAVE_Y + c * SAVE_C + oc + j] = RC(S, 1 + c, bx + x, by + y);
         svLvY[SAVE_Y + c * SAVE_C + oc + j] = S.c->lvC[c][(by + y) * 16 + bx + x];
     }
+#pragma unroll RU
     for (int i = tid; i < 64; i += nthr) S.c->svLm[d][i] = S.c->lm[i];
+#pragma unroll RU
     for (int i = tid; i < 16; i += nthr) S.c->svCm[d][i] = S.c->cm[i];
 }
 __device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int tid, int nthr) {
@@ -716,12 +730,14 @@ __device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int
     const int w = nd.w, oy = sv_off_y(d), oc = sv_off_c(d);
     const uint8_t *svRecY = S.c->gsave;
     const int16_t *svLvY = reinterpret_cast<const int16_t *>(S.c->gsave + SAVE_SAMPLES);
+#pragma unroll RU
     for (int i = tid; i < w * w; i += nthr) {
         int y = i >> ilog2i(w), x = i & (w - 1);
         RY(S, nd.x + x, nd.y + y) = __ldcg(svRecY + oy + i);
         S.c->lvY[(nd.y + y) * 32 + nd.x + x] = __ldcg(svLvY + oy + i);
     }
     const int cw = w >> 1, bx = nd.x >> 1, by = nd.y >> 1;
+#pragma unroll RU
     for (int i = tid; i < 2 * cw * cw; i += nthr) {
         int c = i >= cw * cw, j = i & (cw * cw - 1);
         int y = j >> ilog2i(cw), x = j & (cw - 1);
@@ -729,12 +745,14 @@ __device__ __noinline__ void restore_node(const Ctx S, const Node nd, int d, int
         S.c->lvC[c][(by + y) * 16 + bx + x] = __ldcg(svLvY + SAVE_Y + c * SAVE_C + oc + j);
     }
     const int cells = w >> 2;
+#pragma unroll RU
     for (int i = tid; i < cells * cells; i += nthr) {
         int yy = i >> ilog2i(cells), xx = i & (cells - 1);
         int idx = ((nd.y >> 2) + yy) * 8 + (nd.x >> 2) + xx;
         S.c->lm[idx] = S.c->svLm[d][idx];
     }
     const int cc = w >> 3;
+#pragma unroll RU
     for (int i = tid; i < cc * cc; i += nthr) {
         int yy = i >> ilog2i(cc), xx = i & (cc - 1);
         int idx = ((nd.y >> 3) + yy) * 4 + (nd.x >> 3) + xx;

@@ -39,7 +39,10 @@ namespace wb {
 #ifndef WB_U2
 #define WB_U2 1  // unroll of the dp2a inner loops (measured: 1 beats 2 by 0.8 %, code size)
 #endif
-constexpr int U5 = WB_U5, U2 = WB_U2;
+#ifndef WB_RU
+#define WB_RU 1  // unroll of the copy / element-wise loops that are not on a critical path: rolled (4, what the compiler does by itself, is 7 % more code and measured 2.2 % slower)
+#endif
+constexpr int U5 = WB_U5, U2 = WB_U2, RU = WB_RU;
 constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
 #ifndef WB_K
@@ -324,6 +327,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
     __syncwarp();
     if (c == 0 && n >= 8) {  // [1 2 1] filtered copy, used by modes 0,2,34,66 (intra_predictor.rs:304-352)
         int16_t *LF = S.c->refL[0][1], *AF = S.c->refA[0][1];
+#pragma unroll RU
         for (int i = lane; i < nl; i += 32) {
             int v;
             if (i == 0) v = (L[1] + 2 * L[0] + A[0] + 2) >> 2;
@@ -333,6 +337,7 @@ __device__ __noinline__ void build_refs(const Ctx S, const CtuGeom g, const Node
             S.c->seqF[nl - 1 - i] = (int16_t)v;
             ln_put_left(S, 1, i, n, v);
         }
+#pragma unroll RU
         for (int i = lane; i < na; i += 32) {
             int v;
             if (i == 0) v = (L[0] + 2 * A[0] + A[1] + 2) >> 2;
@@ -410,6 +415,7 @@ __device__ __noinline__ void cclm_downsample(const Ctx S, const CtuGeom g, const
     Node tmp = nd;
     bool avail_l = nb_avail(g, tmp, nd.x - 1, nd.y, false, false);
     int tw = nd.w >> 1;
+#pragma unroll RU
     for (int i = lane; i < tw * tw; i += 32) {
         int y = i >> ilog2i(tw), x = i & (tw - 1);
         S.c->pds[i] = (uint8_t)cclm_ds6(S, nd.x, nd.y, avail_l, 2 * y, 2 * x);
@@ -529,6 +535,7 @@ __device__ __forceinline__ void pred_setup(const Ctx S, const CtuGeom g, const N
     }
     pc.kind = 1;
     int s = 0;
+#pragma unroll RU
     for (int i = lane; i < n; i += 32) s += pc.ab[i] + pc.lf[1 + i];
     s = warp_sum(s) + n;
     pc.dc = (s >> (pc.l2 + 1)) & 255;
@@ -856,7 +863,15 @@ struct LC {
 };
 constexpr int TR_INF = 1 << 28;
 
-__device__ __forceinline__ LC local_costs(const Ctx S, const DevTables *__restrict__ tab, int tc, unsigned w, int k, int kstar, int ls, int sh, int off, int ldq1) {
+#ifndef WB_LC_NOINLINE
+#define WB_LC_NOINLINE 0
+#endif
+#if WB_LC_NOINLINE
+__device__ __noinline__
+#else
+__device__ __forceinline__
+#endif
+LC local_costs(const Ctx S, const DevTables *__restrict__ tab, int tc, unsigned w, int k, int kstar, int ls, int sh, int off, int ldq1) {
     LC r;
     const bool flagged = k > kstar;
     if (w & 2048u) {
@@ -963,6 +978,7 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
     anytc = __any_sync(0xffffffffu, anytc);
     __syncwarp();
     if (!anytc) {  // every candidate level is 0 and every position is a trailing zero: levels 0, rate 0
+#pragma unroll RU
         for (int k = lane; k < nn; k += 32) lev[k] = 0;
         rate_out = 0;
         any_out = false;
@@ -1210,6 +1226,7 @@ __device__ __noinline__ unsigned predict_block(const Ctx S, const CtuGeom g, con
         a4::Mode m = a4_setup(S, c, n, l2, mode);
         if (m.ang < 0) {  // project the side line below index 0 into the warp's scratch line ([-n-3, n+6] around index 0)
             uint8_t *pr = reinterpret_cast<uint8_t *>(refx) + 36;
+#pragma unroll RU
             for (int i = lane; i < 2 * n + 2; i += 32) a4::project_elem(pr, m.main, m.side, n, m.inv, i);
             __syncwarp();
             m.main = pr;
@@ -1283,6 +1300,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         __syncwarp();
         trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
     } else {
+#pragma unroll RU
         for (int i = lane; i < nn; i += 32) B[i] = 0;
         __syncwarp();
     }
@@ -1292,11 +1310,13 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     if (slot >= 0) {
         gRec = S.c->groot + slot * ROOT_SLOT_SAMPLES + soff;
         int16_t *gLv = reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + slot * ROOT_SLOT_SAMPLES + soff;
+#pragma unroll RU
         for (int i = lane; i < nn / 2; i += 32) reinterpret_cast<uint32_t *>(gLv)[i] = reinterpret_cast<const uint32_t *>(B)[i];  // two levels per store
     }
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
         // dequantise (quantizer.rs:1074-1075) into the pair-packed layout of the column pass
+#pragma unroll RU
         for (int o = lane; o < nn / 2; o += 32) {
             const int ip = o >> l2, x = o & (n - 1);
             const int d0 = min(32767, max(-32768, ((int)B[(2 * ip) * n + x] * ls + off) >> sh));
@@ -1550,6 +1570,7 @@ __device__ __noinline__ void commit_slot(const Ctx S, const Node nd, int c, int 
     const int16_t *gLv = reinterpret_cast<const int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + soff;
     int16_t *dst = c == 0 ? S.c->lvY : S.c->lvC[c - 1];
     const int stride = c == 0 ? 32 : 16;
+#pragma unroll RU
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         dst[(by + y) * stride + bx + x] = __ldcg(gLv + i);
