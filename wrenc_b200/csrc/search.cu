@@ -458,11 +458,16 @@ __device__ __noinline__ void small_eval(Shared &S, const SearchParams &P, const 
             const int half = lane >> 4;
             const int cand = cu4 ? 2 * t + half : t - 3, c = cu4 ? 0 : 1 + half;
             const bool valid = cand == 0 || (cand == 1 ? V.c->v0 : (cand == 2 && V.c->v1));
-            if (valid) {
+            // both halves of the warp run full_pair4 in step: the 4x4 CU's second half may have no candidate (dir-1 invalid, or the
+            // empty partner of dir+1) and then runs along on the first half's mode without storing anything
+            const int cand0 = cu4 ? 2 * t : cand;
+            const bool valid0 = cand0 == 0 || (cand0 == 1 ? V.c->v0 : V.c->v1);
+            if (valid0) {
+                const int cm = valid ? cand : cand0;
                 unsigned ssd; int rate;
-                full_pair4(V, tab, V.c->g, nd, c, cand == 0 ? dir : (cand == 1 ? dir - 1 : dir + 1), false, 2 + cand, ws, lane, ssd, rate);
+                full_pair4(V, tab, V.c->g, nd, c, cm == 0 ? dir : (cm == 1 ? dir - 1 : dir + 1), false, 2 + cm, ws, lane, ssd, rate, valid);
                 const int ri = c == 0 ? cand : 3 + 2 * cand + (c - 1);
-                if ((lane & 15) == 0) { V.c->r_ssd[ri] = ssd; V.c->r_rate[ri] = rate; }
+                if (valid && (lane & 15) == 0) { V.c->r_ssd[ri] = ssd; V.c->r_rate[ri] = rate; }
             }
         }
     }

@@ -1350,18 +1350,22 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
 // of a 4x4 luma CU, or the Cb and Cr blocks of one chroma mode).  Same arithmetic as full_task, but the block lives in
 // registers (lane gl = raster sample 4y + x), the 4-point transforms exchange operands by shuffles, and the dependent
 // quantisation runs one trellis STATE per lane (lanes 0-3 of the half) over the 15 sequential steps, reading the local costs
-// that the position lanes tabulated in shared memory.  c, mode, commit and slot may differ between the halves; every
-// collective uses the half's mask, so a half whose TB is not evaluated simply does not call.
+// that the position lanes tabulated in shared memory.  c, mode, commit and slot may differ between the halves, but BOTH halves
+// always run in step (all 32 lanes call; the prediction kind - angular / planar-DC / CCLM - must be the same): a half whose TB
+// is not wanted passes on = false, evaluates the TB it is given and stores nothing.  That keeps every shuffle / ballot a
+// full-warp collective with a constant mask: with per-half masks each of the ~45 shuffles carried its own convergence code
+// (325 of the function's 1 586 instructions).
 constexpr unsigned long long INV_SCAN4 = 0xFDA6EB73C8419520ull;  // nibble r = scan position of raster offset r (inverse of the 4x4 diagonal scan)
 __device__ __forceinline__ int dot4_s8(int packed, int a0, int a1, int a2, int a3) {
     return (int)(int8_t)(packed & 255) * a0 + (int)(int8_t)((packed >> 8) & 255) * a1 + (int)(int8_t)((packed >> 16) & 255) * a2 + (packed >> 24) * a3;
 }
 __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict__ tab, const CtuGeom g, const Node nd, int c, int mode, bool commit, int slot,
-                                        const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out) {
+                                        const WarpScratch ws, int lane, unsigned &ssd_out, int &rate_out, bool on = true) {
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B);
     const int hb = lane & 16, gl = lane & 15, half = hb >> 4;
-    const unsigned hm = half ? 0xffff0000u : 0x0000ffffu;
+    constexpr unsigned hm = 0xffffffffu;  // the two halves run in step (see above): every collective is a full-warp one with a constant mask
+    if (!on) { commit = false; slot = -1; }
     const int cs = c != 0, bx = nd.x >> cs, by = nd.y >> cs;
     const int x = gl & 3, y = gl >> 2;
     int p;  // prediction sample, straight from the reference samples (no projection array, no per-task setup pass)
@@ -1409,7 +1413,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
     const bool anytc = ((__ballot_sync(hm, nz) >> hb) & 0xffffu) != 0;
     int q = 0, rate = 0;
     bool anylev = false;
-    if (anytc) {
+    if (__any_sync(hm, anytc)) {  // warp-uniform: a half without coefficients quantises zeros to zeros (rate 0)
         LC l;
         l.L00 = l.L01 = l.L0s0 = 0; l.L10 = l.L11 = TR_INF; l.pk = 0;
         if (k > 0) l = local_costs(S, tab, tc, w, k, kstar, ls, sh, off, ldq1);  // (k & 15) != 0: no sub-block-start adjustment inside a 4x4 TB
@@ -1425,7 +1429,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
         unsigned dec = 0;
         if (gl < 4) {
             const int s = gl;
-            const unsigned m4 = 0xFu << hb;
+            constexpr unsigned m4 = 0x000F000Fu;  // the state lanes of both halves
             // DC leaf (quantizer.rs:367-409) for this lane's state
             int C;
             {
@@ -1506,7 +1510,7 @@ __device__ __noinline__ void full_pair4(const Ctx S, const DevTables *__restrict
     }
     if (slot >= 0) reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES)[soff] = (int16_t)lev;
     int r = 0;
-    if (anylev) {  // dequantise (quantizer.rs:1074-1075), inverse DCT (transformer.rs:2380-2737 with n = 4)
+    if (__any_sync(hm, anylev)) {  // warp-uniform (all-zero levels give a zero residual); dequantise (quantizer.rs:1074-1075), inverse DCT (transformer.rs:2380-2737 with n = 4)
         const int dq = min(32767, max(-32768, (lev * ls + off) >> sh));
         a0 = __shfl_sync(hm, dq, hb + colq); a1 = __shfl_sync(hm, dq, hb + colq + 4); a2 = __shfl_sync(hm, dq, hb + colq + 8); a3 = __shfl_sync(hm, dq, hb + colq + 12);
         const int v = min(32767, max(-32768, (dot4_s8(Tcol_y, a0, a1, a2, a3) + 64) >> 7));   // V[y][x] = sum_i T[i][y] D[i][x]
