@@ -1202,8 +1202,12 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
             mm_rows_q<false>(S.tb.Qc + to / 4, ws.B, ws.A, n, l2, 2048, 12, lane);  // R[y][x] = sum_i T[i][x] V[y][i]
             __syncwarp();
             for (int i = lane; i < nn; i += 32) out[i] = ws.A[i];
-        } else if (P.op == 3) {
+        } else if (P.op == 3 || P.op == 5) {  // 3: the routine the search uses for this size; 5: trellis() for every size
             int rate; bool any;
+#if WB_CHAIN8
+            if (l2 == 3 && P.op == 3) trellis8_chain(V, P.tab, ws.A, reinterpret_cast<uint16_t *>(ws.A + 128), ws.B, reinterpret_cast<int4 *>(ws.B), lane, rate, any);
+            else
+#endif
             trellis(V, P.tab, ws.A, l2, ws.Wd, ws.B, lane, rate, any);
             for (int i = lane; i < nn; i += 32) out[i] = ws.B[i];
             if (lane == 0) P.outi[blk] = rate;

@@ -42,6 +42,9 @@ namespace wb {
 #ifndef WB_RU
 #define WB_RU 1  // unroll of the copy / element-wise loops that are not on a critical path: rolled (4, what the compiler does by itself, is 7 % more code and measured 2.2 % slower)
 #endif
+#ifndef WB_CHAIN8
+#define WB_CHAIN8 1  // 8x8 TBs quantised by trellis8_chain (one sequential state-per-lane chain) instead of trellis()
+#endif
 constexpr int U5 = WB_U5, U2 = WB_U2, RU = WB_RU;
 constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
@@ -176,17 +179,21 @@ struct Shared {
     int ticket[2];            // dynamic task tickets of the current / previous phase
     int ticket_big[2];        //   and of the tasks that need the large scratch (32x32 luma pipelines of the root)
     // per-warp scratch
-    int16_t bigA[NBIG][1024], bigB[NBIG][1024];
-    uint16_t bigW[NBIG][1024];
+    alignas(16) int16_t bigA[NBIG][1024];
+    alignas(16) int16_t bigB[NBIG][1024];
+    alignas(16) uint16_t bigW[NBIG][1024];
     alignas(16) uint8_t bigP[NBIG][1024];
-    int16_t smA[NW - NBIG + 1][256], smB[NW - NBIG + 1][256];
-    uint16_t smW[NW - NBIG + 1][256];
-    alignas(16) uint8_t smP[NW - NBIG + 1][256];
+    struct alignas(16) SmallScratch {  // B and W are adjacent on purpose: together they hold the 1 kB cost table of trellis8_chain
+        int16_t A[256];
+        int16_t B[256];
+        uint16_t W[256];
+        uint8_t P[256];
+    } sm[NW - NBIG + 1];
     alignas(16) int16_t refx[NW][100];  // per-warp scratch line: projected references of the negative-angle modes (as bytes)
 };
 
 static_assert(offsetof(CtuCtx, lvY) % 8 == 0 && offsetof(CtuCtx, lvC) % 8 == 0 && sizeof(CtuCtx) % 8 == 0, "commit_root_slot stores the levels as 64-bit words");
-static_assert(offsetof(Shared, bigA) % 8 == 0 && offsetof(Shared, bigB) % 8 == 0 && offsetof(Shared, smA) % 8 == 0 && offsetof(Shared, smB) % 8 == 0 &&
+static_assert(offsetof(Shared, bigA) % 16 == 0 && offsetof(Shared, bigB) % 16 == 0 && offsetof(Shared, sm) % 16 == 0 && sizeof(Shared::SmallScratch) % 16 == 0 &&
                   offsetof(Tables, Tt) % 4 == 0,
               "full_pair4 reads these arrays as 32-bit words");
 
@@ -1200,6 +1207,189 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Dependent quantisation of ONE 8x8 TB (128 of the 165 TBs >= 8x8 of a CTU).  Same arithmetic as trellis(), organised the
+// other way round: instead of cutting the TB into chunks and paying for the (min,+) matrices, the chunk-by-chunk pass and the
+// replay, the backward Viterbi pass runs as one sequential chain with one trellis STATE per lane (lanes 0-3) over local costs
+// that all 32 lanes tabulated beforehand (one 16-byte row per position: candidate a0 / a1 for delta 0 / 1).  A chain step
+// is two shuffles (the two predecessor states), one 8-byte table read and ~10 integer instructions; the whole routine is
+// about a third of trellis() in code and in executed instructions.
+//   coef: coefficients (raster); Wd: 64 x / non-zero words; lc: 1 kB cost table (may overlap lev: it is dead before the walk)
+//   lev (out): levels (raster).  Cost bound: see trellis(); the chain is renormalised at every sub-block start.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__restrict__ tab, const int16_t *coef, uint16_t *Wd, int16_t *lev, int4 *lc, int lane,
+                                            int &rate_out, bool &any_out) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(coef); WB_SHARED_PTR(Wd); WB_SHARED_PTR(lev); WB_SHARED_PTR(lc);
+    constexpr int sh = 7, off = 64;
+    const int ls = tab->ls, ldq1 = S.tb->ldq[1];
+    const uint16_t *scan = S.tb->scan + tab_off(3);
+    const int sc_lo = scan[lane], sc_hi = scan[lane + 32];  // this lane's two scan positions: lane and lane + 32
+    // ---- A: x = S / ls, k* (H2), local costs of every position -> table, parity / flag masks of the chain
+    const int tcl = coef[sc_lo], tch = coef[sc_hi];
+    unsigned xl = 0, xh = 0;
+    if (tcl != 0) xl = min(div_ls(S, tcl > 0 ? ((unsigned)tcl << sh) - (unsigned)off : ((unsigned)(-tcl) << sh) + (unsigned)off, (unsigned)ls), 2047u);
+    if (tch != 0) xh = min(div_ls(S, tch > 0 ? ((unsigned)tch << sh) - (unsigned)off : ((unsigned)(-tch) << sh) + (unsigned)off, (unsigned)ls), 2047u);
+    if (!__any_sync(0xffffffffu, (tcl | tch) != 0)) {  // every level is 0, rate 0 (as in trellis())
+        reinterpret_cast<uint32_t *>(lev)[lane] = 0u;
+        rate_out = 0;
+        any_out = false;
+        __syncwarp();
+        return;
+    }
+    const int kstar = warp_max(xh >= 2 ? lane + 32 : (xl >= 2 ? lane : -1));
+    const unsigned wl = xl | ((unsigned)(tcl != 0) << 11), wh = xh | ((unsigned)(tch != 0) << 11);
+    Wd[lane] = (uint16_t)wl;
+    Wd[lane + 32] = (uint16_t)wh;
+    unsigned p1l, p2l, p1h, p2h;
+    {
+        const LC ll = local_costs(S, tab, tcl, wl, lane, kstar, ls, sh, off, ldq1);
+        lc[lane] = make_int4(ll.L00, ll.L10, ll.L01, ll.L11);
+        p1l = __ballot_sync(0xffffffffu, ll.pk & 1u); p2l = __ballot_sync(0xffffffffu, ll.pk & 2u);
+    }
+    {
+        const LC lh = local_costs(S, tab, tch, wh, lane + 32, kstar, ls, sh, off, ldq1);
+        lc[lane + 32] = make_int4(lh.L00, lh.L10, lh.L01, lh.L11);
+        p1h = __ballot_sync(0xffffffffu, lh.pk & 1u); p2h = __ballot_sync(0xffffffffu, lh.pk & 2u);
+    }
+    // state 0 sees candidate a0 = 0 of a flagged position without its rate (LC::L0s0 = L00 - ldq[1])
+    const unsigned mzl = __ballot_sync(0xffffffffu, lane > kstar && (xl >> 1) == 0), mzh = __ballot_sync(0xffffffffu, lane + 32 > kstar && (xh >> 1) == 0);
+    const int tc0 = __shfl_sync(0xffffffffu, tcl, 0);
+    const unsigned x0 = __shfl_sync(0xffffffffu, xl, 0);
+    __syncwarp();
+    // ---- B: the chain, lane s = state s
+    unsigned dlo = 0, dhi = 0;
+    if (lane < 4) {
+        const int s = lane;
+        const unsigned inv = (s & 1) ? 0xffffffffu : 0u;
+        const unsigned msw_lo = (s < 2 ? p1l : p2l) ^ inv, msw_hi = (s < 2 ? p1h : p2h) ^ inv;
+        const unsigned fix_lo = s == 0 ? mzl : 0u, fix_hi = s == 0 ? mzh : 0u;
+        const unsigned adj = s == 0 ? ((unsigned)(16 > kstar) | ((unsigned)(32 > kstar) << 1) | ((unsigned)(48 > kstar) << 2)) : 0u;  // quantizer.rs:512-514 at k = 16, 32, 48
+        const char *lp = reinterpret_cast<const char *>(lc) + (s >> 1) * 8;
+        int C;
+        {   // DC leaf (quantizer.rs:367-409) for this lane's state
+            const bool itz = (s == 0) && (kstar < 0);
+            if (tc0 == 0) {
+                C = itz ? -ldq1 : ldq1;
+            } else {
+                const int delta = s > 1;
+                const int A0 = (int)(x0 >> 1);
+                int q0 = (int)(int16_t)(2 * A0 - delta);  // H3: usize wrap gives -1 for a0 == 0, delta == 1
+                if (tc0 < 0) q0 = -q0;
+                const int d0 = abs(tc0 - ((q0 * ls + off) >> sh));
+                const int bits0 = (A0 != 0 || !itz) ? A0 + 1 : 0;
+                const int cost0 = 128 * d0 + WB_LDQ(bits0);
+                const int A1 = A0 + 1;
+                int q1 = 2 * A1 - delta;
+                if (tc0 < 0) q1 = -q1;
+                const int d1 = abs(tc0 - ((q1 * ls + off) >> sh));
+                const int cost1 = 128 * d1 + WB_LDQ(A1 + 1);
+                if (cost0 <= cost1) {
+                    C = cost0;
+                    if (itz && A0 == 0) C -= ldq1;
+                } else {
+                    C = cost1;
+                    dlo = 1u;
+                }
+            }
+        }
+        // states 0,1 continue from {0,2}, states 2,3 from {1,3}; which of the two feeds candidate a0 depends on the parity of a0
+        const int srcP = s >> 1, srcQ = srcP + 2;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const unsigned msw = h ? msw_hi : msw_lo, fix = h ? fix_hi : fix_lo;
+            unsigned dec = 0;
+            const char *lph = lp + h * 512;
+#pragma unroll 1
+            for (int q4 = 0; q4 < 2; q4++) {  // one sub-block of 16 positions per iteration
+                const int jb = q4 * 16;
+                int j0 = jb + 1;
+                if (h | q4) {  // sub-block start: renormalise, then the step with the post-comparison adjustment
+                    int mn = min(C, __shfl_xor_sync(0xFu, C, 1));
+                    mn = min(mn, __shfl_xor_sync(0xFu, mn, 2));
+                    C -= mn;
+                    const int2 L = *reinterpret_cast<const int2 *>(lph + jb * 16);
+                    const int P = __shfl_sync(0xFu, C, srcP), Q = __shfl_sync(0xFu, C, srcQ);
+                    const bool sw = (msw >> jb) & 1u;
+                    const int La = L.x - (((fix >> jb) & 1u) ? ldq1 : 0);
+                    const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
+                    const bool d = c1 < c0;  // ties keep a0 (quantizer.rs:505)
+                    C = d ? c1 : c0;
+                    if (((adj >> (2 * h + q4 - 1)) & 1u) && !d) C -= ldq1;
+                    dec |= (unsigned)d << jb;
+                }
+#pragma unroll 5
+                for (int j = j0; j < jb + 16; j++) {
+                    const int2 L = *reinterpret_cast<const int2 *>(lph + j * 16);
+                    const int P = __shfl_sync(0xFu, C, srcP), Q = __shfl_sync(0xFu, C, srcQ);
+                    const bool sw = (msw >> j) & 1u;
+                    const int La = L.x - (((fix >> j) & 1u) ? ldq1 : 0);
+                    const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
+                    const bool d = c1 < c0;
+                    C = d ? c1 : c0;
+                    dec |= (unsigned)d << j;
+                }
+            }
+            if (h) dhi = dec; else dlo |= dec;
+        }
+    }
+    __syncwarp();
+    // ---- F: walk from the last scan position with state 0 (quantizer.rs:686-721) + rate (block_splitter.rs:415-460); this lane
+    //      again owns positions lane and lane + 32.  (The cost table is dead from here on: lev may overlap it.)
+    unsigned mdl = 0, mdh = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        mdl |= ((__shfl_sync(0xffffffffu, dlo, q) >> lane) & 1u) << q;
+        mdh |= ((__shfl_sync(0xffffffffu, dhi, q) >> lane) & 1u) << q;
+    }
+    const unsigned pkl = lane == 0 ? ((xl >> 1) & 1u) * 3u : (((xl >> 1) & 1u) | ((((xl + 1) >> 1) & 1u) << 1));
+    const unsigned pkh = ((xh >> 1) & 1u) | ((((xh + 1) >> 1) & 1u) << 1);
+    unsigned inc = pos_map(pkh, mdh, tch != 0);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned u = __shfl_down_sync(0xffffffffu, inc, d);
+        if (lane + d < 32) inc = map_compose(u, inc);
+    }
+    unsigned exc = __shfl_down_sync(0xffffffffu, inc, 1);
+    const unsigned sth = lane == 31 ? 0u : (exc & 3u);            // state entering position lane + 32
+    const unsigned mid = __shfl_sync(0xffffffffu, inc, 0) & 3u;   // state entering position 31
+    inc = pos_map(pkl, mdl, tcl != 0);
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned u = __shfl_down_sync(0xffffffffu, inc, d);
+        if (lane + d < 32) inc = map_compose(u, inc);
+    }
+    exc = __shfl_down_sync(0xffffffffu, inc, 1);
+    const unsigned stl = lane == 31 ? mid : ((exc >> (8 * mid)) & 3u);
+    int qh = 0, ql = 0;
+    const int dh = sth > 1, dl = stl > 1;
+    if (tch != 0) {
+        const unsigned a = ((xh + dh) >> 1) + ((mdh >> sth) & 1u);
+        qh = a > 0 ? 2 * (int)a - dh : 0;
+        if (tch < 0) qh = -qh;
+    }
+    if (tcl != 0) {
+        const unsigned a = (lane == 0 ? (xl >> 1) : ((xl + dl) >> 1)) + ((mdl >> stl) & 1u);
+        if (lane == 0) ql = (int)(int16_t)(2 * (int)a - dl);
+        else ql = a > 0 ? 2 * (int)a - dl : 0;
+        if (tcl < 0) ql = -ql;
+    }
+    __syncwarp();
+    lev[sc_hi] = (int16_t)qh;
+    lev[sc_lo] = (int16_t)ql;
+    // a zero level costs lv[0] iff a non-zero level precedes it in the walk (= sits at a higher scan position)
+    const unsigned bh = __ballot_sync(0xffffffffu, qh != 0), bl = __ballot_sync(0xffffffffu, ql != 0);
+    const int lv0 = S.tb->lv[0];
+    int r = 0;
+    if (qh != 0) r += WB_LV((abs(qh) + dh) >> 1);
+    else if (lane < 31 && (bh >> (lane + 1)) != 0) r += lv0;
+    if (ql != 0) r += WB_LV((abs(ql) + dl) >> 1);
+    else if (bh != 0 || (lane < 31 && (bl >> (lane + 1)) != 0)) r += lv0;
+    rate_out = warp_sum(r);
+    any_out = (bh | bl) != 0;
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // tasks
 // ---------------------------------------------------------------------------------------------------------------
 __device__ WarpScratch warp_scratch(Shared &S, int warp) {
@@ -1207,7 +1397,7 @@ __device__ WarpScratch warp_scratch(Shared &S, int warp) {
     if (warp < NBIG) {
         ws.A = S.bigA[warp]; ws.B = S.bigB[warp]; ws.Wd = S.bigW[warp]; ws.pred = S.bigP[warp];
     } else {
-        ws.A = S.smA[warp - NBIG]; ws.B = S.smB[warp - NBIG]; ws.Wd = S.smW[warp - NBIG]; ws.pred = S.smP[warp - NBIG];
+        ws.A = S.sm[warp - NBIG].A; ws.B = S.sm[warp - NBIG].B; ws.Wd = S.sm[warp - NBIG].W; ws.pred = S.sm[warp - NBIG].P;
     }
     ws.refx = S.refx[warp];
     return ws;
@@ -1298,6 +1488,10 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         __syncwarp();
         mm_cols_q(S.tb->T + to, reinterpret_cast<const int32_t *>(B), A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
         __syncwarp();
+#if WB_CHAIN8
+        if (l2 == 3) trellis8_chain(S, tab, A, reinterpret_cast<uint16_t *>(A + 128), B, reinterpret_cast<int4 *>(B), lane, rate, anylev);  // B..W: 1 kB table
+        else
+#endif
         trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
     } else {
 #pragma unroll RU

@@ -64,7 +64,8 @@ cudaError_t launch_bin_compact(const SyntaxParams &Q, cudaStream_t stream);
 cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream);
 
 struct BlockParams {
-    int op;  // 0 predict, 1 forward DCT, 2 inverse DCT, 3 dep-quant (+rate), 4 dequantise
+    int op;  // 0 predict, 1 forward DCT, 2 inverse DCT, 3 dep-quant (+rate) by the routine the search uses for that size, 4 dequantise,
+             // 5 dep-quant of every size by trellis()
     int W, H, x, y, w, tree, ar, bl, c, mode;
     const uint8_t *rec;   // I420 reconstruction picture (op 0)
     uint8_t *out8;
