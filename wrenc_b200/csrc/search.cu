@@ -1205,11 +1205,11 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
         } else if (P.op == 3 || P.op == 5) {  // 3: the routine the search uses for this size; 5: trellis() for every size
             int rate; bool any;
 #if WB_CHAIN8
-            if (l2 == 3 && P.op == 3) trellis8_chain(V, P.tab, ws.A, reinterpret_cast<uint16_t *>(ws.A + 128), ws.B, reinterpret_cast<int4 *>(ws.B), lane, rate, any);
+            if (l2 == 3 && P.op == 3) trellis8_chain(V, P.tab, ws.A, reinterpret_cast<uint16_t *>(ws.A + 128), ws.A, reinterpret_cast<int4 *>(ws.B), lane, rate, any);
             else
 #endif
-            trellis(V, P.tab, ws.A, l2, ws.Wd, ws.B, lane, rate, any);
-            for (int i = lane; i < nn; i += 32) out[i] = ws.B[i];
+            trellis(V, P.tab, ws.A, l2, ws.Wd, ws.A, lane, rate, any);  // levels in place, as the search does
+            for (int i = lane; i < nn; i += 32) out[i] = ws.A[i];
             if (lane == 0) P.outi[blk] = rate;
         } else if (P.op == 4) {
             const int sh = l2 + 4, off = 1 << (sh - 1), ls = P.tab->ls;

@@ -53,7 +53,7 @@ constexpr int NTHREADS = NW * 32;
 #endif
 constexpr int KC = WB_K;     // CTUs searched in lock step by one CTA
 #ifndef WB_NBIG
-#define WB_NBIG 8
+#define WB_NBIG WB_NW
 #endif
 constexpr int NBIG = NW < WB_NBIG ? NW : WB_NBIG;  // warps with scratch large enough for a 32x32 luma pipeline (they drain those tasks first)
 
@@ -179,23 +179,20 @@ struct Shared {
     int ticket[2];            // dynamic task tickets of the current / previous phase
     int ticket_big[2];        //   and of the tasks that need the large scratch (32x32 luma pipelines of the root)
     // per-warp scratch
-    alignas(16) int16_t bigA[NBIG][1024];
-    alignas(16) int16_t bigB[NBIG][1024];
-    alignas(16) uint16_t bigW[NBIG][1024];
-    alignas(16) uint8_t bigP[NBIG][1024];
-    struct alignas(16) SmallScratch {  // B and W are adjacent on purpose: together they hold the 1 kB cost table of trellis8_chain
-        int16_t A[256];
-        int16_t B[256];
-        uint16_t W[256];
-        uint8_t P[256];
-    } sm[NW - NBIG + 1];
+    // per-warp scratch, the same for every warp (5 kB: a 32x32 luma pipeline fits): A residual -> coefficients -> levels (the
+    // dependent quantisation writes the levels in place) -> reconstruction residual; B transform intermediate, then the
+    // trellis words of trellis() / the 1 kB cost table of trellis8_chain, then the dequantised block; P the prediction
+    struct alignas(16) WarpBuf {
+        int16_t A[1024];
+        int16_t B[1024];
+        uint8_t P[1024];
+    } wbuf[NW];
     alignas(16) int16_t refx[NW][100];  // per-warp scratch line: projected references of the negative-angle modes (as bytes)
 };
 
 static_assert(offsetof(CtuCtx, lvY) % 8 == 0 && offsetof(CtuCtx, lvC) % 8 == 0 && sizeof(CtuCtx) % 8 == 0, "commit_root_slot stores the levels as 64-bit words");
-static_assert(offsetof(Shared, bigA) % 16 == 0 && offsetof(Shared, bigB) % 16 == 0 && offsetof(Shared, sm) % 16 == 0 && sizeof(Shared::SmallScratch) % 16 == 0 &&
-                  offsetof(Tables, Tt) % 4 == 0,
-              "full_pair4 reads these arrays as 32-bit words");
+static_assert(offsetof(Shared, wbuf) % 16 == 0 && sizeof(Shared::WarpBuf) % 16 == 0 && offsetof(Tables, Tt) % 4 == 0,
+              "full_pair4 reads these arrays as 32-bit words, trellis8_chain stores 16-byte rows");
 
 struct Ctx {  // what the per-CTU device functions see
     Tables *tb;
@@ -1394,11 +1391,7 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
 // ---------------------------------------------------------------------------------------------------------------
 __device__ WarpScratch warp_scratch(Shared &S, int warp) {
     WarpScratch ws;
-    if (warp < NBIG) {
-        ws.A = S.bigA[warp]; ws.B = S.bigB[warp]; ws.Wd = S.bigW[warp]; ws.pred = S.bigP[warp];
-    } else {
-        ws.A = S.sm[warp - NBIG].A; ws.B = S.sm[warp - NBIG].B; ws.Wd = S.sm[warp - NBIG].W; ws.pred = S.sm[warp - NBIG].P;
-    }
+    ws.A = S.wbuf[warp].A; ws.B = S.wbuf[warp].B; ws.Wd = reinterpret_cast<uint16_t *>(S.wbuf[warp].B); ws.pred = S.wbuf[warp].P;
     ws.refx = S.refx[warp];
     return ws;
 }
@@ -1488,14 +1481,16 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         __syncwarp();
         mm_cols_q(S.tb->T + to, reinterpret_cast<const int32_t *>(B), A, n, l2, 1 << (l2 + 5), l2 + 6, false, lane);
         __syncwarp();
+        // dependent quantisation: coefficients -> levels, in place in A (every position's coefficient is read by the thread that
+        // writes its level); B holds the trellis words / the cost table meanwhile
 #if WB_CHAIN8
-        if (l2 == 3) trellis8_chain(S, tab, A, reinterpret_cast<uint16_t *>(A + 128), B, reinterpret_cast<int4 *>(B), lane, rate, anylev);  // B..W: 1 kB table
+        if (l2 == 3) trellis8_chain(S, tab, A, reinterpret_cast<uint16_t *>(A + 128), A, reinterpret_cast<int4 *>(B), lane, rate, anylev);
         else
 #endif
-        trellis(S, tab, A, l2, ws.Wd, B, lane, rate, anylev);
+        trellis(S, tab, A, l2, reinterpret_cast<uint16_t *>(B), A, lane, rate, anylev);
     } else {
 #pragma unroll RU
-        for (int i = lane; i < nn; i += 32) B[i] = 0;
+        for (int i = lane; i < nn; i += 32) A[i] = 0;
         __syncwarp();
     }
     // candidate slot (planar, DC, dir, dir-1, dir+1, CCLM): the evaluation's outcome goes to the CTU's global scratch, block-local raster
@@ -1505,7 +1500,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         gRec = S.c->groot + slot * ROOT_SLOT_SAMPLES + soff;
         int16_t *gLv = reinterpret_cast<int16_t *>(S.c->groot + ROOT_SLOTS * ROOT_SLOT_SAMPLES) + slot * ROOT_SLOT_SAMPLES + soff;
 #pragma unroll RU
-        for (int i = lane; i < nn / 2; i += 32) reinterpret_cast<uint32_t *>(gLv)[i] = reinterpret_cast<const uint32_t *>(B)[i];  // two levels per store
+        for (int i = lane; i < nn / 2; i += 32) reinterpret_cast<uint32_t *>(gLv)[i] = reinterpret_cast<const uint32_t *>(A)[i];  // two levels per store
     }
     if (anylev) {
         const int sh = l2 + 4, off = 1 << (sh - 1), ls = tab->ls;
@@ -1513,23 +1508,23 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
 #pragma unroll RU
         for (int o = lane; o < nn / 2; o += 32) {
             const int ip = o >> l2, x = o & (n - 1);
-            const int d0 = min(32767, max(-32768, ((int)B[(2 * ip) * n + x] * ls + off) >> sh));
-            const int d1 = min(32767, max(-32768, ((int)B[(2 * ip + 1) * n + x] * ls + off) >> sh));
-            reinterpret_cast<int32_t *>(A)[o] = (d0 & 0xffff) | (d1 << 16);
+            const int d0 = min(32767, max(-32768, ((int)A[(2 * ip) * n + x] * ls + off) >> sh));
+            const int d1 = min(32767, max(-32768, ((int)A[(2 * ip + 1) * n + x] * ls + off) >> sh));
+            reinterpret_cast<int32_t *>(B)[o] = (d0 & 0xffff) | (d1 << 16);
         }
         __syncwarp();
         // vertical: V[y][x] = clamp16((sum_i T[i][y] * D[i][x] + 64) >> 7)   (Tt's rows are T's columns)
-        mm_cols_q(S.tb->Tt + to, reinterpret_cast<const int32_t *>(A), B, n, l2, 64, 7, true, lane);
+        mm_cols_q(S.tb->Tt + to, reinterpret_cast<const int32_t *>(B), A, n, l2, 64, 7, true, lane);
         __syncwarp();
         // horizontal: R[y][x] = (sum_i T[i][x] * V[y][i] + 2048) >> 12
-        mm_rows_q<false>(S.tb->Qc + to / 4, B, A, n, l2, 2048, 12, lane);
+        mm_rows_q<false>(S.tb->Qc + to / 4, A, B, n, l2, 2048, 12, lane);
         __syncwarp();
     }
     unsigned ssd = 0;
 #pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
-        int res = anylev ? (int)A[i] : 0;
+        int res = anylev ? (int)B[i] : 0;
         int rec = clip8((int)(int16_t)((int)ws.pred[i] + res));
         int d = rec - (int)org[(y << osh) + x];
         ssd += (unsigned)(d * d);
