@@ -32,10 +32,10 @@ def test_forward_inverse_dct(pair, n):
     assert np.array_equal(enc.block_inv_dct(deq), np.stack([ora.inv_dct(b) for b in deq]))
 
 
-@pytest.mark.parametrize("n,general", [(4, 0), (8, 0), (8, 1), (16, 0), (32, 0)])
+@pytest.mark.parametrize("n,general", [(4, 0), (8, 0), (8, 1), (16, 0), (16, 1), (32, 0)])
 def test_dep_quant_trellis_rate_dequant(pair, n, general, monkeypatch):
-    """Dependent quantisation + rate + dequantisation of random, sparse, DCT-like and adversarial (DC-leaf wrap) blocks.  8x8 TBs have
-    two routines in the kernel: the state-per-lane chain the search uses and the general chunk-matrix routine; both are checked."""
+    """Dependent quantisation + rate + dequantisation of random, sparse, DCT-like and adversarial (DC-leaf wrap) blocks.  8x8 and 16x16
+    TBs have two routines in the kernel: the state-per-lane chain the search uses and the general chunk-matrix routine; both are checked."""
     enc, ora = pair
     monkeypatch.setenv("WRENC_B200_BLOCK_GENERAL", str(general))
     rng = np.random.default_rng(100 + n)

@@ -1208,6 +1208,10 @@ extern "C" __global__ void __launch_bounds__(NTHREADS, 1) wrenc_b200_block_kerne
             if (l2 == 3 && P.op == 3) trellis8_chain(V, P.tab, ws.A, reinterpret_cast<uint16_t *>(ws.A + 128), ws.A, reinterpret_cast<int4 *>(ws.B), lane, rate, any);
             else
 #endif
+#if WB_CHAIN16
+            if (l2 == 4 && P.op == 3) trellis16_chain(V, P.tab, ws.A, reinterpret_cast<uint8_t *>(ws.A + 256), reinterpret_cast<int4 *>(ws.A + 384), lane, rate, any);
+            else
+#endif
             trellis(V, P.tab, ws.A, l2, ws.Wd, ws.A, lane, rate, any);  // levels in place, as the search does
             for (int i = lane; i < nn; i += 32) out[i] = ws.A[i];
             if (lane == 0) P.outi[blk] = rate;

@@ -42,6 +42,9 @@ namespace wb {
 #ifndef WB_RU
 #define WB_RU 1  // unroll of the copy / element-wise loops that are not on a critical path: rolled (4, what the compiler does by itself, is 7 % more code and measured 2.2 % slower)
 #endif
+#ifndef WB_CHAIN16
+#define WB_CHAIN16 0  // 1: 16x16 TBs quantised by trellis16_chain too (bit-exact; measured 4.6 % slower: a 255-step chain is longer than the chunked pass)
+#endif
 #ifndef WB_CHAIN8
 #define WB_CHAIN8 1  // 8x8 TBs quantised by trellis8_chain (one sequential state-per-lane chain) instead of trellis()
 #endif
@@ -1386,6 +1389,170 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
     __syncwarp();
 }
 
+// The same for ONE 16x16 TB (256 positions, 16 sub-blocks), in place: coef -> levels.  The warp's whole 5 kB scratch is laid out
+// by the caller: coefficients / levels 512 B | fl: one flag byte per position (bit 0 / 1 parity of a0 for delta 0 / 1, bit 2:
+// state 0 sees a0 = 0 without its rate) | lc: 4 kB cost table | (prediction, 256 B).  All 32 lanes run the chain, as eight
+// identical groups of four state lanes: nothing diverges, and group w simply keeps the decision word of positions 32w .. 32w+31,
+// so the 4 x 256 decision bits need no memory.  x = S / ls is recomputed where it is needed instead of being stored.
+__device__ __noinline__ void trellis16_chain(const Ctx S, const DevTables *__restrict__ tab, int16_t *coef, uint8_t *fl, int4 *lc, int lane, int &rate_out, bool &any_out) {
+    WB_SHARED_CTX(S);
+    WB_SHARED_PTR(coef); WB_SHARED_PTR(fl); WB_SHARED_PTR(lc);
+    constexpr int sh = 8, off = 128;
+    const int ls = tab->ls, ldq1 = S.tb->ldq[1];
+    const uint16_t *scan = S.tb->scan + tab_off(4);
+    auto xq_of = [&](int tc) -> unsigned {
+        return tc == 0 ? 0u : min(div_ls(S, tc > 0 ? ((unsigned)tc << sh) - (unsigned)off : ((unsigned)(-tc) << sh) + (unsigned)off, (unsigned)ls), 2047u);
+    };
+    // ---- A1: k* (H2), any coefficient at all?
+    int kstar = -1;
+    bool anytc = false;
+#pragma unroll 1
+    for (int k = lane; k < 256; k += 32) {
+        const int tc = coef[scan[k]];
+        anytc |= tc != 0;
+        if (xq_of(tc) >= 2) kstar = k;
+    }
+    kstar = warp_max(kstar);
+    if (!__any_sync(0xffffffffu, anytc)) {  // every level is 0, rate 0 (as in trellis())
+#pragma unroll 1
+        for (int k = lane; k < 128; k += 32) reinterpret_cast<uint32_t *>(coef)[k] = 0u;
+        rate_out = 0;
+        any_out = false;
+        __syncwarp();
+        return;
+    }
+    // ---- A2: local costs of every position -> table, flag bytes
+#pragma unroll 1
+    for (int k = lane; k < 256; k += 32) {
+        const int tc = coef[scan[k]];
+        const unsigned x = xq_of(tc);
+        const LC l = local_costs(S, tab, tc, x | ((unsigned)(tc != 0) << 11), k, kstar, ls, sh, off, ldq1);
+        lc[k] = make_int4(l.L00, l.L10, l.L01, l.L11);
+        fl[k] = (uint8_t)((l.pk & 3u) | ((k > kstar && (x >> 1) == 0) ? 4u : 0u));
+    }
+    __syncwarp();
+    // ---- B: the chain, lane (w, s): state s; group w keeps decision word w
+    unsigned keep = 0;
+    {
+        const int s = lane & 3, w_own = lane >> 2;
+        const char *lp = reinterpret_cast<const char *>(lc) + (s >> 1) * 8;
+        const int fsh = s < 2 ? 0 : 1;  // which parity bit of the flag byte this state looks at
+        const unsigned finv = s & 1;
+        int C;
+        unsigned dec = 0;
+        {   // DC leaf (quantizer.rs:367-409) for this lane's state
+            const int tc0 = coef[0];
+            const unsigned x0 = xq_of(tc0);
+            const bool itz = (s == 0) && (kstar < 0);
+            if (tc0 == 0) {
+                C = itz ? -ldq1 : ldq1;
+            } else {
+                const int delta = s > 1;
+                const int A0 = (int)(x0 >> 1);
+                int q0 = (int)(int16_t)(2 * A0 - delta);  // H3: usize wrap gives -1 for a0 == 0, delta == 1
+                if (tc0 < 0) q0 = -q0;
+                const int d0 = abs(tc0 - ((q0 * ls + off) >> sh));
+                const int bits0 = (A0 != 0 || !itz) ? A0 + 1 : 0;
+                const int cost0 = 128 * d0 + WB_LDQ(bits0);
+                const int A1 = A0 + 1;
+                int q1 = 2 * A1 - delta;
+                if (tc0 < 0) q1 = -q1;
+                const int d1 = abs(tc0 - ((q1 * ls + off) >> sh));
+                const int cost1 = 128 * d1 + WB_LDQ(A1 + 1);
+                if (cost0 <= cost1) {
+                    C = cost0;
+                    if (itz && A0 == 0) C -= ldq1;
+                } else {
+                    C = cost1;
+                    dec = 1u;
+                }
+            }
+        }
+        // states 0,1 continue from {0,2}, states 2,3 from {1,3}; which of the two feeds candidate a0 depends on the parity of a0
+        const int srcP = (lane & ~3) | (s >> 1), srcQ = srcP + 2;
+#pragma unroll 1
+        for (int sb = 0; sb < 16; sb++) {  // one sub-block of 16 positions per iteration
+            const int jb = sb * 16;
+            int j0 = jb + 1;
+            if (sb) {  // sub-block start: renormalise, then the step with the post-comparison adjustment (quantizer.rs:512-514)
+                int mn = min(C, __shfl_xor_sync(0xffffffffu, C, 1));
+                mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, 2));
+                C -= mn;
+                const int2 L = *reinterpret_cast<const int2 *>(lp + jb * 16);
+                const unsigned f = fl[jb];
+                const int P = __shfl_sync(0xffffffffu, C, srcP), Q = __shfl_sync(0xffffffffu, C, srcQ);
+                const bool sw = (((f >> fsh) ^ finv) & 1u) != 0;
+                const int La = L.x - ((s == 0 && (f & 4u)) ? ldq1 : 0);
+                const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
+                const bool d = c1 < c0;  // ties keep a0 (quantizer.rs:505)
+                C = d ? c1 : c0;
+                if (s == 0 && jb > kstar && !d) C -= ldq1;
+                dec |= (unsigned)d << (jb & 31);
+            }
+#pragma unroll 5
+            for (int j = j0; j < jb + 16; j++) {
+                const int2 L = *reinterpret_cast<const int2 *>(lp + j * 16);
+                const unsigned f = fl[j];
+                const int P = __shfl_sync(0xffffffffu, C, srcP), Q = __shfl_sync(0xffffffffu, C, srcQ);
+                const bool sw = (((f >> fsh) ^ finv) & 1u) != 0;
+                const int La = L.x - ((s == 0 && (f & 4u)) ? ldq1 : 0);
+                const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
+                const bool d = c1 < c0;
+                C = d ? c1 : c0;
+                dec |= (unsigned)d << (j & 31);
+            }
+            if (sb & 1) {  // a decision word is complete
+                if (w_own == (sb >> 1)) keep = dec;
+                dec = 0;
+            }
+        }
+    }
+    __syncwarp();
+    // ---- F: walk from the last scan position with state 0 (quantizer.rs:686-721) + rate (block_splitter.rs:415-460), 32 positions
+    //      at a time from the top; this lane owns position 32 i + lane of segment i
+    unsigned state = 0;  // state entering the segment's highest position
+    bool seen_nz = false;
+    int rate = 0;
+    const int lv0 = S.tb->lv[0];
+#pragma unroll 1
+    for (int i = 7; i >= 0; i--) {
+        const int k = 32 * i + lane;
+        const int sc = scan[k];
+        const int tc = coef[sc];
+        const unsigned x = xq_of(tc);
+        unsigned md = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) md |= ((__shfl_sync(0xffffffffu, keep, 4 * i + q) >> lane) & 1u) << q;
+        const unsigned pk = k == 0 ? ((x >> 1) & 1u) * 3u : (((x >> 1) & 1u) | ((((x + 1) >> 1) & 1u) << 1));
+        unsigned inc = pos_map(pk, md, tc != 0);
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned u = __shfl_down_sync(0xffffffffu, inc, d);
+            if (lane + d < 32) inc = map_compose(u, inc);
+        }
+        const unsigned exc = __shfl_down_sync(0xffffffffu, inc, 1);
+        const unsigned st = lane == 31 ? state : ((exc >> (8 * state)) & 3u);  // state entering this lane's position
+        state = (__shfl_sync(0xffffffffu, inc, 0) >> (8 * state)) & 3u;
+        const int dl = st > 1;
+        int q = 0;
+        if (tc != 0) {
+            const unsigned a = (k == 0 ? (x >> 1) : ((x + dl) >> 1)) + ((md >> st) & 1u);
+            if (k == 0) q = (int)(int16_t)(2 * (int)a - dl);
+            else q = a > 0 ? 2 * (int)a - dl : 0;
+            if (tc < 0) q = -q;
+        }
+        coef[sc] = (int16_t)q;  // in place: this thread read the coefficient above
+        // a zero level costs lv[0] iff a non-zero level precedes it in the walk (= sits at a higher scan position)
+        const unsigned bal = __ballot_sync(0xffffffffu, q != 0);
+        if (q != 0) rate += WB_LV((abs(q) + dl) >> 1);
+        else if (seen_nz || (lane < 31 && (bal >> (lane + 1)) != 0)) rate += lv0;
+        seen_nz = seen_nz || bal != 0;
+    }
+    rate_out = warp_sum(rate);
+    any_out = seen_nz;
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // tasks
 // ---------------------------------------------------------------------------------------------------------------
@@ -1460,7 +1627,10 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     WB_SHARED_CTX(S);
     WB_SHARED_PTR(ws.A); WB_SHARED_PTR(ws.B); WB_SHARED_PTR(ws.Wd); WB_SHARED_PTR(ws.pred); WB_SHARED_PTR(ws.refx);
     const int cs = c != 0, n = nd.w >> cs, bx = nd.x >> cs, by = nd.y >> cs, l2 = ilog2i(n), nn = n * n;
-    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, ws.pred, lane) != 0;
+    // (a 16x16 TB keeps its prediction in the last 256 bytes of the warp's scratch: everything between the coefficients and it is the
+    //  cost table of trellis16_chain)
+    uint8_t *const pred = ws.pred + ((WB_CHAIN16 && l2 == 4) ? 768 : 0);
+    const bool anysad = predict_block(S, g, nd, c, mode, ws.refx, pred, lane) != 0;
     __syncwarp();
     int16_t *A = ws.A, *B = ws.B;
     bool anyres = anysad;
@@ -1469,7 +1639,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
 #pragma unroll 1
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
-        A[i] = (int16_t)((int)org[(y << osh) + x] - (int)ws.pred[i]);
+        A[i] = (int16_t)((int)org[(y << osh) + x] - (int)pred[i]);
     }
     anyres = __any_sync(0xffffffffu, anyres);
     __syncwarp();
@@ -1485,6 +1655,10 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
         // writes its level); B holds the trellis words / the cost table meanwhile
 #if WB_CHAIN8
         if (l2 == 3) trellis8_chain(S, tab, A, reinterpret_cast<uint16_t *>(A + 128), A, reinterpret_cast<int4 *>(B), lane, rate, anylev);
+        else
+#endif
+#if WB_CHAIN16
+        if (l2 == 4) trellis16_chain(S, tab, A, reinterpret_cast<uint8_t *>(A + 256), reinterpret_cast<int4 *>(A + 384), lane, rate, anylev);
         else
 #endif
         trellis(S, tab, A, l2, reinterpret_cast<uint16_t *>(B), A, lane, rate, anylev);
@@ -1525,7 +1699,7 @@ __device__ __noinline__ void full_task(const Ctx S, const DevTables *__restrict_
     for (int i = lane; i < nn; i += 32) {
         int y = i >> l2, x = i & (n - 1);
         int res = anylev ? (int)B[i] : 0;
-        int rec = clip8((int)(int16_t)((int)ws.pred[i] + res));
+        int rec = clip8((int)(int16_t)((int)pred[i] + res));
         int d = rec - (int)org[(y << osh) + x];
         ssd += (unsigned)(d * d);
         if (slot >= 0) gRec[i] = (uint8_t)rec;
