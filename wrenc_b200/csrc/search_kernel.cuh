@@ -48,7 +48,10 @@ namespace wb {
 #ifndef WB_CHAIN8
 #define WB_CHAIN8 1  // 8x8 TBs quantised by trellis8_chain (one sequential state-per-lane chain) instead of trellis()
 #endif
-constexpr int U5 = WB_U5, U2 = WB_U2, RU = WB_RU;
+#ifndef WB_U8C
+#define WB_U8C 5  // unroll of the 15 steps per sub-block of trellis8_chain
+#endif
+constexpr int U5 = WB_U5, U2 = WB_U2, RU = WB_RU, U8C = WB_U8C;
 constexpr int NW = WB_NW;    // warps per CTA
 constexpr int NTHREADS = NW * 32;
 #ifndef WB_K
@@ -1317,7 +1320,7 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
                     if (((adj >> (2 * h + q4 - 1)) & 1u) && !d) C -= ldq1;
                     dec |= (unsigned)d << jb;
                 }
-#pragma unroll 5
+#pragma unroll U8C
                 for (int j = j0; j < jb + 16; j++) {
                     const int2 L = *reinterpret_cast<const int2 *>(lph + j * 16);
                     const int P = __shfl_sync(0xFu, C, srcP), Q = __shfl_sync(0xFu, C, srcQ);
