@@ -46,7 +46,7 @@ sys.path.insert(0, ROOT)
 DEPTH = 3
 OPS_PER_CTU = 8290304          # SURVEY.md section 8(d) nominal integer ops per CTU (transforms 4 358 144 + trellis 3 932 160)
 ALG_BYTES_PER_CTU = 1536 + 1536 + 3072 + 88   # source read + recon write + level write + record
-NCU_DRAM_BYTES_PER_CTU = 49740  # dram__bytes_read.sum + dram__bytes_write.sum per CTU of the ncu capture at the bench launch (profiles/r2_search_kernel_ncu_full.txt)
+NCU_DRAM_BYTES_PER_CTU = 49360  # dram__bytes_read.sum + dram__bytes_write.sum per CTU of the ncu capture at the bench launch (profiles/r2_search_kernel_ncu_full.txt)
 UNIT = "frames/s"
 
 # The configurations BASELINE.json names.  frames = the configuration's total; frames_weak = per GPU when --scaling weak.
