@@ -1100,17 +1100,40 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
                 }
             }
         }
-        // ---- C: apply head + matrix chunk by chunk; lane j owns chunk r*32 + j
+#ifndef WB_PAIR16
+#define WB_PAIR16 0  // 1: 16x16 TBs: the matrices of the two chunks of a sub-block are combined before the serial pass (16 steps instead of 32); bit-exact, measured 1.2 % slower
+#endif
+        // ---- B2 (16x16 TBs: 32 chunks of 8, the sub-block starts - the only steps that may be non-linear - are the even chunks):
+        //      the even lanes combine their matrix with their right neighbour's, the serial pass then runs over pairs
+        const bool pair = WB_PAIR16 && nn == 256;
+        int A0[4][4];  // the chunk's own matrix, for the way back down
+        if (pair) {
+            int N[4][4];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                const int b0 = __shfl_down_sync(0xffffffffu, M[s][0], 1), b1 = __shfl_down_sync(0xffffffffu, M[s][1], 1);
+                const int b2 = __shfl_down_sync(0xffffffffu, M[s][2], 1), b3 = __shfl_down_sync(0xffffffffu, M[s][3], 1);
+#pragma unroll
+                for (int t = 0; t < 4; t++) N[s][t] = min(min(b0 + M[0][t], b1 + M[1][t]), min(b2 + M[2][t], b3 + M[3][t]));
+            }
+#pragma unroll
+            for (int s = 0; s < 4; s++)
+#pragma unroll
+                for (int t = 0; t < 4; t++) { A0[s][t] = M[s][t]; M[s][t] = N[s][t]; }
+        }
+        const int cstep = pair ? 2 : 1;
+        // ---- C: apply head + matrix chunk (pair) by chunk (pair); lane j owns chunk r*32 + j
         int O0 = 0, O1 = 0, O2 = 0, O3 = 0, my0 = 0, my1 = 0, my2 = 0, my3 = 0;
+        int X0 = 0, X1 = 0, X2 = 0, X3 = 0;  // what the owner's matrix applies to (= its entry costs after its separate head, if any)
         const int cnt = min(32, nch - r * 32);
         const unsigned sepmask = __ballot_sync(0xffffffffu, sep_head);
 #pragma unroll 1
-        for (int j = 0; j < cnt; j++) {
+        for (int j = 0; j < cnt; j += cstep) {
             int I0, I1, I2, I3;
             if (j == 0) { I0 = carry0; I1 = carry1; I2 = carry2; I3 = carry3; }
             else {
-                I0 = __shfl_sync(0xffffffffu, O0, j - 1); I1 = __shfl_sync(0xffffffffu, O1, j - 1);
-                I2 = __shfl_sync(0xffffffffu, O2, j - 1); I3 = __shfl_sync(0xffffffffu, O3, j - 1);
+                I0 = __shfl_sync(0xffffffffu, O0, j - cstep); I1 = __shfl_sync(0xffffffffu, O1, j - cstep);
+                I2 = __shfl_sync(0xffffffffu, O2, j - cstep); I3 = __shfl_sync(0xffffffffu, O3, j - cstep);
             }
             int H0 = I0, H1 = I1, H2 = I2, H3 = I3;
             if ((sepmask >> j) & 1u) {  // uniform: chunk j has a separate head (every lane applies its own, only lane j's result is used)
@@ -1123,10 +1146,20 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
             int T3 = min(min(M[3][0] + H0, M[3][1] + H1), min(M[3][2] + H2, M[3][3] + H3));
             const int mn = min(min(T0, T1), min(T2, T3));
             O0 = T0 - mn; O1 = T1 - mn; O2 = T2 - mn; O3 = T3 - mn;
-            if (lane == j) { my0 = I0; my1 = I1; my2 = I2; my3 = I3; }
+            if (lane == j) { my0 = I0; my1 = I1; my2 = I2; my3 = I3; X0 = H0; X1 = H1; X2 = H2; X3 = H3; }
         }
-        carry0 = __shfl_sync(0xffffffffu, O0, cnt - 1); carry1 = __shfl_sync(0xffffffffu, O1, cnt - 1);
-        carry2 = __shfl_sync(0xffffffffu, O2, cnt - 1); carry3 = __shfl_sync(0xffffffffu, O3, cnt - 1);
+        carry0 = __shfl_sync(0xffffffffu, O0, cnt - cstep); carry1 = __shfl_sync(0xffffffffu, O1, cnt - cstep);
+        carry2 = __shfl_sync(0xffffffffu, O2, cnt - cstep); carry3 = __shfl_sync(0xffffffffu, O3, cnt - cstep);
+        if (pair) {  // the way back down: entry costs of the odd chunk = the even chunk's own matrix applied to what it started from
+            int E0 = min(min(A0[0][0] + X0, A0[0][1] + X1), min(A0[0][2] + X2, A0[0][3] + X3));
+            int E1 = min(min(A0[1][0] + X0, A0[1][1] + X1), min(A0[1][2] + X2, A0[1][3] + X3));
+            int E2 = min(min(A0[2][0] + X0, A0[2][1] + X1), min(A0[2][2] + X2, A0[2][3] + X3));
+            int E3 = min(min(A0[3][0] + X0, A0[3][1] + X1), min(A0[3][2] + X2, A0[3][3] + X3));
+            const int mn = min(min(E0, E1), min(E2, E3));
+            E0 = __shfl_up_sync(0xffffffffu, E0 - mn, 1); E1 = __shfl_up_sync(0xffffffffu, E1 - mn, 1);
+            E2 = __shfl_up_sync(0xffffffffu, E2 - mn, 1); E3 = __shfl_up_sync(0xffffffffu, E3 - mn, 1);
+            if (lane & 1) { my0 = E0; my1 = E1; my2 = E2; my3 = E3; }
+        }
         // ---- D: replay the chunk from its true entry costs, record decisions and the chunk's walk map
         if (vc) {
             int C0 = my0, C1 = my1, C2 = my2, C3 = my3;
