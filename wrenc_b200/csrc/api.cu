@@ -4,8 +4,10 @@
 // Host-plane path (submit / receive): a ring of batch slots, each with its own picture, decision and coder buffers.  Pictures
 // are copied to the device as they are submitted (copy stream); a slot that fills up is launched at once: search kernel on the
 // search stream, syntax + CABAC kernels on the coder stream, device-to-host copies on their own stream, chained by events.  The
-// search of batch n+1 therefore overlaps the H2D copies of batch n+2 and the coder + D2H copies of batch n, and receive returns
-// picture i as soon as ITS bytes have landed.  Nothing in the launch path synchronises with the host.
+// search of batch n+1 therefore overlaps the H2D copies of batch n+2 and the D2H copies of batch n, and receive returns picture i
+// as soon as ITS bytes have landed.  (The coder kernels of batch n are only ORDERED independently of the next search: on one GPU they
+// cannot run under it, because the search grid holds every register of every SM - DESIGN.md section 1.)  Nothing in the launch path
+// synchronises with the host.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
