@@ -99,8 +99,9 @@ __device__ __forceinline__ void fill_cm(const Ctx S, const Node nd, int mode, in
 
 // Tasks of a phase are handed out in list order (the large luma tasks first) to whichever warp is free: a shared-memory
 // ticket per phase (S.ticket[phase parity], reset two phases later); a phase with at most one task per warp is assigned
-// statically.  32x32 luma pipelines need the large scratch buffers that only the first NBIG warps own: those `nbig` tasks lead
-// the list and have their own ticket, which the NBIG warps drain before they join the others on the general ticket.
+// statically.  The long tasks of a phase (the 32x32 luma pipelines of the root) lead the list and have their own ticket, which
+// the warps drain before they join the general one: longest tasks first.  (Until round 2 only NBIG = 8 warps owned a scratch
+// large enough for them; now every warp does.)
 #ifndef WB_NT_NOINLINE
 #define WB_NT_NOINLINE 0
 #endif
@@ -151,7 +152,7 @@ __device__ __noinline__ void leaf_eval(Shared &S, const SearchParams &P, const N
     const WarpScratch ws = warp_scratch(S, warp);
     constexpr int ncomp = 3;  // SINGLE_TREE 32x32 / 16x16 CUs (smaller CUs: small_eval)
     const bool is_root = id.depth == 0;
-    int nst = 0;  // number of leading tasks that need the large scratch (32x32 luma pipelines of the root), see next_task
+    int nst = 0;  // number of leading long tasks (32x32 luma pipelines of the root) with their own ticket, see next_task
     constexpr int sb = 0;  // every full evaluation's outcome is kept in a candidate slot of the CTU's global scratch
     [[maybe_unused]] const int pk_ = 16 * id.depth;
     if (tid < KC && S.c[tid].active) S.c[tid].node = pack_node(make_node(S.c[tid].g, id));

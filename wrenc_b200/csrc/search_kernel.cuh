@@ -17,6 +17,10 @@
 // tasks, one warp (4x4 TBs: half a warp) each.  What is written once and read back at most once (candidate slots, saved
 // no-split states) lives in a per-CTA global scratch.  All arithmetic is exact integer except the RD cost, which is IEEE f32
 // with explicit _rn intrinsics (no FMA contraction) in the reference's operation order.
+//
+// Code size is a first-order effect here: the kernel is ~15 000 instructions (234 kB) against a 32 kB
+// instruction cache, and lock step is what keeps the 16 warps of an SM in the same few kB at any moment.  Hence the rolled copy
+// loops (WB_RU), the constant-mask collectives, and the build knobs below, each of which records what it measured.
 #pragma once
 #include <cuda_runtime.h>
 #include <stddef.h>
@@ -61,7 +65,7 @@ constexpr int KC = WB_K;     // CTUs searched in lock step by one CTA
 #ifndef WB_NBIG
 #define WB_NBIG WB_NW
 #endif
-constexpr int NBIG = NW < WB_NBIG ? NW : WB_NBIG;  // warps with scratch large enough for a 32x32 luma pipeline (they drain those tasks first)
+constexpr int NBIG = NW < WB_NBIG ? NW : WB_NBIG;  // warps that take the leading ('big') tasks of a phase first: all of them since every warp owns a 5 kB scratch
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -183,7 +187,7 @@ struct Shared {
 #endif
     unsigned long long tma_bar;  // mbarrier the TMA bulk copies of the source blocks complete on
     int ticket[2];            // dynamic task tickets of the current / previous phase
-    int ticket_big[2];        //   and of the tasks that need the large scratch (32x32 luma pipelines of the root)
+    int ticket_big[2];        //   and of the leading long tasks of a phase (32x32 luma pipelines of the root), handed out first
     // per-warp scratch
     // per-warp scratch, the same for every warp (5 kB: a 32x32 luma pipeline fits): A residual -> coefficients -> levels (the
     // dependent quantisation writes the levels in place) -> reconstruction residual; B transform intermediate, then the
