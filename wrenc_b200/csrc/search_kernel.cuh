@@ -1250,8 +1250,8 @@ __device__ __noinline__ void trellis(const Ctx S, const DevTables *__restrict__ 
 // Dependent quantisation of ONE 8x8 TB (128 of the 165 TBs >= 8x8 of a CTU).  Same arithmetic as trellis(), organised the
 // other way round: instead of cutting the TB into chunks and paying for the (min,+) matrices, the chunk-by-chunk pass and the
 // replay, the backward Viterbi pass runs as one sequential chain with one trellis STATE per lane (lanes 0-3) over local costs
-// that all 32 lanes tabulated beforehand (one 16-byte row per position: candidate a0 / a1 for delta 0 / 1).  A chain step
-// is two shuffles (the two predecessor states), one 8-byte table read and ~10 integer instructions; the whole routine is
+// that all 32 lanes tabulated beforehand (one 32-byte row per position: the costs of candidate a0 / a1 as each of the four
+// states sees them).  A chain step is two shuffles (the two predecessor states), one 8-byte table read and ~8 integer instructions; the whole routine is
 // about a third of trellis() in code and in executed instructions.
 //   coef: coefficients (raster); Wd: 64 x / non-zero words; lc: 1 kB cost table (may overlap lev: it is dead before the walk)
 //   lev (out): levels (raster).  Cost bound: see trellis(); the chain is renormalised at every sub-block start.
@@ -1283,16 +1283,16 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
     unsigned p1l, p2l, p1h, p2h;
     {
         const LC ll = local_costs(S, tab, tcl, wl, lane, kstar, ls, sh, off, ldq1);
-        lc[lane] = make_int4(ll.L00, ll.L10, ll.L01, ll.L11);
+        lc[2 * lane] = make_int4(ll.L0s0, ll.L10, ll.L00, ll.L10);  // two 16-byte halves per position: (a0, a1) costs as seen by states 0 | 1 and 2 | 3
+        lc[2 * lane + 1] = make_int4(ll.L01, ll.L11, ll.L01, ll.L11);
         p1l = __ballot_sync(0xffffffffu, ll.pk & 1u); p2l = __ballot_sync(0xffffffffu, ll.pk & 2u);
     }
     {
         const LC lh = local_costs(S, tab, tch, wh, lane + 32, kstar, ls, sh, off, ldq1);
-        lc[lane + 32] = make_int4(lh.L00, lh.L10, lh.L01, lh.L11);
+        lc[2 * (lane + 32)] = make_int4(lh.L0s0, lh.L10, lh.L00, lh.L10);
+        lc[2 * (lane + 32) + 1] = make_int4(lh.L01, lh.L11, lh.L01, lh.L11);
         p1h = __ballot_sync(0xffffffffu, lh.pk & 1u); p2h = __ballot_sync(0xffffffffu, lh.pk & 2u);
     }
-    // state 0 sees candidate a0 = 0 of a flagged position without its rate (LC::L0s0 = L00 - ldq[1])
-    const unsigned mzl = __ballot_sync(0xffffffffu, lane > kstar && (xl >> 1) == 0), mzh = __ballot_sync(0xffffffffu, lane + 32 > kstar && (xh >> 1) == 0);
     const int tc0 = __shfl_sync(0xffffffffu, tcl, 0);
     const unsigned x0 = __shfl_sync(0xffffffffu, xl, 0);
     __syncwarp();
@@ -1302,9 +1302,8 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
         const int s = lane;
         const unsigned inv = (s & 1) ? 0xffffffffu : 0u;
         const unsigned msw_lo = (s < 2 ? p1l : p2l) ^ inv, msw_hi = (s < 2 ? p1h : p2h) ^ inv;
-        const unsigned fix_lo = s == 0 ? mzl : 0u, fix_hi = s == 0 ? mzh : 0u;
         const unsigned adj = s == 0 ? ((unsigned)(16 > kstar) | ((unsigned)(32 > kstar) << 1) | ((unsigned)(48 > kstar) << 2)) : 0u;  // quantizer.rs:512-514 at k = 16, 32, 48
-        const char *lp = reinterpret_cast<const char *>(lc) + (s >> 1) * 8;
+        const char *lp = reinterpret_cast<const char *>(lc) + s * 8;  // this state's (a0, a1) pair inside a position's 32-byte row
         int C;
         {   // DC leaf (quantizer.rs:367-409) for this lane's state
             const bool itz = (s == 0) && (kstar < 0);
@@ -1336,9 +1335,9 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
         const int srcP = s >> 1, srcQ = srcP + 2;
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
-            const unsigned msw = h ? msw_hi : msw_lo, fix = h ? fix_hi : fix_lo;
+            const unsigned msw = h ? msw_hi : msw_lo;
             unsigned dec = 0;
-            const char *lph = lp + h * 512;
+            const char *lph = lp + h * 1024;
 #pragma unroll 1
             for (int q4 = 0; q4 < 2; q4++) {  // one sub-block of 16 positions per iteration
                 const int jb = q4 * 16;
@@ -1347,11 +1346,10 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
                     int mn = min(C, __shfl_xor_sync(0xFu, C, 1));
                     mn = min(mn, __shfl_xor_sync(0xFu, mn, 2));
                     C -= mn;
-                    const int2 L = *reinterpret_cast<const int2 *>(lph + jb * 16);
+                    const int2 L = *reinterpret_cast<const int2 *>(lph + jb * 32);
                     const int P = __shfl_sync(0xFu, C, srcP), Q = __shfl_sync(0xFu, C, srcQ);
                     const bool sw = (msw >> jb) & 1u;
-                    const int La = L.x - (((fix >> jb) & 1u) ? ldq1 : 0);
-                    const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
+                    const int c0 = L.x + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
                     const bool d = c1 < c0;  // ties keep a0 (quantizer.rs:505)
                     C = d ? c1 : c0;
                     if (((adj >> (2 * h + q4 - 1)) & 1u) && !d) C -= ldq1;
@@ -1359,11 +1357,10 @@ __device__ __noinline__ void trellis8_chain(const Ctx S, const DevTables *__rest
                 }
 #pragma unroll U8C
                 for (int j = j0; j < jb + 16; j++) {
-                    const int2 L = *reinterpret_cast<const int2 *>(lph + j * 16);
+                    const int2 L = *reinterpret_cast<const int2 *>(lph + j * 32);
                     const int P = __shfl_sync(0xFu, C, srcP), Q = __shfl_sync(0xFu, C, srcQ);
                     const bool sw = (msw >> j) & 1u;
-                    const int La = L.x - (((fix >> j) & 1u) ? ldq1 : 0);
-                    const int c0 = La + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
+                    const int c0 = L.x + (sw ? Q : P), c1 = L.y + (sw ? P : Q);
                     const bool d = c1 < c0;
                     C = d ? c1 : c0;
                     dec |= (unsigned)d << j;
