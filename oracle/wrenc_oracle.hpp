@@ -132,5 +132,8 @@ struct Encoder {
 
 // CABAC-coded slice_data() of a searched picture (phase 2; wrenc_oracle_cabac.cpp)
 std::vector<uint8_t> code_slice_data(const Consts &k, Picture &p);
+// test hooks (wrenc_oracle_cabac.cpp): bin string in the product's entry format; the reference engine over any bin string
+std::vector<uint8_t> code_slice_data_traced(const Consts &k, Picture &p, std::vector<uint16_t> &bins);
+std::vector<uint8_t> code_bin_string(int slice_qp, const uint16_t *entries, size_t n);
 
 }  // namespace wo

@@ -26,6 +26,7 @@ struct BoolCoder {
     unsigned range = 510, offset = 0;
     int outstanding = 0;
     bool first_bit = true;
+    std::vector<uint16_t> *trace = nullptr;  // test hook: the bin string in the product's entry format (ctx | bin << 9 | bypass << 10)
 
     void init(int slice_qp) {  // bool_coder.rs:1073-1111
         for (int i = 0; i < CTX_TOTAL; i++) {
@@ -70,6 +71,7 @@ struct BoolCoder {
         }
     }
     void bypass(bool b) {  // :202-216
+        if (trace) trace->push_back((uint16_t)(((unsigned)b << 9) | (1u << 10)));
         offset <<= 1;
         if (b) offset += range;
         if (offset >= 1024) {
@@ -82,6 +84,7 @@ struct BoolCoder {
         }
     }
     void decision(int ctx, bool b) {  // :254-296 + :136-154
+        if (trace) trace->push_back((uint16_t)((unsigned)ctx | ((unsigned)b << 9)));
         unsigned q_range_idx = range >> 5;
         unsigned p_state = p[ctx][1] + 16u * p[ctx][0];
         unsigned val_mps = p_state >> 14;
@@ -476,22 +479,47 @@ struct SliceWriter {
         for (int i = 0; i < 4; i++) encode_coding_tree(px + (i % 2) * (size / 2), py + (i / 2) * (size / 2), size / 2);
     }
 
-    std::vector<uint8_t> run() {
-        c.init(K.qp);  // first CTU of the picture: ctu_encoder.rs:38-47
-        for (int cy = 0; cy < P.H; cy += 32)
-            for (int cx = 0; cx < P.W; cx += 32) {
-                is_cu_qp_delta_coded = false;  // quantisation group = CTU (ctu_encoder.rs:305-310)
-                encode_coding_tree(cx, cy, 32);
-            }
+    static std::vector<uint8_t> finish(BoolCoder &c) {
         c.stop_one_bit();  // end_of_slice_one_bit (slice_encoder.rs:380-388)
         std::vector<uint8_t> out((c.bits.size() + 7) / 8, 0);  // bins.byte_align(): zero padding (slice_encoder.rs:419)
         for (size_t i = 0; i < c.bits.size(); i++)
             if (c.bits[i]) out[i / 8] |= (uint8_t)(0x80u >> (i % 8));
         return out;
     }
+
+    std::vector<uint8_t> run(std::vector<uint16_t> *trace = nullptr) {
+        c.trace = trace;
+        c.init(K.qp);  // first CTU of the picture: ctu_encoder.rs:38-47
+        for (int cy = 0; cy < P.H; cy += 32)
+            for (int cx = 0; cx < P.W; cx += 32) {
+                is_cu_qp_delta_coded = false;  // quantisation group = CTU (ctu_encoder.rs:305-310)
+                encode_coding_tree(cx, cy, 32);
+            }
+        c.trace = nullptr;
+        return finish(c);
+    }
 };
 
 }  // namespace
+
+// Test hooks for the product's arithmetic coder (wrenc_b200/csrc/cabac_engine.cuh): the bin string of a searched picture in
+// the product's 16-bit entry format, and the reference engine run over an arbitrary bin string (+ end_of_slice_one_bit and
+// byte alignment, as SliceWriter::run does).
+std::vector<uint8_t> code_slice_data_traced(const Consts &k, Picture &p, std::vector<uint16_t> &bins) {
+    SliceWriter w(k, p);
+    bins.clear();
+    return w.run(&bins);
+}
+std::vector<uint8_t> code_bin_string(int slice_qp, const uint16_t *entries, size_t n) {
+    BoolCoder c;
+    c.init(slice_qp);
+    for (size_t i = 0; i < n; i++) {
+        const unsigned e = entries[i];
+        if (e & 1024u) c.bypass(((e >> 9) & 1) != 0);
+        else c.decision((int)(e & 511u), ((e >> 9) & 1) != 0);
+    }
+    return SliceWriter::finish(c);
+}
 
 std::vector<uint8_t> code_slice_data(const Consts &k, Picture &p) {
     SliceWriter w(k, p);

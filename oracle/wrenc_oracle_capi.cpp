@@ -1,4 +1,5 @@
 // C API over the CPU ORACLE for ctypes (tests/, smoke(), bench.py cpu_baseline only — NOT product code).
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -92,4 +93,18 @@ void wo_inv_dct(const int16_t *deq, int log2n, int16_t *out) { inv_dct(deq, log2
 void wo_quantize(wo_handle *h, const int16_t *coef, int log2n, int16_t *q) { quantize_dq(h->enc.k, coef, log2n, q); }
 void wo_dequantize(wo_handle *h, const int16_t *q, int log2n, int16_t *d) { dequantize(h->enc.k, q, log2n, d); }
 int64_t wo_rate(wo_handle *h, const int16_t *q, int log2n) { return rate_levels(h->enc.k, q, log2n); }
+}
+
+// ---- test hook: the bin string of a picture in the product's entry format (tests of the product's arithmetic coder) ----
+extern "C" long wo_trace_bins(wo_handle *h, int W, int H, const uint8_t *y, const uint8_t *cb, const uint8_t *cr, uint16_t *bins, size_t cap,
+                              uint8_t *slice_data, size_t sd_cap, long *sd_len) {
+    Picture p;
+    p.init(W, H, y, cb, cr);
+    h->enc.search_picture(p);
+    std::vector<uint16_t> b;
+    std::vector<uint8_t> sd = code_slice_data_traced(h->enc.k, p, b);
+    if (sd_len) *sd_len = (long)sd.size();
+    if (slice_data && sd.size() <= sd_cap) memcpy(slice_data, sd.data(), sd.size());
+    if (bins) memcpy(bins, b.data(), std::min(cap, b.size()) * sizeof(uint16_t));
+    return (long)b.size();
 }

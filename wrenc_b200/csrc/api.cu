@@ -35,6 +35,7 @@ struct Workspace {
     int coder_pics = 0;
     uint16_t *d_bins = nullptr;
     size_t bins_cap = 0;
+    NzMap *d_nzmap = nullptr;     // per-CTU map of the non-zero 4x4 level blocks
     uint16_t *d_stage = nullptr;  // per-CTU staging slots of the bin strings (stage_cap() entries each)
     int *d_bin_count = nullptr;
     unsigned long long *d_bin_offset = nullptr, *d_bin_total = nullptr;
@@ -100,7 +101,7 @@ struct wrenc_b200 {
 
 static void free_workspace(Workspace &w) {
     cudaFree(w.d_mode_map); cudaFree(w.d_done); cudaFree(w.d_counter);
-    cudaFree(w.d_bins); cudaFree(w.d_stage); cudaFree(w.d_bin_count); cudaFree(w.d_bin_offset); cudaFree(w.d_bin_total);
+    cudaFree(w.d_bins); cudaFree(w.d_stage); cudaFree(w.d_nzmap); cudaFree(w.d_bin_count); cudaFree(w.d_bin_offset); cudaFree(w.d_bin_total);
     w = Workspace();
 }
 
@@ -222,11 +223,12 @@ static int ensure_coder(wrenc_b200 *h, Workspace &w, int n_pics) {
     if (n_pics <= w.coder_pics) return 0;
     CK(cudaSetDevice(h->cfg.device));
     CK(cudaDeviceSynchronize());
-    cudaFree(w.d_bin_count); cudaFree(w.d_bin_offset); cudaFree(w.d_stage);
-    w.d_bin_count = nullptr; w.d_bin_offset = nullptr; w.d_stage = nullptr;
+    cudaFree(w.d_bin_count); cudaFree(w.d_bin_offset); cudaFree(w.d_stage); cudaFree(w.d_nzmap);
+    w.d_bin_count = nullptr; w.d_bin_offset = nullptr; w.d_stage = nullptr; w.d_nzmap = nullptr;
     const size_t nctu = (size_t)h->Wc * h->Hc * n_pics;
     CK(cudaMalloc(&w.d_bin_count, nctu * sizeof(int)));
     CK(cudaMalloc(&w.d_stage, nctu * stage_cap() * sizeof(uint16_t)));
+    CK(cudaMalloc(&w.d_nzmap, nctu * sizeof(NzMap)));
     CK(cudaMalloc(&w.d_bin_offset, nctu * sizeof(unsigned long long)));
     if (!w.d_bin_total) CK(cudaMalloc(&w.d_bin_total, sizeof(unsigned long long)));
     if (w.bins_cap < nctu * arena_entries_per_ctu()) {  // first guess; grown from the measured totals (grow_arena)
@@ -260,14 +262,14 @@ static int enqueue_coder(wrenc_b200 *h, Workspace &w, int n_pics, const int16_t 
     if (rc) return rc;
     SyntaxParams Q;
     Q.W = h->W; Q.H = h->H; Q.Wc = h->Wc; Q.Hc = h->Hc; Q.n_pics = n_pics; Q.qp = h->cfg.qp;
-    Q.lev = d_lev; Q.records = d_records; Q.mode_map = w.d_mode_map;
+    Q.lev = d_lev; Q.records = d_records; Q.mode_map = w.d_mode_map; Q.nzmap = w.d_nzmap;
     Q.bins = nullptr; Q.bins_cap = w.bins_cap; Q.bin_count = w.d_bin_count; Q.bin_offset = w.d_bin_offset;
     Q.stage = w.d_stage; Q.stage_cap = stage_cap();
     Q.out = d_out; Q.out_cap = out_cap; Q.out_len = d_out_len;
     if (first_pass) {
         CK(launch_syntax(Q, st));
         CK(launch_bin_scan(Q, w.d_bin_total, st));
-        h->launches += 2;
+        h->launches += 1 + syntax_first_pass_kernels();
     }
     Q.bins = w.d_bins;
     CK(launch_syntax(Q, st));       // only the CTUs that did not fit their staging slot

@@ -1,0 +1,218 @@
+// cabac_engine.cuh — the arithmetic coder of the slice coder (bool_coder.rs:136-296), restated for a latency-bound device loop
+// and written so that it compiles for the device (wrenc_b200_cabac_kernel) and for the host (tests/host/cabac_engine_host_test.cpp
+// runs it against the oracle's bit-by-bit engine on random and real bin strings without a GPU).
+//
+// The reference keeps a 10-bit `offset`, emits one bit per renormalisation step and counts outstanding bits (put-bit form).  The
+// coded string depends only on the sequence of interval updates, so the same bytes come out of the register form used here:
+//   * `low` is a 32-bit window of the code value, `bits_left` counts the free bits below its top; a renormalisation is ONE shift by
+//     n = clz(range) - 23 bits (no loop), and whole bytes leave the window in write_out() when fewer than 12 bits are free;
+//   * a carry out of the window is resolved against one buffered byte and a count of 0xff bytes behind it (write_out / finish);
+//   * a run of up to 8 bypass bins is one update  low = (low << k) + range * value  (k single steps are exactly that);
+//   * the probability pair of a context and its two adaptation shifts are ONE 32-bit word
+//         q0 (10 bits) | q1 (14 bits) << 10 | shift0 << 24 | shift1 << 28        (bool_coder.rs:136-154, 1073-1093)
+//     so that a context-coded bin costs one load and one store.
+// The dropped first bit of the reference (flush_cabac_bin) is the top bit of its 10-bit offset, which is always 0: the register form
+// starts with 9 bits in the window (bits_left = 23) and never holds it.  end_of_slice_one_bit, the two trailing bits with the
+// forced stop bit and the zero padding (bool_coder.rs:218-235, slice_encoder.rs:419) are finish().
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CE_HD __host__ __device__ __forceinline__
+#else
+#define CE_HD inline
+#endif
+
+namespace ce {
+
+#if defined(__CUDA_ARCH__)
+CE_HD int clz32(unsigned v) { return __clz((int)v); }
+CE_HD int ffs32(unsigned v) { return __ffs((int)v); }
+CE_HD unsigned brev32(unsigned v) { return __brev(v); }
+#else
+CE_HD int clz32(unsigned v) { return v ? __builtin_clz(v) : 32; }
+CE_HD int ffs32(unsigned v) { return __builtin_ffs((int)v); }
+CE_HD unsigned brev32(unsigned v) {
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
+    return r;
+}
+#endif
+
+// context word: init_ctx_table (bool_coder.rs:1073-1093)
+CE_HD unsigned ctx_init_word(int init_value, int shift_idx, int slice_qp) {
+    const int m = (init_value >> 3) - 4, nn = (init_value & 7) * 18 + 1;
+    const int qp = slice_qp < 0 ? 0 : (slice_qp > 63 ? 63 : slice_qp);
+    int pre = ((m * (qp - 16)) >> 1) + nn;
+    pre = pre < 1 ? 1 : (pre > 127 ? 127 : pre);
+    const unsigned s0 = (unsigned)((shift_idx >> 2) + 2), s1 = (unsigned)((shift_idx & 3) + 3) + s0;
+    return (unsigned)(pre << 3) | ((unsigned)(pre << 7) << 10) | (s0 << 24) | (s1 << 28);
+}
+
+// probability token of a bin coded with context word w: qlps | is_mps << 5
+CE_HD unsigned ctx_token(unsigned w, unsigned bin) {
+    const unsigned ps = ((w >> 10) & 16383u) + 16u * (w & 1023u);
+    const unsigned mps = ps >> 14;
+    return ((mps ? 32767u - ps : ps) >> 9) | (bin == mps ? 32u : 0u);
+}
+// the context word after coding `bin` (bool_coder.rs:136-154: two estimators with their own adaptation shifts)
+CE_HD unsigned adapt(unsigned w, unsigned bin) {
+    const unsigned q0 = w & 1023u, q1 = (w >> 10) & 16383u, s0 = (w >> 24) & 7u, s1 = w >> 28;
+    const unsigned n0 = q0 - (q0 >> s0) + (bin ? 1023u >> s0 : 0u);
+    const unsigned n1 = q1 - (q1 >> s1) + (bin ? 16383u >> s1 : 0u);
+    return (w & 0xff000000u) | n0 | (n1 << 10);
+}
+
+struct Arith {
+    unsigned low, range, buf_byte;
+    int bits_left, n_buf;
+    uint8_t *p;  // nullptr: count only
+    size_t n, cap;
+
+    CE_HD void init(uint8_t *out, size_t out_cap) {
+        low = 0; range = 510; buf_byte = 0xff; bits_left = 23; n_buf = 0;
+        p = out; n = 0; cap = out_cap;
+    }
+    CE_HD void emit(unsigned b) {
+        if (p && n < cap) p[n] = (uint8_t)b;
+        n++;
+    }
+    // the top byte of the window leaves it; a carry (bit 8 of lead) goes into the buffered byte and the 0xff run behind it
+    CE_HD void write_out() {
+        const unsigned lead = low >> (24 - bits_left);
+        bits_left += 8;
+        low &= 0xffffffffu >> bits_left;
+        if (lead == 0xffu) n_buf++;
+        else if (n_buf > 0) {
+            const unsigned carry = lead >> 8;
+            emit(buf_byte + carry);
+            buf_byte = lead & 0xffu;
+            const unsigned fill = (0xffu + carry) & 0xffu;
+#pragma unroll 1
+            while (n_buf > 1) { emit(fill); n_buf--; }
+        } else {
+            n_buf = 1;
+            buf_byte = lead;
+        }
+    }
+    // interval update of a context-coded bin (bool_coder.rs:254-296) from the bin's probability token: the LPS probability index
+    // qlps = (p < 0.5 ? p : 1 - p) >> 9 of the context word before the bin, and whether the bin is the more probable symbol
+    CE_HD void decision_tok(unsigned qlps, bool is_mps) {
+        const unsigned lps = (((range >> 5) * qlps) >> 1) + 4u;
+        const unsigned rmps = range - lps;
+        const unsigned r = is_mps ? rmps : lps;
+        const unsigned add = is_mps ? 0u : rmps;
+        const int nsh = clz32(r) - 23;  // r < 512; the MPS interval is at least 128 wide, the LPS interval at least 4
+        low = (low + add) << nsh;
+        range = r << nsh;
+        bits_left -= nsh;
+        if (bits_left < 12) write_out();
+    }
+    // context-coded bin; returns the adapted context word
+    CE_HD unsigned decision(unsigned w, unsigned bin) {
+        const unsigned t = ctx_token(w, bin);
+        decision_tok(t & 31u, (t & 32u) != 0u);
+        return adapt(w, bin);
+    }
+    // k <= 8 bypass bins, first bin in the most significant bit of v (bool_coder.rs:202-216, k times)
+    CE_HD void bypass(unsigned v, int k) {
+        low = (low << k) + range * v;
+        bits_left -= k;
+        if (bits_left < 12) write_out();
+    }
+    // end_of_slice_one_bit = 1, flush, stop bit, zero padding to the byte boundary; returns the byte count
+    CE_HD size_t finish() {
+        range -= 2;
+        low = (low + range) << 7;
+        range = 2u << 7;
+        bits_left -= 7;
+        if (bits_left < 12) write_out();
+        if (low >> (32 - bits_left)) {
+            emit(buf_byte + 1);
+#pragma unroll 1
+            while (n_buf > 1) { emit(0x00u); n_buf--; }
+            low -= 1u << (32 - bits_left);
+        } else {
+            if (n_buf > 0) emit(buf_byte);
+#pragma unroll 1
+            while (n_buf > 1) { emit(0xffu); n_buf--; }
+        }
+        int k = 24 - bits_left;                         // bits of the code value still in the window (above bit 8)
+        unsigned v = ((low >> 8) << 1) | 1u;            // + the stop bit the reference forces into its last trailing bit
+        k += 1;
+        const int pad = (8 - (k & 7)) & 7;
+        v <<= pad;
+        k += pad;
+#pragma unroll 1
+        for (int sh = k - 8; sh >= 0; sh -= 8) emit((v >> sh) & 0xffu);
+        return n;
+    }
+};
+
+// One batch of up to 32 bin-string entries (16 bits each: context index | bin << 9 | bypass << 10), given as two masks over the
+// batch (bypass flags, bin values; bits at and above cnt are 0) and an environment that hands out the context index of entry i
+// and loads / stores context words.  The state of the next context-coded bin is fetched before the current bin is coded (and
+// replaced by the adapted word when it is the same context), so that its latency is off the dependent chain.
+template <class Env>
+CE_HD void code_batch(Arith &E, Env &env, unsigned bypm, unsigned binm, int cnt) {
+    const unsigned valid = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    const unsigned ctxm = ~bypm & valid;
+    int i = 0;
+    bool have = false;
+    unsigned nci = 0, nw = 0;
+    while (i < cnt) {
+        if ((bypm >> i) & 1u) {
+            const unsigned run = ~(bypm >> i);
+            int k = run ? ffs32(run) - 1 : 32;
+            k = k > 8 ? 8 : k;
+            const unsigned v = brev32(binm >> i) >> (32 - k);
+            E.bypass(v, k);
+            i += k;
+            continue;
+        }
+        unsigned ci, w;
+        if (have) { ci = nci; w = nw; }
+        else { ci = env.ci(i); w = env.load(ci); }
+        const unsigned rest = (ctxm >> i) >> 1;
+        have = rest != 0u;
+        if (have) {
+            nci = env.ci(i + ffs32(rest));
+            nw = env.load(nci);
+        }
+        const unsigned neww = E.decision(w, (binm >> i) & 1u);
+        env.store(ci, neww);
+        if (have && nci == ci) nw = neww;
+        i++;
+    }
+}
+
+// ---- the same batch as a token program (wrenc_b200_cabac_kernel): every entry of the batch is turned into one word by its own
+// lane, in parallel, and the sequential part only walks the words:
+//     context-coded entry  qlps | is_mps << 5 |                              next << 19     (next = own position + 1)
+//     bypass entry         64 | k << 7 | value << 11 |                       next << 19     (the run of up to 8 bypass bins that
+//                                                                                            starts at this entry; next = position + k)
+enum { TOK_BYPASS = 64u };
+CE_HD unsigned token_ctx(unsigned w, unsigned bin, int pos) { return ctx_token(w, bin) | ((unsigned)(pos + 1) << 19); }
+CE_HD unsigned token_bypass(unsigned bypm, unsigned binm, int pos) {  // bit pos of bypm is set
+    const unsigned run = ~(bypm >> pos);
+    int k = run ? ffs32(run) - 1 : 32;
+    k = k > 8 ? 8 : k;
+    const unsigned v = brev32(binm >> pos) >> (32 - k);
+    return (unsigned)TOK_BYPASS | ((unsigned)k << 7) | (v << 11) | ((unsigned)(pos + k) << 19);
+}
+// get(i): the word of entry i (i < 32).  The word of the next entry is fetched before the current one is coded.
+template <class Get>
+CE_HD void run_tokens(Arith &E, Get get, int cnt) {
+    int i = 0;
+    unsigned t = get(0);
+    while (i < cnt) {
+        const int ni = (int)(t >> 19);
+        const unsigned tn = get(ni & 31);
+        if (t & TOK_BYPASS) E.bypass((t >> 11) & 255u, (int)((t >> 7) & 15u));
+        else E.decision_tok(t & 31u, (t & 32u) != 0u);
+        t = tn;
+        i = ni;
+    }
+}
+
+}  // namespace ce

@@ -42,11 +42,17 @@ static_assert(CTU_SCRATCH_BYTES % 16 == 0 && ROOT_SLOT_BYTES % 16 == 0 && SAVE_S
 enum { SINGLE_TREE = 0, DUAL_TREE_LUMA = 1, DUAL_TREE_CHROMA = 2 };
 enum { MODE_PLANAR = 0, MODE_DC = 1, MODE_LT_CCLM = 81, MODE_L_CCLM = 82, MODE_T_CCLM = 83 };
 
+struct NzMap {  // per CTU: which 4x4 blocks of the level planes hold a non-zero level (luma bit by * 8 + bx, chroma bit by * 4 + bx)
+    unsigned long long y;
+    unsigned short cb, cr;
+    unsigned int pad;
+};
 struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_data() per picture
     int W, H, Wc, Hc, n_pics, qp;
     const int16_t *lev;        // [pic][W*H*3/2]
     const CtuRecord *records;  // [pic][Wc*Hc]
     const uint8_t *mode_map;   // [pic][(W/4)*(H/4)]
+    NzMap *nzmap;              // [pic][ctu] written by the counting pass's first kernel, read by both syntax passes
     uint16_t *bins;            // bin arena (entries: ctx index | bin << 9 | bypass << 10); nullptr = counting + staging pass
     unsigned long long bins_cap;  // entries the arena holds: strings that would end beyond it are not written and their picture reports
                                //   out_len = -2, so that the host can grow the arena and run the passes again WITHOUT a mid-path sync
@@ -58,7 +64,8 @@ struct SyntaxParams {  // slice_coder.cu: decided trees -> CABAC-coded slice_dat
     size_t out_cap;
     int *out_len;              // [pic] bytes written, -1 on overflow
 };
-cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream);
+cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream);  // Q.bins == nullptr: non-zero map + counting pass
+int syntax_first_pass_kernels();  // kernels launch_syntax enqueues for the counting pass
 cudaError_t launch_bin_scan(const SyntaxParams &Q, unsigned long long *d_total, cudaStream_t stream);
 cudaError_t launch_bin_compact(const SyntaxParams &Q, cudaStream_t stream);
 cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream);

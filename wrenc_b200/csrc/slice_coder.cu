@@ -13,9 +13,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef WB_NZMAP
+#define WB_NZMAP 1  // 1: the syntax walk reads a per-CTU map of non-zero 4x4 level blocks instead of scanning the level planes
+#endif
 #define WB_CABAC_TABLE static __constant__ const
 #include "cabac_tables.h"
 #include "search_kernel_api.h"
+#include "cabac_engine.cuh"
 
 namespace wb {
 
@@ -86,7 +90,9 @@ struct TuState {
 };
 
 // residual_coding() of one transform block (ctu_encoder.rs:1786-2269), regular (non transform-skip) path with dep-quant
-__device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int stride, int c_idx, int l2, TuState &ts, uint16_t *pass1, uint16_t *absl) {
+// (nzm, rs, b0): the CTU's map of non-zero 4x4 blocks of this component, its row stride in bits and the bit of the TB's first block
+__device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int stride, int c_idx, int l2, TuState &ts, uint8_t *pass1, uint8_t *absl,
+                              unsigned long long nzm, int rs, int b0) {
     const int n = 1 << l2, nn = n * n, nsbw = n >> 2;
     const uint8_t *sbo = SO.o + sb_off(l2);
     auto pos_of = [&](int k, int &x, int &y) {
@@ -94,12 +100,28 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
         x = ((sbo[sb] & 15) << 2) + (c_diag4[p] & 3);
         y = ((sbo[sb] >> 4) << 2) + (c_diag4[p] >> 2);
     };
+#if WB_NZMAP
+    auto sb_nonzero = [&](int xs, int ys) { return ((nzm >> (b0 + ys * rs + xs)) & 1ull) != 0ull; };
+#else
+    auto sb_nonzero = [&](int xs, int ys) {
+        for (int yy = 0; yy < 4; yy++)
+            for (int xx = 0; xx < 4; xx++)
+                if (q[((ys << 2) + yy) * stride + (xs << 2) + xx] != 0) return true;
+        return false;
+    };
+#endif
     // last significant coefficient in coding order (ctu.rs:867-899)
     int last_k = 0, lx = 0, ly = 0;
-    for (int k = nn - 1; k >= 0; k--) {
-        int x, y;
-        pos_of(k, x, y);
-        if (q[y * stride + x] != 0 || k == 0) { last_k = k; lx = x; ly = y; break; }
+    {
+        int k = nn - 1;
+#if WB_NZMAP
+        while (k > 15 && !sb_nonzero(sbo[k >> 4] & 15, sbo[k >> 4] >> 4)) k -= 16;  // whole sub-blocks without a level: the map, not 16 loads
+#endif
+        for (; k >= 0; k--) {
+            int x, y;
+            pos_of(k, x, y);
+            if (q[y * stride + x] != 0 || k == 0) { last_k = k; lx = x; ly = y; break; }
+        }
     }
     // last_sig_coeff_{x,y}_{prefix,suffix} (ctu_encoder.rs:1818-1849, bool_coder.rs:2053-2083)
     int pre[2], suf[2], sbits[2];
@@ -128,15 +150,10 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
     int rem = (nn * 7) >> 2;
     const int last_sb = last_k >> 4, last_pos = last_k & 15;
     if ((last_sb > 0 || last_pos > 0) && c_idx == 0) ts.mts_dc_only = false;
-    for (int y = 0; y < n; y++)
-        for (int x = 0; x < n; x++) { pass1[y * n + x] = 0; absl[y * n + x] = 0; }
-    auto sb_nonzero = [&](int xs, int ys) {
-        for (int yy = 0; yy < 4; yy++)
-            for (int xx = 0; xx < 4; xx++)
-                if (q[((ys << 2) + yy) * stride + (xs << 2) + xx] != 0) return true;
-        return false;
-    };
-    auto loc_sums = [&](const uint16_t *a, int x, int y, int &num) {
+    // per-position history of this TB, one byte each (thread-local): pass1 <= 5; absolute levels saturate at 255, which leaves every
+    // use exact (they only enter the five-neighbour sums that select a Rice parameter, and those saturate at 31 resp. 51)
+    for (int i = 0; i < nn / 4; i++) { reinterpret_cast<uint32_t *>(pass1)[i] = 0u; reinterpret_cast<uint32_t *>(absl)[i] = 0u; }
+    auto loc_sums = [&](const uint8_t *a, int x, int y, int &num) {
         int sum = 0; num = 0;
         if (x < n - 1) {
             int v = a[y * n + x + 1]; sum += v; num += v > 0;
@@ -175,6 +192,17 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
     int qstate = 0;
     for (int i = last_sb; i >= 0; i--) {
         const int xs = sbo[i] & 15, ys = sbo[i] >> 4;
+#if WB_NZMAP
+        if (i < last_sb && i > 0 && !sb_nonzero(xs, ys)) {
+            // a sub-block without levels codes its sb_coded_flag and nothing else: every absolute level is 0 whatever the
+            // quantiser state, pass1 / absl stay 0, and 16 transitions with parity 0 take the state back to where it was
+            int csbf = 0;
+            if (xs < nsbw - 1) csbf += sb_nonzero(xs + 1, ys);
+            if (ys < nsbw - 1) csbf += sb_nonzero(xs, ys + 1);
+            S.ctx(CTX_SB_CODED + (c_idx == 0 ? min(csbf, 1) : 2 + min(csbf, 1)), 0);
+            continue;
+        }
+#endif
         int a[16];
         {
             int st = qstate;
@@ -233,7 +261,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
                 }
             }
             const int p1 = (int)sig + (int)par + (int)gt1 + 2 * (int)gt3;
-            pass1[y * n + x] = (uint16_t)p1;
+            pass1[y * n + x] = (uint8_t)p1;
             qstate = tr_state(qstate, p1);
             fp1 = p - 1;
         }
@@ -245,11 +273,11 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
                 const int rice = c_rice[min(31, max(0, sum - 20))];
                 code_rem((a[p] - pass1[y * n + x]) >> 1, rice);
             }
-            absl[y * n + x] = (uint16_t)a[p];
+            absl[y * n + x] = (uint8_t)min(a[p], 255);
         }
         for (int p = fp1; p >= 0; p--) {  // dec_abs_level of the rest
             const int x = (xs << 2) + (c_diag4[p] & 3), y = (ys << 2) + (c_diag4[p] >> 2);
-            absl[y * n + x] = (uint16_t)a[p];
+            absl[y * n + x] = (uint8_t)min(a[p], 255);
             if (sbcoded) {
                 int num;
                 const int sum = loc_sums(absl, x, y, num);
@@ -321,8 +349,8 @@ __device__ void code_luma_mode(Sink &S, const PicView &P, int px, int py, int si
 }
 
 // coding_unit() + transform_unit() of one CU (ctu_encoder.rs:440-1321, 1414-1784); (x, y) CTU-relative luma position
-__device__ void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, int ctu_x, int ctu_y, int x, int y, int size, int tree, TuState &ts,
-                        uint16_t *pass1, uint16_t *absl) {
+__device__ void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, const NzMap &nz, int ctu_x, int ctu_y, int x, int y, int size, int tree,
+                        TuState &ts, uint8_t *pass1, uint8_t *absl) {
     const int px = ctu_x + x, py = ctu_y + y;
     if (tree != DUAL_TREE_CHROMA) code_luma_mode(S, P, px, py, size, rec.luma_mode[(y >> 2) * 8 + (x >> 2)]);
     if (tree != DUAL_TREE_LUMA) {
@@ -343,9 +371,21 @@ __device__ void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuR
     const int16_t *qy = P.lev[0] + (size_t)py * P.W + px;
     const int16_t *qcb = P.lev[1] + (size_t)(py >> 1) * cw + (px >> 1), *qcr = P.lev[2] + (size_t)(py >> 1) * cw + (px >> 1);
     const int l2 = 31 - __clz(size);
+    const int by0 = (y >> 2) * 8 + (x >> 2), bc0 = (y >> 3) * 4 + (x >> 3);  // first 4x4 block of the CU in the luma / chroma maps
+#if WB_NZMAP
+    const int nb = size >> 2, nbc = max(1, size >> 3);  // 4x4 blocks per CU row, luma / chroma
+    unsigned long long my = 0ull;
+    unsigned mc = 0u;
+    for (int r = 0; r < nb; r++) my |= ((1ull << nb) - 1ull) << (by0 + r * 8);
+    for (int r = 0; r < nbc; r++) mc |= ((1u << nbc) - 1u) << (bc0 + r * 4);
+    const bool ycbf = tree != DUAL_TREE_CHROMA && (nz.y & my) != 0ull;
+    const bool cbcbf = tree != DUAL_TREE_LUMA && ((unsigned)nz.cb & mc) != 0u;
+    const bool crcbf = tree != DUAL_TREE_LUMA && ((unsigned)nz.cr & mc) != 0u;
+#else
     const bool ycbf = tree != DUAL_TREE_CHROMA && block_nonzero(qy, P.W, size);
     const bool cbcbf = tree != DUAL_TREE_LUMA && block_nonzero(qcb, cw, size >> 1);
     const bool crcbf = tree != DUAL_TREE_LUMA && block_nonzero(qcr, cw, size >> 1);
+#endif
     if (tree != DUAL_TREE_LUMA) {
         S.ctx(CTX_TU_CB, cbcbf);
         S.ctx(CTX_TU_CR + (cbcbf ? 1 : 0), crcbf);
@@ -357,15 +397,15 @@ __device__ void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuR
     }
     if (ycbf) {
         S.ctx(CTX_TS_FLAG, 0);
-        code_residual(S, SO, qy, P.W, 0, l2, ts, pass1, absl);
+        code_residual(S, SO, qy, P.W, 0, l2, ts, pass1, absl, nz.y, 8, by0);
     }
     if (cbcbf) {
         S.ctx(CTX_TS_FLAG + 1, 0);
-        code_residual(S, SO, qcb, cw, 1, l2 - 1, ts, pass1, absl);
+        code_residual(S, SO, qcb, cw, 1, l2 - 1, ts, pass1, absl, nz.cb, 4, bc0);
     }
     if (crcbf) {
         S.ctx(CTX_TS_FLAG + 1, 0);
-        code_residual(S, SO, qcr, cw, 2, l2 - 1, ts, pass1, absl);
+        code_residual(S, SO, qcr, cw, 2, l2 - 1, ts, pass1, absl, nz.cr, 4, bc0);
     }
     if (tree != DUAL_TREE_CHROMA && ts.mts_zero_out && !ts.mts_dc_only) S.ctx(CTX_MTS, 0);  // mts_idx == 0
 }
@@ -381,30 +421,81 @@ __device__ __forceinline__ bool code_split_flag(Sink &S, const PicView &P, const
     return split;
 }
 
-__device__ void code_ctu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, int ctu_x, int ctu_y, TuState &ts, uint16_t *pass1, uint16_t *absl) {
+__device__ void code_ctu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, const NzMap &nz, int ctu_x, int ctu_y, TuState &ts, uint8_t *pass1, uint8_t *absl) {
     if (!code_split_flag(S, P, rec, ctu_x, ctu_y, 32, 0)) {
-        code_cu(S, SO, P, rec, ctu_x, ctu_y, 0, 0, 32, SINGLE_TREE, ts, pass1, absl);
+        code_cu(S, SO, P, rec, nz, ctu_x, ctu_y, 0, 0, 32, SINGLE_TREE, ts, pass1, absl);
         return;
     }
     for (int a = 0; a < 4; a++) {
         const int x16 = (a & 1) * 16, y16 = (a >> 1) * 16;
         if (!code_split_flag(S, P, rec, ctu_x + x16, ctu_y + y16, 16, 1 + a)) {
-            code_cu(S, SO, P, rec, ctu_x, ctu_y, x16, y16, 16, SINGLE_TREE, ts, pass1, absl);
+            code_cu(S, SO, P, rec, nz, ctu_x, ctu_y, x16, y16, 16, SINGLE_TREE, ts, pass1, absl);
             continue;
         }
         for (int b = 0; b < 4; b++) {
             const int x8 = x16 + (b & 1) * 8, y8 = y16 + (b >> 1) * 8;
             if (!code_split_flag(S, P, rec, ctu_x + x8, ctu_y + y8, 8, 5 + 4 * a + b)) {
-                code_cu(S, SO, P, rec, ctu_x, ctu_y, x8, y8, 8, SINGLE_TREE, ts, pass1, absl);
+                code_cu(S, SO, P, rec, nz, ctu_x, ctu_y, x8, y8, 8, SINGLE_TREE, ts, pass1, absl);
                 continue;
             }
-            for (int i = 0; i < 4; i++) code_cu(S, SO, P, rec, ctu_x, ctu_y, x8 + (i & 1) * 4, y8 + (i >> 1) * 4, 4, DUAL_TREE_LUMA, ts, pass1, absl);
-            code_cu(S, SO, P, rec, ctu_x, ctu_y, x8, y8, 8, DUAL_TREE_CHROMA, ts, pass1, absl);
+            for (int i = 0; i < 4; i++) code_cu(S, SO, P, rec, nz, ctu_x, ctu_y, x8 + (i & 1) * 4, y8 + (i >> 1) * 4, 4, DUAL_TREE_LUMA, ts, pass1, absl);
+            code_cu(S, SO, P, rec, nz, ctu_x, ctu_y, x8, y8, 8, DUAL_TREE_CHROMA, ts, pass1, absl);
         }
     }
 }
 
-extern "C" __global__ void __launch_bounds__(64) wrenc_b200_syntax_kernel(SyntaxParams Q) {
+// Map of the non-zero 4x4 level blocks, one warp per CTU, coalesced: lane r reads luma row r (64 bytes) and one chroma row (lanes
+// 0-15 Cb, 16-31 Cr, 32 bytes); a ballot per block column gathers the rows.  The syntax walk (one THREAD per CTU, scattered 2-byte
+// loads) then answers "is this CU / sub-block coded" and "where is the last coded sub-block" from the map instead of scanning.
+extern "C" __global__ void __launch_bounds__(256) wrenc_b200_nzmap_kernel(SyntaxParams Q) {
+    const long long gid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nctu = Q.Wc * Q.Hc;
+    if (gid >= (long long)Q.n_pics * nctu) return;
+    const int pic = (int)(gid / nctu), ctu = (int)(gid - (long long)pic * nctu);
+    const int cx = (ctu % Q.Wc) * 32, cy = (ctu / Q.Wc) * 32, cw = Q.W >> 1;
+    const size_t ps = (size_t)Q.W * Q.H * 3 / 2;
+    const int16_t *ly = Q.lev + (size_t)pic * ps, *lcb = ly + (size_t)Q.W * Q.H, *lcr = lcb + (size_t)cw * (Q.H >> 1);
+    const uint4 *ry = reinterpret_cast<const uint4 *>(ly + (size_t)(cy + lane) * Q.W + cx);  // 32 levels = 4 x 16 bytes, 8 per block column pair
+    unsigned fy = 0;
+    for (int j = 0; j < 4; j++) {
+        const uint4 v = ry[j];
+        fy |= ((v.x | v.y) != 0u ? 1u : 0u) << (2 * j);
+        fy |= ((v.z | v.w) != 0u ? 1u : 0u) << (2 * j + 1);
+    }
+    const int16_t *pc = (lane < 16 ? lcb : lcr) + (size_t)((cy >> 1) + (lane & 15)) * cw + (cx >> 1);
+    const uint4 *rc = reinterpret_cast<const uint4 *>(pc);
+    unsigned fc = 0;
+    for (int j = 0; j < 2; j++) {
+        const uint4 v = rc[j];
+        fc |= ((v.x | v.y) != 0u ? 1u : 0u) << (2 * j);
+        fc |= ((v.z | v.w) != 0u ? 1u : 0u) << (2 * j + 1);
+    }
+    unsigned long long my = 0ull;
+    for (int bx = 0; bx < 8; bx++) {
+        const unsigned rows = __ballot_sync(0xffffffffu, (fy >> bx) & 1u);
+        for (int by = 0; by < 8; by++)
+            if ((rows >> (4 * by)) & 15u) my |= 1ull << (by * 8 + bx);
+    }
+    unsigned mcb = 0, mcr = 0;
+    for (int bx = 0; bx < 4; bx++) {
+        const unsigned rows = __ballot_sync(0xffffffffu, (fc >> bx) & 1u);
+        for (int by = 0; by < 4; by++) {
+            if ((rows >> (4 * by)) & 15u) mcb |= 1u << (by * 4 + bx);
+            if ((rows >> (16 + 4 * by)) & 15u) mcr |= 1u << (by * 4 + bx);
+        }
+    }
+    if (lane == 0) {
+        NzMap m;
+        m.y = my; m.cb = (unsigned short)mcb; m.cr = (unsigned short)mcr; m.pad = 0;
+        Q.nzmap[gid] = m;
+    }
+}
+
+#ifndef WB_SYN_MINB
+#define WB_SYN_MINB 1  // resident blocks of 64 threads per SM the register allocation aims for
+#endif
+extern "C" __global__ void __launch_bounds__(64, WB_SYN_MINB) wrenc_b200_syntax_kernel(SyntaxParams Q) {
     __shared__ SbOrder SO;
     if (threadIdx.x == 0) build_sb_order(SO);
     __syncthreads();
@@ -434,13 +525,19 @@ extern "C" __global__ void __launch_bounds__(64) wrenc_b200_syntax_kernel(Syntax
         S.p = Q.bins + Q.bin_offset[gid];
         S.cap = 0x7fffffff;
     }
-    uint16_t pass1[1024], absl[1024];
+    __align__(4) uint8_t pass1[1024], absl[1024];
     TuState ts;
     ts.qp_delta_coded = false;  // quantisation group = CTU (cu_qp_delta_subdiv 0, ctu_encoder.rs:305-310)
     ts.mts_dc_only = true;
     ts.mts_zero_out = true;
     const int cx = (ctu % Q.Wc) * 32, cy = (ctu / Q.Wc) * 32;
-    code_ctu(S, SO, P, P.rec[ctu], cx, cy, ts, pass1, absl);
+    NzMap nz;
+#if WB_NZMAP
+    nz = Q.nzmap[gid];
+#else
+    nz.y = 0; nz.cb = 0; nz.cr = 0; nz.pad = 0;
+#endif
+    code_ctu(S, SO, P, P.rec[ctu], nz, cx, cy, ts, pass1, absl);
     if (!Q.bins) Q.bin_count[gid] = S.n;
 }
 
@@ -478,70 +575,41 @@ extern "C" __global__ void __launch_bounds__(1024) wrenc_b200_bin_scan_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// arithmetic coder (bool_coder.rs:136-296, 1073-1111) — one thread per picture
+// arithmetic coder (bool_coder.rs:136-296, 1073-1111) — one warp per picture; the engine itself is cabac_engine.cuh
 // ---------------------------------------------------------------------------------------------------------------
-struct BitOut {
-    uint8_t *p;
-    size_t n, cap;
-    unsigned acc;
-    int nb;
-    __device__ __forceinline__ void bit(int b) {
-        acc = (acc << 1) | (unsigned)(b & 1);
-        if (++nb == 8) {
-            if (p && n < cap) p[n] = (uint8_t)acc;
-            n++;
-            nb = 0;
-            acc = 0;
-        }
-    }
-};
-struct Engine {
-    unsigned low, range;
-    int outstanding;
-    bool first;
-    BitOut out;
-    __device__ __forceinline__ void put(int b) {  // flush_cabac_bin: the very first bit of the slice is dropped
-        if (!first) out.bit(b);
-        first = false;
-        while (outstanding > 0) { out.bit(!b); outstanding--; }
-    }
-    __device__ __forceinline__ void renorm() {
-        while (range < 256) {
-            if (low < 256) put(0);
-            else if (low >= 512) { low -= 512; put(1); }
-            else { low -= 256; outstanding++; }
-            range <<= 1;
-            low <<= 1;
-        }
+struct WarpEnv {  // what ce::code_batch needs: the context index of entry i of the batch, context words in shared memory
+    unsigned cur;
+    unsigned *ctx;
+    __device__ __forceinline__ unsigned ci(int i) const { return __shfl_sync(0xffffffffu, cur, i) & 511u; }
+    __device__ __forceinline__ unsigned load(unsigned c) const { return ctx[c]; }
+    __device__ __forceinline__ void store(unsigned c, unsigned w) {
+        __syncwarp();  // every lane has read the old word (its own load and the prefetch of the next bin) before anyone stores the (identical) new one
+        ctx[c] = w;
     }
 };
 
-// One WARP per picture.  The coder itself is sequential, so every lane runs it redundantly on identical state (context
-// states in shared memory, engine state in registers; lane 0 alone stores the output bytes); what the warp buys is the
-// memory side: the bin strings are fetched 32 entries at a time with one coalesced load, double-buffered, and handed to the
-// coder by shuffles, instead of one dependent 2-byte global load per bin.
+#ifndef WB_CABAC2
+#define WB_CABAC2 1  // 1: token program (parallel probability states, sequential interval updates only); 0: ce::code_batch (all sequential)
+#endif
+
+// One WARP per picture; the bin strings are fetched 32 entries at a time with one coalesced load, double-buffered, and two
+// ballots turn a batch into a bypass mask and a bin mask.  What is sequential by nature is only the interval (range / low) update.
+// The probability state a context-coded bin sees depends on the bin history of its context alone, so it is resolved by the
+// lanes in parallel: lane i owns entry i, match.any groups the lanes by context, the group's first lane takes the context word
+// from shared memory and the adapted word travels down the group by shuffles (as many rounds as the most frequent context of
+// the batch has entries), the group's last lane stores it back.  Every lane then packs its entry into one token word - LPS
+// probability index and MPS flag, or a whole run of up to 8 bypass bins - and the sequential part (every lane redundantly on
+// identical registers; lane 0 alone stores the output bytes) walks the tokens: per context-coded bin one shuffle and the chain
+// range -> LPS width -> one-shift renormalisation (no per-bit loop, no outstanding-bit counter: cabac_engine.cuh).
 extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxParams Q) {
     const int pic = blockIdx.x, lane = threadIdx.x;
     if (pic >= Q.n_pics) return;
     const int nctu = Q.Wc * Q.Hc;
-    __shared__ uint16_t p0[CTX_TOTAL], p1[CTX_TOTAL];
-    __shared__ uint8_t sh0[CTX_TOTAL], sh1[CTX_TOTAL];
-    for (int i = lane; i < CTX_TOTAL; i += 32) {  // init_ctx_table (bool_coder.rs:1073-1093)
-        const int iv = kCabacInitValue[i];
-        const int m = (iv >> 3) - 4, nn = (iv & 7) * 18 + 1;
-        const int pre = min(127, max(1, ((m * (min(63, max(0, Q.qp)) - 16)) >> 1) + nn));
-        p0[i] = (uint16_t)(pre << 3);
-        p1[i] = (uint16_t)(pre << 7);
-        const int si = kCabacShiftIdx[i];
-        sh0[i] = (uint8_t)((si >> 2) + 2);
-        sh1[i] = (uint8_t)((si & 3) + 3 + (si >> 2) + 2);
-    }
+    __shared__ unsigned ctx[CTX_TOTAL];
+    for (int i = lane; i < CTX_TOTAL; i += 32) ctx[i] = ce::ctx_init_word(kCabacInitValue[i], kCabacShiftIdx[i], Q.qp);  // init_ctx_table (bool_coder.rs:1073-1093)
     __syncwarp();
-    Engine E;
-    E.low = 0; E.range = 510; E.outstanding = 0; E.first = true;
-    E.out.p = lane == 0 ? Q.out + (size_t)pic * Q.out_cap : nullptr;  // lanes other than 0 only count
-    E.out.n = 0; E.out.cap = Q.out_cap; E.out.acc = 0; E.out.nb = 0;
-    int overflow = 0;
+    ce::Arith E;
+    E.init(lane == 0 ? Q.out + (size_t)pic * Q.out_cap : nullptr, Q.out_cap);  // lanes other than 0 only count
     // the CTUs' bin strings lie back to back in the arena (exclusive scan of the counts), in raster order
     const size_t g0 = (size_t)pic * nctu;
     const unsigned long long beg = Q.bin_offset[g0];
@@ -553,57 +621,54 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
     const uint16_t *b = Q.bins + beg;
     const long long total = (long long)(end - beg);
     unsigned nxt = lane < total ? b[lane] : 0u;
+#if !WB_CABAC2
+    WarpEnv env;
+    env.ctx = ctx;
+#endif
     for (long long base = 0; base < total; base += 32) {
-        const unsigned cur = nxt;
+        const unsigned e = nxt;
         const long long pf = base + 32 + lane;
         nxt = pf < total ? b[pf] : 0u;  // prefetch the next 32 entries while this batch is coded
         const int cnt = (int)min(32ll, total - base);
-        for (int i = 0; i < cnt; i++) {
-            const unsigned e = __shfl_sync(0xffffffffu, cur, i);
-            const int bin = (e >> 9) & 1;
-            if (e & 1024u) {  // bypass (bool_coder.rs:202-216)
-                E.low <<= 1;
-                if (bin) E.low += E.range;
-                if (E.low >= 1024) { E.put(1); E.low -= 1024; }
-                else if (E.low < 512) E.put(0);
-                else { E.low -= 512; E.outstanding++; }
-            } else {  // context coded (bool_coder.rs:254-296)
-                const int ci = e & 511;
-                const unsigned q0 = p0[ci], q1 = p1[ci], s0 = sh0[ci], s1 = sh1[ci];
-                const unsigned ps = q1 + 16u * q0;
-                const unsigned mps = ps >> 14;
-                const unsigned lps = ((((E.range >> 5) * ((mps ? 32767u - ps : ps) >> 9)) >> 1) + 4);
-                if ((unsigned)bin == mps) E.range -= lps;
-                else { E.low += E.range - lps; E.range = lps; }
-                E.renorm();
-                __syncwarp();  // every lane has read the old state before anyone stores the (identical) new one
-                p0[ci] = (uint16_t)(q0 - (q0 >> s0) + ((1023 * bin) >> s0));
-                p1[ci] = (uint16_t)(q1 - (q1 >> s1) + ((16383 * bin) >> s1));
-                __syncwarp();
-            }
+        const unsigned bypm = __ballot_sync(0xffffffffu, (e & 1024u) != 0u);  // entries at and above cnt are 0
+        const unsigned binm = __ballot_sync(0xffffffffu, (e & 512u) != 0u);
+#if WB_CABAC2
+        const bool is_ctx = lane < cnt && !(e & 1024u);
+        const unsigned bin = (e >> 9) & 1u, ci = e & 511u;
+        // lanes of one context, in entry order: rank within the group, predecessor, last of the group
+        const unsigned peers = __match_any_sync(0xffffffffu, is_ctx ? ci : 512u + (unsigned)lane);
+        const unsigned before = peers & ((1u << lane) - 1u);
+        const int rank = __popc(before);
+        const int pred = before ? 31 - __clz((int)before) : lane;
+        const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)rank);
+        unsigned w = ctx[is_ctx ? ci : 0u];
+        unsigned adapted = ce::adapt(w, bin);
+        for (int r = 1; r <= rounds; r++) {  // after round r the lanes of rank <= r hold the word their bin sees
+            const unsigned t = __shfl_sync(0xffffffffu, adapted, pred);
+            if (rank == r) w = t;
+            adapted = ce::adapt(w, bin);
         }
+        __syncwarp();  // every lane has read its group's word before the group's last lane replaces it
+        if (is_ctx && (peers >> lane) == 1u) ctx[ci] = adapted;
+        __syncwarp();
+        const unsigned tok = (e & 1024u) ? ce::token_bypass(bypm, binm, lane) : ce::token_ctx(w, bin, lane);
+        ce::run_tokens(E, [&](int i) { return __shfl_sync(0xffffffffu, tok, i); }, cnt);
+#else
+        env.cur = e;
+        ce::code_batch(E, env, bypm, binm, cnt);
+#endif
     }
     // end_of_slice_one_bit = 1 (bool_coder.rs:218-235), then byte alignment with zeros (slice_encoder.rs:419)
-    E.range -= 2;
-    E.low += E.range;
-    E.range = 2;
-    E.renorm();
-    E.put((E.low >> 9) & 1);
-    {
-        const unsigned two = ((E.low >> 7) & 3) | 1;
-        for (int k = 1; k >= 0; k--) {  // flush_cabac_trailing_bin
-            const int bb = (two >> k) & 1;
-            E.out.bit(bb);
-            while (E.outstanding > 0) { E.out.bit(!bb); E.outstanding--; }
-        }
-    }
-    while (E.out.nb != 0) E.out.bit(0);
-    if (E.out.n > E.out.cap) overflow = 1;
-    if (lane == 0) Q.out_len[pic] = overflow ? -1 : (int)E.out.n;
+    const size_t n = E.finish();
+    if (lane == 0) Q.out_len[pic] = n > Q.out_cap ? -1 : (int)n;
 }
 
-cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream) {  // Q.bins == nullptr: counting pass
+int syntax_first_pass_kernels() { return 1 + WB_NZMAP; }
+cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream) {  // Q.bins == nullptr: non-zero map + counting pass
     const long long total = (long long)Q.n_pics * Q.Wc * Q.Hc;
+#if WB_NZMAP
+    if (!Q.bins) wrenc_b200_nzmap_kernel<<<(unsigned)((total * 32 + 255) / 256), 256, 0, stream>>>(Q);
+#endif
     wrenc_b200_syntax_kernel<<<(unsigned)((total + 63) / 64), 64, 0, stream>>>(Q);
     return cudaGetLastError();
 }
