@@ -17,6 +17,7 @@
 #pragma once
 #include <stdint.h>
 
+#define CE_UNLIKELY(x) __builtin_expect(!!(x), 0)
 #if defined(__CUDACC__)
 #define CE_HD __host__ __device__ __forceinline__
 #else
@@ -64,7 +65,8 @@ CE_HD unsigned adapt(unsigned w, unsigned bin) {
 }
 
 struct Arith {
-    unsigned low, range, buf_byte;
+    unsigned long long low;  // 64-bit window: up to 32 bits may be added before whole bytes have to leave it (flush)
+    unsigned range, buf_byte;
     int bits_left, n_buf;
     uint8_t *p;  // nullptr: count only
     size_t n, cap;
@@ -79,9 +81,9 @@ struct Arith {
     }
     // the top byte of the window leaves it; a carry (bit 8 of lead) goes into the buffered byte and the 0xff run behind it
     CE_HD void write_out() {
-        const unsigned lead = low >> (24 - bits_left);
+        const unsigned lead = (unsigned)(low >> (24 - bits_left));
         bits_left += 8;
-        low &= 0xffffffffu >> bits_left;
+        low &= 0xffffffffffffffffull >> (32 + bits_left);
         if (lead == 0xffu) n_buf++;
         else if (n_buf > 0) {
             const unsigned carry = lead >> 8;
@@ -106,7 +108,12 @@ struct Arith {
         low = (low + add) << nsh;
         range = r << nsh;
         bits_left -= nsh;
-        if (bits_left < 12) write_out();
+        flush();
+    }
+    // whole bytes out of the window until at least 12 bits are free below bit 32 again (bits_left >= -20 on entry)
+    CE_HD void flush() {
+#pragma unroll 1
+        while (bits_left < 12) write_out();
     }
     // context-coded bin; returns the adapted context word
     CE_HD unsigned decision(unsigned w, unsigned bin) {
@@ -118,7 +125,7 @@ struct Arith {
     CE_HD void bypass(unsigned v, int k) {
         low = (low << k) + range * v;
         bits_left -= k;
-        if (bits_left < 12) write_out();
+        flush();
     }
     // end_of_slice_one_bit = 1, flush, stop bit, zero padding to the byte boundary; returns the byte count
     CE_HD size_t finish() {
@@ -126,19 +133,19 @@ struct Arith {
         low = (low + range) << 7;
         range = 2u << 7;
         bits_left -= 7;
-        if (bits_left < 12) write_out();
+        flush();
         if (low >> (32 - bits_left)) {
             emit(buf_byte + 1);
 #pragma unroll 1
             while (n_buf > 1) { emit(0x00u); n_buf--; }
-            low -= 1u << (32 - bits_left);
+            low -= 1ull << (32 - bits_left);
         } else {
             if (n_buf > 0) emit(buf_byte);
 #pragma unroll 1
             while (n_buf > 1) { emit(0xffu); n_buf--; }
         }
         int k = 24 - bits_left;                         // bits of the code value still in the window (above bit 8)
-        unsigned v = ((low >> 8) << 1) | 1u;            // + the stop bit the reference forces into its last trailing bit
+        unsigned v = ((unsigned)(low >> 8) << 1) | 1u;            // + the stop bit the reference forces into its last trailing bit
         k += 1;
         const int pad = (8 - (k & 7)) & 7;
         v <<= pad;
@@ -187,31 +194,54 @@ CE_HD void code_batch(Arith &E, Env &env, unsigned bypm, unsigned binm, int cnt)
 }
 
 // ---- the same batch as a token program (wrenc_b200_cabac_kernel): every entry of the batch is turned into one word by its own
-// lane, in parallel, and the sequential part only walks the words:
-//     context-coded entry  qlps | is_mps << 5 |                              next << 19     (next = own position + 1)
-//     bypass entry         64 | k << 7 | value << 11 |                       next << 19     (the run of up to 8 bypass bins that
-//                                                                                            starts at this entry; next = position + k)
-enum { TOK_BYPASS = 64u };
+// lane, in parallel, and the sequential part only walks the words with ONE branch-free update per word:
+//     lps  = (((range >> 5) * qlps) >> 1) + c4          c4 = 4 for a context-coded bin, 0 for a bypass run (qlps = 0: lps = 0)
+//     r    = mps ? range - lps : lps                    bypass runs carry mps = 1: r = range, nothing is added to low
+//     n    = clz(r) - 23                                0 for a bypass run
+//     low  = ((low + (mps ? 0 : range - lps)) << (n + k)) + range * v        k, v = length and value of the bypass run, 0 otherwise
+//     range = r << n
+// word layout: qlps (bits 0-4) | mps << 5 | bypass << 6 | k << 7 | v << 11 | next << 19   (next = position of the next word to
+// walk: own position + 1, or + k for a bypass run; a word with k = 0, v = 0, bypass = mps = 1 changes nothing: TOK_NOP)
+enum : unsigned { TOK_BYPASS = 64u, TOK_NOP = 32u | 64u | (32u << 19) };
 CE_HD unsigned token_ctx(unsigned w, unsigned bin, int pos) { return ctx_token(w, bin) | ((unsigned)(pos + 1) << 19); }
 CE_HD unsigned token_bypass(unsigned bypm, unsigned binm, int pos) {  // bit pos of bypm is set
     const unsigned run = ~(bypm >> pos);
     int k = run ? ffs32(run) - 1 : 32;
     k = k > 8 ? 8 : k;
     const unsigned v = brev32(binm >> pos) >> (32 - k);
-    return (unsigned)TOK_BYPASS | ((unsigned)k << 7) | (v << 11) | ((unsigned)(pos + k) << 19);
+    return 32u | (unsigned)TOK_BYPASS | ((unsigned)k << 7) | (v << 11) | ((unsigned)(pos + k) << 19);
 }
-// get(i): the word of entry i (i < 32).  The word of the next entry is fetched before the current one is coded.
+CE_HD void step(Arith &E, unsigned t) {
+    const unsigned qlps = t & 31u, c4 = ((t >> 4) & 4u) ^ 4u, k = (t >> 7) & 15u, v = (t >> 11) & 255u;
+    const bool mps = (t & 32u) != 0u;
+    const unsigned lps = (((E.range >> 5) * qlps) >> 1) + c4;
+    const unsigned rmps = E.range - lps;
+    const unsigned r = mps ? rmps : lps;
+    const unsigned add = mps ? 0u : rmps;
+    const int nsh = clz32(r) - 23;
+    const int sh = nsh + (int)k;
+    E.low = ((E.low + add) << sh) + (unsigned long long)(E.range * v);
+    E.range = r << nsh;
+    E.bits_left -= sh;
+}
+// get(i): the word of entry i (i < 32).  The word of the next entry is fetched before the current one is coded; the walk is
+// unrolled by four with no branch inside (words past the end are TOK_NOP; four words add at most 32 bits to the 64-bit window,
+// whole bytes leave it once per round).
 template <class Get>
 CE_HD void run_tokens(Arith &E, Get get, int cnt) {
     int i = 0;
-    unsigned t = get(0);
+    unsigned t = cnt > 0 ? get(0) : (unsigned)TOK_NOP;
     while (i < cnt) {
-        const int ni = (int)(t >> 19);
-        const unsigned tn = get(ni & 31);
-        if (t & TOK_BYPASS) E.bypass((t >> 11) & 255u, (int)((t >> 7) & 15u));
-        else E.decision_tok(t & 31u, (t & 32u) != 0u);
-        t = tn;
-        i = ni;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int ni = (int)(t >> 19);
+            unsigned tn = get(ni & 31);
+            tn = ni >= cnt ? (unsigned)TOK_NOP : tn;
+            step(E, t);
+            t = tn;
+            i = ni;
+        }
+        E.flush();
     }
 }
 

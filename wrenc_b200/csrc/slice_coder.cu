@@ -16,6 +16,22 @@
 #ifndef WB_NZMAP
 #define WB_NZMAP 1  // 1: the syntax walk reads a per-CTU map of non-zero 4x4 level blocks instead of scanning the level planes
 #endif
+#ifndef WB_SYN_OUTLINE
+#define WB_SYN_OUTLINE 1  // 1: coding_unit / residual_coding / luma mode are real functions (the walk is 28 k instructions when everything is inlined)
+#endif
+#ifndef WB_SYN_ROLL
+#define WB_SYN_ROLL 1  // 1: the fixed-trip loops of residual_coding stay rolled
+#endif
+#if WB_SYN_ROLL
+#define WB_SYN_UNROLL1 _Pragma("unroll 1")
+#else
+#define WB_SYN_UNROLL1
+#endif
+#if WB_SYN_OUTLINE
+#define WB_SYN_NOINLINE __noinline__
+#else
+#define WB_SYN_NOINLINE
+#endif
 #define WB_CABAC_TABLE static __constant__ const
 #include "cabac_tables.h"
 #include "search_kernel_api.h"
@@ -57,6 +73,7 @@ struct Sink {
     __device__ __forceinline__ void ctx(int c, int b) { put((unsigned)c | ((unsigned)(b & 1) << 9)); }
     __device__ __forceinline__ void byp(int b) { put(((unsigned)(b & 1) << 9) | (1u << 10)); }
     __device__ __forceinline__ void byp_bits(unsigned v, int nb) {
+        WB_SYN_UNROLL1
         for (int i = nb - 1; i >= 0; i--) byp((v >> i) & 1);
     }
 };
@@ -91,7 +108,7 @@ struct TuState {
 
 // residual_coding() of one transform block (ctu_encoder.rs:1786-2269), regular (non transform-skip) path with dep-quant
 // (nzm, rs, b0): the CTU's map of non-zero 4x4 blocks of this component, its row stride in bits and the bit of the TB's first block
-__device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int stride, int c_idx, int l2, TuState &ts, uint8_t *pass1, uint8_t *absl,
+__device__ WB_SYN_NOINLINE void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int stride, int c_idx, int l2, TuState &ts, uint8_t *pass1, uint8_t *absl,
                               unsigned long long nzm, int rs, int b0) {
     const int n = 1 << l2, nn = n * n, nsbw = n >> 2;
     const uint8_t *sbo = SO.o + sb_off(l2);
@@ -141,6 +158,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
         else { off = 20; shift = min(2, max(0, n >> 3)); }
         for (int d = 0; d < 2; d++) {
             const int base = d ? CTX_LAST_Y : CTX_LAST_X;
+            WB_SYN_UNROLL1
             for (int i = 0; i < pre[d]; i++) S.ctx(base + (i >> shift) + off, 1);
             if (pre[d] < cmax) S.ctx(base + (pre[d] >> shift) + off, 0);
         }
@@ -171,10 +189,12 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
         const int pv = min(cmax, value);
         const int pre_ = pv >> rice;
         if (pre_ < 6) {
+            WB_SYN_UNROLL1
             for (int i = 0; i < pre_; i++) S.byp(1);
             S.byp(0);
             if (rice > 0) S.byp_bits((unsigned)(pv - (pre_ << rice)), rice);
         } else {
+            WB_SYN_UNROLL1
             for (int i = 0; i < 6; i++) S.byp(1);
             // limited k-th order exp-Golomb escape, k = rice + 1, maxPreExtLen 11, truncSuffixLen 15 (bool_coder.rs:1278-1303)
             int sym = value - cmax;
@@ -206,6 +226,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
         int a[16];
         {
             int st = qstate;
+            WB_SYN_UNROLL1
             for (int p = 15; p >= 0; p--) {
                 const int x = (xs << 2) + (c_diag4[p] & 3), y = (ys << 2) + (c_diag4[p] >> 2);
                 const int v = q[y * stride + x];
@@ -225,6 +246,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
         if (sbcoded && (xs > 3 || ys > 3) && c_idx == 0) ts.mts_zero_out = false;
         const int fp0 = i == last_sb ? last_pos : 15;
         int fp1 = fp0;
+        WB_SYN_UNROLL1
         for (int p = fp0; p >= 0; p--) {
             if (rem < 4) break;
             const int x = (xs << 2) + (c_diag4[p] & 3), y = (ys << 2) + (c_diag4[p] >> 2);
@@ -265,6 +287,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
             qstate = tr_state(qstate, p1);
             fp1 = p - 1;
         }
+        WB_SYN_UNROLL1
         for (int p = fp0; p > fp1; p--) {  // abs_remainder of the positions coded in pass 1
             const int x = (xs << 2) + (c_diag4[p] & 3), y = (ys << 2) + (c_diag4[p] >> 2);
             if (a[p] > 3) {
@@ -275,6 +298,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
             }
             absl[y * n + x] = (uint8_t)min(a[p], 255);
         }
+        WB_SYN_UNROLL1
         for (int p = fp1; p >= 0; p--) {  // dec_abs_level of the rest
             const int x = (xs << 2) + (c_diag4[p] & 3), y = (ys << 2) + (c_diag4[p] >> 2);
             absl[y * n + x] = (uint8_t)min(a[p], 255);
@@ -289,6 +313,7 @@ __device__ void code_residual(Sink &S, const SbOrder &SO, const int16_t *q, int 
             }
             qstate = tr_state(qstate, a[p]);
         }
+        WB_SYN_UNROLL1
         for (int p = 15; p >= 0; p--) {  // coeff_sign_flag (sign data hiding off)
             if (a[p] > 0) {
                 const int x = (xs << 2) + (c_diag4[p] & 3), y = (ys << 2) + (c_diag4[p] >> 2);
@@ -306,7 +331,7 @@ __device__ bool block_nonzero(const int16_t *q, int stride, int n) {
 }
 
 // MPM list of the syntax pass (ctu.rs:1498-1635): true neighbours from the final mode map
-__device__ void code_luma_mode(Sink &S, const PicView &P, int px, int py, int size, int mode) {
+__device__ WB_SYN_NOINLINE void code_luma_mode(Sink &S, const PicView &P, int px, int py, int size, int mode) {
     if (mode == 0) { S.ctx(CTX_MPM_FLAG, 1); S.ctx(CTX_NOT_PLANAR + 1, 0); return; }
     const int left = px > 0 ? luma_mode_at(P, px - 1, py + size - 1) : 0;
     const int above = (py > 0 && (py & 31) != 0) ? luma_mode_at(P, px + size - 1, py - 1) : 0;
@@ -349,7 +374,7 @@ __device__ void code_luma_mode(Sink &S, const PicView &P, int px, int py, int si
 }
 
 // coding_unit() + transform_unit() of one CU (ctu_encoder.rs:440-1321, 1414-1784); (x, y) CTU-relative luma position
-__device__ void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, const NzMap &nz, int ctu_x, int ctu_y, int x, int y, int size, int tree,
+__device__ WB_SYN_NOINLINE void code_cu(Sink &S, const SbOrder &SO, const PicView &P, const CtuRecord &rec, const NzMap &nz, int ctu_x, int ctu_y, int x, int y, int size, int tree,
                         TuState &ts, uint8_t *pass1, uint8_t *absl) {
     const int px = ctu_x + x, py = ctu_y + y;
     if (tree != DUAL_TREE_CHROMA) code_luma_mode(S, P, px, py, size, rec.luma_mode[(y >> 2) * 8 + (x >> 2)]);
@@ -493,7 +518,7 @@ extern "C" __global__ void __launch_bounds__(256) wrenc_b200_nzmap_kernel(Syntax
 }
 
 #ifndef WB_SYN_MINB
-#define WB_SYN_MINB 1  // resident blocks of 64 threads per SM the register allocation aims for
+#define WB_SYN_MINB 16  // resident blocks of 64 threads per SM the register allocation aims for (64 registers per thread)
 #endif
 extern "C" __global__ void __launch_bounds__(64, WB_SYN_MINB) wrenc_b200_syntax_kernel(SyntaxParams Q) {
     __shared__ SbOrder SO;
