@@ -52,6 +52,42 @@ static std::vector<uint8_t> code_tokens(int qp, const std::vector<uint16_t> &bin
     return out;
 }
 
+// the compacted record list of the two-warp kernel: walked entries only, padded with no-ops to a multiple of four
+static std::vector<uint8_t> code_records(int qp, const std::vector<uint16_t> &bins) {
+    std::vector<unsigned> ctx(CTX_TOTAL);
+    for (int i = 0; i < CTX_TOTAL; i++) ctx[i] = ce::ctx_init_word(kCabacInitValue[i], kCabacShiftIdx[i], qp);
+    std::vector<uint8_t> out(bins.size() / 4 + 64);
+    ce::Arith E;
+    E.init(out.data(), out.size());
+    for (size_t base = 0; base < bins.size(); base += 32) {
+        const int cnt = (int)std::min<size_t>(32, bins.size() - base);
+        unsigned bypm = 0, binm = 0;
+        for (int i = 0; i < cnt; i++) {
+            bypm |= (unsigned)((bins[base + i] >> 10) & 1) << i;
+            binm |= (unsigned)((bins[base + i] >> 9) & 1) << i;
+        }
+        ce::TokRec rec[36];
+        int count = 0;
+        for (int i = 0; i < cnt; i++) {
+            const unsigned e = bins[base + i], bin = (e >> 9) & 1u;
+            const bool walked = ce::tok_walked(bypm, i);
+            if (e & 1024u) {
+                if (walked) rec[count++] = ce::rec_bypass(bypm, binm, i);
+            } else {
+                if (!walked) { fprintf(stderr, "context-coded entry not walked\n"); exit(2); }
+                rec[count++] = ce::rec_ctx(ctx[e & 511u], bin);
+                ctx[e & 511u] = ce::adapt(ctx[e & 511u], bin);
+            }
+        }
+        for (int i = 0; i < 3; i++) rec[count + i] = ce::rec_nop();
+        ce::walk_records(E, [&](int j) { return rec[j]; }, count);
+    }
+    const size_t n = E.finish();
+    if (n > out.size()) { fprintf(stderr, "host buffer too small\n"); exit(2); }
+    out.resize(n);
+    return out;
+}
+
 static std::vector<uint8_t> code_fast(int qp, const std::vector<uint16_t> &bins) {
     std::vector<unsigned> ctx(CTX_TOTAL);
     for (int i = 0; i < CTX_TOTAL; i++) ctx[i] = ce::ctx_init_word(kCabacInitValue[i], kCabacShiftIdx[i], qp);
@@ -82,6 +118,10 @@ static void check(int qp, const std::vector<uint16_t> &bins, const char *what) {
     g_bins += (long)bins.size();
     if (want != code_tokens(qp, bins)) {
         if (g_bad < 5) fprintf(stderr, "MISMATCH (token program) %s: %zu bins\n", what, bins.size());
+        g_bad++;
+    }
+    if (want != code_records(qp, bins)) {
+        if (g_bad < 5) fprintf(stderr, "MISMATCH (record list) %s: %zu bins\n", what, bins.size());
         g_bad++;
     }
     if (want != got) {
@@ -163,7 +203,7 @@ int main(int argc, char **argv) {
         long nbyp = 0;
         for (uint16_t e : bins) nbyp += (e >> 10) & 1;
         printf("picture qp %d: %zu bins (%ld bypass), %zu bytes\n", qp, bins.size(), nbyp, want.size());
-        if (want != got || want != code_tokens(qp, bins)) { fprintf(stderr, "MISMATCH real picture qp %d\n", qp); g_bad++; }
+        if (want != got || want != code_tokens(qp, bins) || want != code_records(qp, bins)) { fprintf(stderr, "MISMATCH real picture qp %d\n", qp); g_bad++; }
     }
     printf("%ld strings, %ld bins, %ld mismatches\n", g_checked, g_bins, g_bad);
     return g_bad ? 1 : 0;

@@ -128,9 +128,10 @@ struct Arith {
         flush();
     }
     // end_of_slice_one_bit = 1, flush, stop bit, zero padding to the byte boundary; returns the byte count
-    CE_HD size_t finish() {
-        range -= 2;
-        low = (low + range) << 7;
+    CE_HD size_t finish() { return finish_low(range - 2u); }
+    // the same from the low side alone: term_add = range - 2 of the interval before end_of_slice_one_bit
+    CE_HD size_t finish_low(unsigned term_add) {
+        low = (low + term_add) << 7;
         range = 2u << 7;
         bits_left -= 7;
         flush();
@@ -241,6 +242,64 @@ CE_HD void run_tokens(Arith &E, Get get, int cnt) {
             t = tn;
             i = ni;
         }
+        E.flush();
+    }
+}
+
+// ---- the token program as a COMPACTED record list (wrenc_b200_cabac_kernel, two warps per picture): the producer warp writes one
+// ready-to-use record per walked entry (no packing, nothing to decode) into shared memory, densely, so that the consumer walks
+// consecutive records: four branch-free steps per round with every load address known in advance.
+struct TokRec {
+    unsigned qlps, c4, k, v;  // step() operands (see above)
+    unsigned mps, pad0, pad1, pad2;
+};
+// entry pos of a batch is walked when it is context-coded or starts a (sub-)run of 8 bypass bins: bins 0, 8, 16, 24 of a run
+CE_HD bool tok_walked(unsigned bypm, int pos) {
+    if (!((bypm >> pos) & 1u)) return true;
+    const unsigned below = ~bypm & ((1u << pos) - 1u);  // context-coded entries before pos
+    const int start = below ? 32 - clz32(below) : 0;    // first entry of the bypass run that holds pos
+    return ((pos - start) & 7) == 0;
+}
+CE_HD TokRec rec_nop() { TokRec t = {0u, 0u, 0u, 0u, 1u, 0u, 0u, 0u}; return t; }
+CE_HD TokRec rec_ctx(unsigned w, unsigned bin) {
+    const unsigned c = ctx_token(w, bin);
+    TokRec t = {c & 31u, 4u, 0u, 0u, (c >> 5) & 1u, 0u, 0u, 0u};
+    return t;
+}
+CE_HD TokRec rec_bypass(unsigned bypm, unsigned binm, int pos) {
+    const unsigned b = token_bypass(bypm, binm, pos);
+    TokRec t = {0u, 0u, (b >> 7) & 15u, (b >> 11) & 255u, 1u, 0u, 0u, 0u};
+    return t;
+}
+// One step, split where the data flow splits: the RANGE side is the only sequential dependency between steps (range -> LPS width ->
+// renormalisation shift -> range); what it leaves for the LOW side is  add | sh << 16  and  range * v  (LowOp), and the low side
+// (window, carries, bytes) never feeds back.  The kernel runs the two sides in different warps.
+struct LowOp {
+    unsigned add_sh, rv;
+};
+CE_HD LowOp step_range(unsigned &range, const TokRec &t) {
+    const unsigned lps = (((range >> 5) * t.qlps) >> 1) + t.c4;
+    const unsigned rmps = range - lps;
+    const bool mps = t.mps != 0u;
+    const unsigned r = mps ? rmps : lps;
+    const unsigned add = mps ? 0u : rmps;
+    const int nsh = clz32(r) - 23;
+    LowOp o = {add | ((unsigned)(nsh + (int)t.k) << 16), range * t.v};
+    range = r << nsh;
+    return o;
+}
+CE_HD void step_low(Arith &E, const LowOp &o) {
+    const int sh = (int)(o.add_sh >> 16);
+    E.low = ((E.low + (o.add_sh & 0xffffu)) << sh) + (unsigned long long)o.rv;
+    E.bits_left -= sh;
+}
+CE_HD void step_rec(Arith &E, const TokRec &t) { step_low(E, step_range(E.range, t)); }
+// get(j): record j of the batch's list, padded with rec_nop() to a multiple of four
+template <class Get>
+CE_HD void walk_records(Arith &E, Get get, int count) {
+    for (int j = 0; j < count; j += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) step_rec(E, get(j + u));
         E.flush();
     }
 }

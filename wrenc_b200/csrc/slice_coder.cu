@@ -614,9 +614,150 @@ struct WarpEnv {  // what ce::code_batch needs: the context index of entry i of 
 };
 
 #ifndef WB_CABAC2
-#define WB_CABAC2 1  // 1: token program (parallel probability states, sequential interval updates only); 0: ce::code_batch (all sequential)
+#define WB_CABAC2 2  // 2: two warps per picture (token records through shared memory); 1: one warp, token words by shuffle; 0: ce::code_batch (all sequential)
 #endif
 
+#if WB_CABAC2 == 2
+__device__ __forceinline__ void nbar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+constexpr int CABAC_SUBS = 8;                         // 32-entry batches per slot hand-over
+constexpr int CABAC_SLOT = CABAC_SUBS * 32 + 8;       // records per slot (+ the no-op padding of the last round + the range warp's look-ahead)
+enum { BAR_REC_FULL = 1, BAR_REC_EMPTY = 3, BAR_OP_FULL = 5, BAR_OP_EMPTY = 7, BAR_TERM = 9 };  // + slot; 64 participants each (32 arrive, 32 wait)
+
+// THREE warps per picture, one per stage of the data flow.  What is sequential by nature is only the interval width: the
+// probability state a context-coded bin sees depends on the bin history of its context alone, and the code value (low) never
+// feeds back into the widths.
+//   warp 1, states: fetches the bin string 32 entries at a time (one coalesced load, double-buffered); lane i owns entry i;
+//     match.any groups the lanes by context, the group's first lane takes the context word from shared memory and the adapted
+//     word travels down the group by shuffles (as many rounds as the most frequent context of the batch has entries), the
+//     group's last lane stores it back; every walked entry - a context-coded bin, or the start of a run of up to 8 bypass bins -
+//     becomes one ready-to-use record (ce::TokRec), written densely into one of two shared-memory slots;
+//   warp 0, range: walks the records; per record the dependent chain range -> LPS width -> one-shift renormalisation and nothing
+//     else (ce::step_range); leaves what the code value needs (ce::LowOp: addend, shift, bypass term) in a second pair of slots;
+//   warp 2, low: accumulates the code value in a 64-bit window, four records per round, resolves carries and stores the bytes
+//     (ce::step_low / flush / finish_low; lane 0 stores).
+// Warps 0 and 2 run every lane redundantly on identical registers.  The slots are handed over with named barriers (full /
+// empty per slot and pair) every CABAC_SUBS batches, so each stage works one slot ahead of the next.
+extern "C" __global__ void __launch_bounds__(96) wrenc_b200_cabac_kernel(SyntaxParams Q) {
+    const int pic = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (pic >= Q.n_pics) return;
+    const int nctu = Q.Wc * Q.Hc;
+    __shared__ unsigned ctx[CTX_TOTAL];
+    __shared__ __align__(16) ce::TokRec rec[2][CABAC_SLOT];
+    __shared__ __align__(8) ce::LowOp ops[2][CABAC_SLOT];
+    __shared__ int rec_count[2], op_count[2];
+    __shared__ unsigned term_add;
+    // the CTUs' bin strings lie back to back in the arena (exclusive scan of the counts), in raster order
+    const size_t g0 = (size_t)pic * nctu;
+    const unsigned long long beg = Q.bin_offset[g0];
+    const unsigned long long end = Q.bin_offset[g0 + nctu - 1] + (unsigned long long)Q.bin_count[g0 + nctu - 1];
+    if (end > Q.bins_cap) {  // this picture's strings did not fit the arena (sized from earlier batches): nothing was written for it
+        if (threadIdx.x == 0) Q.out_len[pic] = -2;
+        return;
+    }
+    const uint16_t *b = Q.bins + beg;
+    const long long total = (long long)(end - beg);
+    if (warp == 1) {
+        for (int i = lane; i < CTX_TOTAL; i += 32) ctx[i] = ce::ctx_init_word(kCabacInitValue[i], kCabacShiftIdx[i], Q.qp);  // init_ctx_table (bool_coder.rs:1073-1093)
+        __syncwarp();
+        unsigned nxt = lane < total ? b[lane] : 0u;
+        int slot = 0;
+        for (long long sbase = 0; sbase < total; sbase += 32 * CABAC_SUBS, slot ^= 1) {
+            int fill = 0;  // records of this slot so far
+            for (long long base = sbase; base < min(total, sbase + 32 * CABAC_SUBS); base += 32) {
+                const unsigned e = nxt;
+                const long long pf = base + 32 + lane;
+                nxt = pf < total ? b[pf] : 0u;  // prefetch the next 32 entries
+                const int cnt = (int)min(32ll, total - base);
+                const unsigned bypm = __ballot_sync(0xffffffffu, (e & 1024u) != 0u);  // entries at and above cnt are 0
+                const unsigned binm = __ballot_sync(0xffffffffu, (e & 512u) != 0u);
+                const bool is_ctx = lane < cnt && !(e & 1024u);
+                const unsigned bin = (e >> 9) & 1u, ci = e & 511u;
+                // lanes of one context, in entry order: rank within the group, predecessor, last of the group
+                const unsigned peers = __match_any_sync(0xffffffffu, is_ctx ? ci : 512u + (unsigned)lane);
+                const unsigned before = peers & ((1u << lane) - 1u);
+                const int rank = __popc(before);
+                const int pred = before ? 31 - __clz((int)before) : lane;
+                const int rounds = (int)__reduce_max_sync(0xffffffffu, (unsigned)rank);
+                unsigned w = ctx[is_ctx ? ci : 0u];
+                unsigned adapted = ce::adapt(w, bin);
+                for (int r = 1; r <= rounds; r++) {  // after round r the lanes of rank <= r hold the word their bin sees
+                    const unsigned t = __shfl_sync(0xffffffffu, adapted, pred);
+                    if (rank == r) w = t;
+                    adapted = ce::adapt(w, bin);
+                }
+                __syncwarp();  // every lane has read its group's word before the group's last lane replaces it
+                if (is_ctx && (peers >> lane) == 1u) ctx[ci] = adapted;
+                __syncwarp();
+                const bool walked = lane < cnt && ce::tok_walked(bypm, lane);
+                const unsigned wm = __ballot_sync(0xffffffffu, walked);
+                const int idx = fill + __popc(wm & ((1u << lane) - 1u));
+                if (base == sbase && sbase >= 2ll * 32 * CABAC_SUBS) nbar_sync(BAR_REC_EMPTY + slot);  // the range warp is done with this slot's previous records
+                if (walked) rec[slot][idx] = (e & 1024u) ? ce::rec_bypass(bypm, binm, lane) : ce::rec_ctx(w, bin);
+                fill += __popc(wm);
+            }
+            if (lane < 3) rec[slot][fill + lane] = ce::rec_nop();  // the walkers take four records per round
+            if (lane == 0) rec_count[slot] = fill;
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            nbar_arrive(BAR_REC_FULL + slot);
+        }
+    } else if (warp == 0) {
+        unsigned range = 510u;
+        int slot = 0;
+        for (long long sbase = 0; sbase < total; sbase += 32 * CABAC_SUBS, slot ^= 1) {
+            nbar_sync(BAR_REC_FULL + slot);
+            if (sbase >= 2ll * 32 * CABAC_SUBS) nbar_sync(BAR_OP_EMPTY + slot);  // the low warp is done with this slot's previous records
+            const ce::TokRec *rs = rec[slot];
+            ce::LowOp *os = ops[slot];
+            const int count = rec_count[slot];
+            // four records per round, the next round's records loaded before this round's chain (the slot is padded with no-ops
+            // and four more entries, so the look-ahead never leaves it)
+            ce::TokRec cur[4], nxt4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) cur[u] = rs[u];
+            for (int j = 0; j < count; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) nxt4[u] = rs[j + 4 + u];
+                ce::LowOp o[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) o[u] = ce::step_range(range, cur[u]);
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) os[j + u] = o[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) cur[u] = nxt4[u];
+            }
+            if (lane == 0) op_count[slot] = count;
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            nbar_arrive(BAR_OP_FULL + slot);
+            nbar_arrive(BAR_REC_EMPTY + slot);
+        }
+        if (lane == 0) term_add = range - 2u;  // end_of_slice_one_bit = 1 (bool_coder.rs:218-235)
+        asm volatile("fence.acq_rel.cta;" ::: "memory");
+        nbar_arrive(BAR_TERM);
+    } else {
+        ce::Arith E;
+        E.init(lane == 0 ? Q.out + (size_t)pic * Q.out_cap : nullptr, Q.out_cap);  // lanes other than 0 only count
+        int slot = 0;
+        for (long long sbase = 0; sbase < total; sbase += 32 * CABAC_SUBS, slot ^= 1) {
+            nbar_sync(BAR_OP_FULL + slot);
+            const ce::LowOp *os = ops[slot];
+            const int count = op_count[slot];
+            for (int j = 0; j < count; j += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) ce::step_low(E, os[j + u]);
+                E.flush();
+            }
+            nbar_arrive(BAR_OP_EMPTY + slot);
+        }
+        nbar_sync(BAR_TERM);
+        // flush, stop bit, byte alignment with zeros (slice_encoder.rs:419)
+        const size_t n = E.finish_low(term_add);
+        if (lane == 0) Q.out_len[pic] = n > Q.out_cap ? -1 : (int)n;
+    }
+}
+#else
 // One WARP per picture; the bin strings are fetched 32 entries at a time with one coalesced load, double-buffered, and two
 // ballots turn a batch into a bypass mask and a bin mask.  What is sequential by nature is only the interval (range / low) update.
 // The probability state a context-coded bin sees depends on the bin history of its context alone, so it is resolved by the
@@ -687,6 +828,7 @@ extern "C" __global__ void __launch_bounds__(32) wrenc_b200_cabac_kernel(SyntaxP
     const size_t n = E.finish();
     if (lane == 0) Q.out_len[pic] = n > Q.out_cap ? -1 : (int)n;
 }
+#endif
 
 int syntax_first_pass_kernels() { return 1 + WB_NZMAP; }
 cudaError_t launch_syntax(const SyntaxParams &Q, cudaStream_t stream) {  // Q.bins == nullptr: non-zero map + counting pass
@@ -708,7 +850,7 @@ cudaError_t launch_bin_compact(const SyntaxParams &Q, cudaStream_t stream) {
     return cudaGetLastError();
 }
 cudaError_t launch_cabac(const SyntaxParams &Q, cudaStream_t stream) {
-    wrenc_b200_cabac_kernel<<<Q.n_pics, 32, 0, stream>>>(Q);
+    wrenc_b200_cabac_kernel<<<Q.n_pics, WB_CABAC2 == 2 ? 96 : 32, 0, stream>>>(Q);
     return cudaGetLastError();
 }
 
