@@ -111,8 +111,9 @@ int wrenc_b200_search_resident(wrenc_b200 *h, int32_t n_pictures, const uint8_t 
 /* Phase 2 on resident data: CABAC-codes the pictures the preceding wrenc_b200_search_resident call on this handle decided
  * (same n_pictures, its d_levels / d_records) into d_out[n_pictures][out_cap] bytes and d_out_len[n_pictures] (-1 = overflow).
  * (-1 = the picture's output buffer is too small, -2 = the bin arena, which is sized from earlier batches, was too small for
- * this batch: call wrenc_b200_code_resident_retry).  Device pointers; runs on `stream` after the search; does not synchronise.
- * Returns kernel launches enqueued (5) or <0.
+ * this batch: call wrenc_b200_code_resident_retry).  Device pointers (d_levels 16-byte aligned); runs on `stream` after the
+ * search; does not synchronise.  Returns kernel launches enqueued (6: non-zero map, syntax, scan, syntax of the long strings,
+ * compaction, arithmetic coder) or <0.
  * Replaces CtuEncoder::encode_coding_tree .. encode_residual + BoolCoder (src/ctu_encoder.rs:227-2269, src/bool_coder.rs:136-296)
  * and the end_of_slice_one_bit / byte alignment of SliceEncoder::encode (src/slice_encoder.rs:380-388,419). */
 int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d_levels, const wrenc_b200_ctu_record *d_records, uint8_t *d_out,

@@ -677,10 +677,14 @@ int wrenc_b200_code_resident(wrenc_b200 *h, int32_t n_pictures, const int16_t *d
         h->err = "wrenc_b200_code_resident must follow wrenc_b200_search_resident of the same pictures on this handle";
         return WRENC_B200_EINVAL;
     }
+    if (reinterpret_cast<uintptr_t>(d_levels) & 15u) {  // the non-zero map kernel reads the level rows with 16-byte loads
+        h->err = "wrenc_b200_code_resident: d_levels must be 16-byte aligned";
+        return WRENC_B200_EINVAL;
+    }
     CK(cudaSetDevice(h->cfg.device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     int rc = enqueue_coder(h, h->rws, n_pictures, d_levels, reinterpret_cast<const CtuRecord *>(d_records), d_out, out_cap, d_out_len, st);
-    return rc ? rc : 5;
+    return rc ? rc : 4 + syntax_first_pass_kernels();
 }
 
 // After a code_resident call whose d_out_len reported -2 (bin arena too small for that batch): grows the arena to the total the
