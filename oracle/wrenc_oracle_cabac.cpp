@@ -4,7 +4,9 @@
 //   BoolCoder arithmetic engine, context init, binarisations, ctxInc derivations                  (bool_coder.rs)
 //   end_of_slice_one_bit + byte alignment of SliceEncoder::encode                                 (slice_encoder.rs:380-388,419)
 // It works on the searched Picture (final levels, records, mode map) and drives the arithmetic coder bin by bin, like the
-// reference.  PARITY UNPINNED: nothing but the source text pins it (no bitstream fixtures, no VTM here).
+// reference.  Pinned by data the reference produced: wrapped in the product's header writers, its output reproduces the sizes of
+// all 16 .vvc files of tools/evaluation/summary.json to the byte (tests/test_reference_pin.py).  The trace hooks at the end of
+// the file hand the bin string and the engine to the tests of the product's arithmetic coder (tests/host/cabac_engine_host_test.cpp).
 #include <algorithm>
 #include <cassert>
 #include <cstdio>

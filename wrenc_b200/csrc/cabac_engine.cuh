@@ -4,8 +4,9 @@
 //
 // The reference keeps a 10-bit `offset`, emits one bit per renormalisation step and counts outstanding bits (put-bit form).  The
 // coded string depends only on the sequence of interval updates, so the same bytes come out of the register form used here:
-//   * `low` is a 32-bit window of the code value, `bits_left` counts the free bits below its top; a renormalisation is ONE shift by
-//     n = clz(range) - 23 bits (no loop), and whole bytes leave the window in write_out() when fewer than 12 bits are free;
+//   * `low` is a window of the code value (64 bits wide: up to 32 bits may be added before bytes have to leave), `bits_left`
+//     counts the free bits below bit 32; a renormalisation is ONE shift by n = clz(range) - 23 bits (no loop), and whole bytes
+//     leave the window in flush() / write_out() until at least 12 bits are free again;
 //   * a carry out of the window is resolved against one buffered byte and a count of 0xff bytes behind it (write_out / finish);
 //   * a run of up to 8 bypass bins is one update  low = (low << k) + range * value  (k single steps are exactly that);
 //   * the probability pair of a context and its two adaptation shifts are ONE 32-bit word
@@ -14,6 +15,9 @@
 // The dropped first bit of the reference (flush_cabac_bin) is the top bit of its 10-bit offset, which is always 0: the register form
 // starts with 9 bits in the window (bits_left = 23) and never holds it.  end_of_slice_one_bit, the two trailing bits with the
 // forced stop bit and the zero padding (bool_coder.rs:218-235, slice_encoder.rs:419) are finish().
+// Three forms of the same coder, each checked on the host: code_batch (all sequential: one load and one store per context-coded
+// bin), run_tokens (every entry packed into one word by its own lane, one branch-free step per word) and the record list of the
+// shipped kernel (TokRec / step_range / step_low: the interval-width side and the code-value side of a step, run by different warps).
 #pragma once
 #include <stdint.h>
 

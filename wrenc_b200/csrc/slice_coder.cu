@@ -1,12 +1,15 @@
 // slice_coder.cu — phase 2 of the hot path: the decided trees are turned into the CABAC-coded slice_data() of each picture on
 // the device (reference src/ctu_encoder.rs:227-2269 syntax order, src/bool_coder.rs:136-296 arithmetic coder).
 //
-// Two kernels, because every context index of the emitted subset depends only on the decisions (levels, modes, tree), never
-// on the arithmetic coder's state:
-//   wrenc_b200_syntax_kernel  one thread per CTU: walks the CTU's coding tree in syntax order and writes the bin string as
-//                             16-bit entries (context index | bin value | bypass flag) into the CTU's slot of the bin arena;
-//   wrenc_b200_cabac_kernel   one thread per picture: initialises the 253 contexts from the slice QP, runs the range coder
-//                             over the CTUs' bin strings in raster order, terminates, byte-aligns.
+// Every context index of the emitted subset depends only on the decisions (levels, modes, tree), never on the arithmetic
+// coder's state, so the stage is a syntax walk that produces bin strings and an arithmetic coder that consumes them:
+//   wrenc_b200_nzmap_kernel        one warp per CTU: map of the CTU's non-zero 4x4 level blocks (coalesced 16-byte loads);
+//   wrenc_b200_syntax_kernel       one thread per CTU: walks the CTU's coding tree in syntax order and writes the bin string as
+//                                  16-bit entries (context index | bin value | bypass flag): counting + staging pass, then a
+//                                  second pass for the CTUs whose string outgrew its staging slot;
+//   wrenc_b200_bin_scan_kernel / wrenc_b200_bin_compact_kernel   arena offsets of the strings, staged strings -> arena;
+//   wrenc_b200_cabac_kernel        three warps per picture (context states / interval widths / code value and bytes) over the
+//                                  CTUs' bin strings in raster order; terminates, byte-aligns.  The engine is cabac_engine.cuh.
 // I-slice subset actually emitted: split_cu_flag; intra_luma_mpm_flag / not_planar / mpm_idx / mpm_remainder;
 // cclm_mode_flag / cclm_mode_idx / intra_chroma_pred_mode(=4); tu_cb/cr/y_coded_flag; cu_qp_delta_abs(=0) once per CTU;
 // transform_skip_flag(=0); residual_coding with dependent quantisation; mts_idx(=0); end_of_slice_one_bit.
