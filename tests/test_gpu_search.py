@@ -315,3 +315,31 @@ def test_bin_arena_grow_and_retry_path():
     env = dict(os.environ, WRENC_B200_ARENA_ENTRIES_PER_CTU="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.startswith("ok"), f"{out.stdout} {out.stderr[-400:]}"
+
+
+@pytest.mark.parametrize("qp", [17, 32, 45])
+def test_slice_coder_string_length_sweep(qp):
+    """The arithmetic coder hands its records over in slots of 8 x 32 bin-string entries and walks them four at a time: 24 two-CTU
+    pictures per QP whose bin strings run from a few dozen to several thousand entries (flat, synthetic, noise blended in at
+    growing amplitude), so that the string lengths fall on many residues of 32 and 256; slice_data byte-identical to the oracle."""
+    W, H = 64, 32
+    rng = np.random.default_rng(1000 + qp)
+    frames = []
+    for i in range(24):
+        y, cb, cr = wrenc_b200.synth_frame(W, H, seed=0xB2000007, frame=i)
+        amp = (0, 0, 1, 2, 3, 5, 8, 12, 20, 32, 48, 64)[i % 12]
+        if amp:
+            y = np.clip(y.astype(np.int32) + rng.integers(-amp, amp + 1, y.shape), 0, 255).astype(np.uint8)
+            if i % 3 == 0:
+                cb = np.clip(cb.astype(np.int32) + rng.integers(-amp, amp + 1, cb.shape), 0, 255).astype(np.uint8)
+        elif i == 0:
+            y, cb, cr = np.full((H, W), 128, np.uint8), np.full((H // 2, W // 2), 128, np.uint8), np.full((H // 2, W // 2), 128, np.uint8)
+        frames.append((np.ascontiguousarray(y), np.ascontiguousarray(cb), np.ascontiguousarray(cr)))
+    ora = Oracle(qp, 3)
+    want = [ora.encode_picture(*f, want_slice_data=True) for f in frames]
+    enc = wrenc_b200.SearchEncoder(W, H, qp=qp, pictures_in_flight=len(frames))
+    res = enc.encode_pictures(frames)
+    enc.close()
+    assert len({len(o["slice_data"]) for o in want}) >= 8  # the sweep really produces different string lengths
+    for i, (o, r) in enumerate(zip(want, res)):
+        assert_same(o, r, f"qp {qp}, picture {i}")
