@@ -253,7 +253,7 @@ static int grow_arena(wrenc_b200 *h, Workspace &w, unsigned long long total) {
 
 // CABAC-code the pictures the last search with this workspace decided (its mode map).  Pass 1 counts the bins of every CTU
 // and stages the short strings, an exclusive scan turns the counts into arena offsets (and leaves the total in d_bin_total),
-// pass 2 writes the long strings, the compaction moves the staged ones, then one warp per picture runs the arithmetic coder.
+// pass 2 writes the long strings, the compaction moves the staged ones, then three warps per picture run the arithmetic coder (states, interval widths, code value).
 // No host synchronisation: the arena is sized from earlier batches; pictures whose strings would not fit report
 // out_len = -2 and the caller grows the arena (d_bin_total) and calls again with first_pass = false.
 static int enqueue_coder(wrenc_b200 *h, Workspace &w, int n_pics, const int16_t *d_lev, const CtuRecord *d_records, uint8_t *d_out, size_t out_cap, int *d_out_len,

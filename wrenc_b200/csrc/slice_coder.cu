@@ -603,7 +603,7 @@ extern "C" __global__ void __launch_bounds__(1024) wrenc_b200_bin_scan_kernel(co
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// arithmetic coder (bool_coder.rs:136-296, 1073-1111) — one warp per picture; the engine itself is cabac_engine.cuh
+// arithmetic coder (bool_coder.rs:136-296, 1073-1111) — the engine itself is cabac_engine.cuh
 // ---------------------------------------------------------------------------------------------------------------
 struct WarpEnv {  // what ce::code_batch needs: the context index of entry i of the batch, context words in shared memory
     unsigned cur;
