@@ -205,6 +205,36 @@ int main(int argc, char **argv) {
         printf("picture qp %d: %zu bins (%ld bypass), %zu bytes\n", qp, bins.size(), nbyp, want.size());
         if (want != got || want != code_tokens(qp, bins) || want != code_records(qp, bins)) { fprintf(stderr, "MISMATCH real picture qp %d\n", qp); g_bad++; }
     }
+    // optional: raw I420 clips (the reference's test clips decoded by tools/decode_assets.py) after the seed count: file W H qp [...],
+    // first frame cropped to multiples of 32: the real bin string of a natural picture through all three forms of the coder
+    for (int a = 2; a + 3 < argc; a += 4) {
+        const int W0 = atoi(argv[a + 1]), H0 = atoi(argv[a + 2]), qp = atoi(argv[a + 3]);
+        const int Wc = W0 / 32 * 32, Hc = H0 / 32 * 32;
+        FILE *f = fopen(argv[a], "rb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", argv[a]); return 2; }
+        std::vector<uint8_t> raw((size_t)W0 * H0 * 3 / 2);
+        if (fread(raw.data(), 1, raw.size(), f) != raw.size()) { fprintf(stderr, "short read %s\n", argv[a]); return 2; }
+        fclose(f);
+        std::vector<uint8_t> y((size_t)Wc * Hc), cb((size_t)Wc * Hc / 4), cr((size_t)Wc * Hc / 4);
+        for (int j = 0; j < Hc; j++) memcpy(&y[(size_t)j * Wc], &raw[(size_t)j * W0], Wc);
+        for (int j = 0; j < Hc / 2; j++) {
+            memcpy(&cb[(size_t)j * (Wc / 2)], &raw[(size_t)W0 * H0 + (size_t)j * (W0 / 2)], Wc / 2);
+            memcpy(&cr[(size_t)j * (Wc / 2)], &raw[(size_t)W0 * H0 * 5 / 4 + (size_t)j * (W0 / 2)], Wc / 2);
+        }
+        wo::Tuning tu;
+        wo::Encoder enc;
+        enc.k.init(qp, tu);
+        enc.max_depth = 3;
+        wo::Picture pic;
+        pic.init(Wc, Hc, y.data(), cb.data(), cr.data());
+        enc.search_picture(pic);
+        std::vector<uint16_t> bins;
+        const std::vector<uint8_t> want = wo::code_slice_data_traced(enc.k, pic, bins);
+        g_checked++;
+        g_bins += (long)bins.size();
+        printf("%s qp %d: %zu bins, %zu bytes\n", argv[a], qp, bins.size(), want.size());
+        if (want != code_fast(qp, bins) || want != code_tokens(qp, bins) || want != code_records(qp, bins)) { fprintf(stderr, "MISMATCH clip %s qp %d\n", argv[a], qp); g_bad++; }
+    }
     printf("%ld strings, %ld bins, %ld mismatches\n", g_checked, g_bins, g_bad);
     return g_bad ? 1 : 0;
 }
